@@ -1,0 +1,442 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring ->
+// tcgen05.mma (single issuing thread, fp32 accumulators in TMEM, double-buffered) ->
+// tcgen05.ld epilogue with the fused element-wise tails the UMD block needs.
+//
+// Covers every dense contraction on the training-step path of the reference
+// (big_vision/models/vit.py:54,57 MLP; :71 adaLN projection; :82-87 q/k/v/out projections;
+//  big_vision/models/ae.py:94-97 final modulation / un-patchify; embeddings.py:56,58 trunks)
+// and their autodiff transposes (dgrad: A K-major x W K-major; wgrad: both MN-major).
+//
+// One CTA per SM, 384 threads:
+//   warp 0 lane 0 : TMA producer           warp 1 lane 0 : MMA issuer
+//   warp 2        : TMEM allocator         warps 4..11   : epilogue (2 warps per TMEM lane quadrant)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace umd {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 384;
+
+struct GemmParams {
+  int M, N, K, batch, split_k;
+  int a_bcast, b_bcast;
+  void* out0;
+  long long ld0, bs0;
+  void* out1;
+  long long ld1;
+  const float* bias;
+  long long bias_bs;
+  const void* aux;
+  long long ldaux;
+  const float* gate;
+  long long ldgate;
+  RowMap rmap;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_tanh(float u) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (u + k1 * u * u * u);
+  return 0.5f * u * (1.f + tanh_fast(inner));
+}
+__device__ __forceinline__ float gelu_tanh_grad(float u) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u2 = u * u;
+  float inner = k0 * (u + k1 * u * u2);
+  float t = tanh_fast(inner);
+  return 0.5f * (1.f + t) + 0.5f * u * (1.f - t * t) * k0 * (1.f + 3.f * k1 * u2);
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int tiles_mn = m_tiles * n_tiles;
+  const long long total_items = static_cast<long long>(tiles_mn) * p.split_k * p.batch;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int tile = static_cast<int>(item % tiles_mn);
+      const int rest = static_cast<int>(item / tiles_mn);
+      const int ks = rest % p.split_k;
+      const int b = rest / p.split_k;
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / p.split_k);
+      const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * kb_total / p.split_k);
+      const int ba = p.a_bcast ? 0 : b;
+      const int bb = p.b_bcast ? 0 : b;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
+        uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
+        const int k0 = kb * BK;
+        if (!A_MN) {
+          tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0, ba);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], m0 + 64 * i, k0, ba);
+        }
+        if (!B_MN) {
+          tma_load_3d(sb, &tmB, &full_bar[stage], k0, n0, bb);
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + 64 * i, k0, bb);
+        }
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+    // per UMMA_K (=16 elements) advance of the descriptor start address, in 16-byte units
+    constexpr uint32_t a_adv = A_MN ? (16 * 128) >> 4 : 32 >> 4;
+    constexpr uint32_t b_adv = B_MN ? (16 * 128) >> 4 : 32 >> 4;
+    constexpr uint32_t lbo = 64 * BK * 2;  // MN-major: next 64-element MN atom
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int rest = static_cast<int>(item / tiles_mn);
+      const int ks = rest % p.split_k;
+      const int kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / p.split_k);
+      const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * kb_total / p.split_k);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc =
+            make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES), A_MN ? lbo : 0, 1024);
+        const uint64_t bdesc =
+            make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES), B_MN ? lbo : 0, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_f16_ss(d_tmem, adesc + k * a_adv, bdesc + k * b_adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;           // which half of the BN columns
+    constexpr int HALF_COLS = BN / 2;
+    int it = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      const int tile = static_cast<int>(item % tiles_mn);
+      const int rest = static_cast<int>(item / tiles_mn);
+      const int b = rest / p.split_k;
+      const int m0 = (tile / n_tiles) * BM;
+      const int n0 = (tile % n_tiles) * BN;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * HALF_COLS;
+      const float* bias = p.bias ? p.bias + static_cast<long long>(b) * p.bias_bs : nullptr;
+      int sample = 0;
+      if (EPI == UMD_EPI_GATE_RES && p.gate && row_ok) sample = sample_of(p.rmap, row);
+
+#pragma unroll 1
+      for (int c = 0; c < HALF_COLS; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + half * HALF_COLS + c;
+        if (row_ok && col0 < p.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const int ncols = min(32, p.N - col0);  // multiple of 8 by contract
+        if (EPI != UMD_EPI_ATOMIC && EPI != UMD_EPI_DGELU && bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) {
+              float4 bv = *reinterpret_cast<const float4*>(bias + col0 + j);
+              v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+            }
+          }
+        }
+        if (EPI == UMD_EPI_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(b) * p.bs0 +
+                             static_cast<long long>(row) * p.ld0 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              uint4 pk = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                    pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+              *reinterpret_cast<uint4*>(o + j) = pk;
+            }
+          }
+        } else if (EPI == UMD_EPI_F32) {
+          float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(b) * p.bs0 +
+                     static_cast<long long>(row) * p.ld0 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else if (EPI == UMD_EPI_GELU) {
+          __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
+          __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(p.out1) + static_cast<long long>(row) * p.ld1 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              uint4 pu = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                    pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+              *reinterpret_cast<uint4*>(o0 + j) = pu;
+              float g[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) g[q] = gelu_tanh(v[j + q]);
+              uint4 pg = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                                    pack_bf16x2(g[6], g[7]));
+              *reinterpret_cast<uint4*>(o1 + j) = pg;
+            }
+          }
+        } else if (EPI == UMD_EPI_GATE_RES) {
+          const float* xin = reinterpret_cast<const float*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0;
+          float* xo = reinterpret_cast<float*>(p.out1) + static_cast<long long>(row) * p.ld1 + col0;
+          const float* gp = p.gate ? p.gate + static_cast<long long>(sample) * p.ldgate + col0 : nullptr;
+          __nv_bfloat16* o0 =
+              p.out0 ? reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              if (o0) {
+                uint4 pa = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                      pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+                *reinterpret_cast<uint4*>(o0 + j) = pa;
+              }
+#pragma unroll
+              for (int q = 0; q < 8; q += 4) {
+                float4 xi = *reinterpret_cast<const float4*>(xin + j + q);
+                float4 gv = gp ? *reinterpret_cast<const float4*>(gp + j + q) : make_float4(1.f, 1.f, 1.f, 1.f);
+                float4 o;
+                o.x = xi.x + gv.x * v[j + q];
+                o.y = xi.y + gv.y * v[j + q + 1];
+                o.z = xi.z + gv.z * v[j + q + 2];
+                o.w = xi.w + gv.w * v[j + q + 3];
+                *reinterpret_cast<float4*>(xo + j + q) = o;
+              }
+            }
+          }
+        } else if (EPI == UMD_EPI_DGELU) {
+          const __nv_bfloat16* up =
+              reinterpret_cast<const __nv_bfloat16*>(p.aux) + static_cast<long long>(row) * p.ldaux + col0;
+          __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(p.out0) + static_cast<long long>(row) * p.ld0 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (j < ncols) {
+              uint4 uu = *reinterpret_cast<const uint4*>(up + j);
+              uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
+              float d[8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                d[2 * q] = v[j + 2 * q] * gelu_tanh_grad(bf16_lo(uw[q]));
+                d[2 * q + 1] = v[j + 2 * q + 1] * gelu_tanh_grad(bf16_hi(uw[q]));
+              }
+              uint4 pd = make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]),
+                                    pack_bf16x2(d[6], d[7]));
+              *reinterpret_cast<uint4*>(o0 + j) = pd;
+            }
+          }
+        } else if (EPI == UMD_EPI_ATOMIC) {
+          float* o = reinterpret_cast<float*>(p.out0) + static_cast<long long>(b) * p.bs0 +
+                     static_cast<long long>(row) * p.ld0 + col0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (j < ncols) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+        }  // row_ok && col0 < N
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------
+extern long long g_launch_count;
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = ceil_div(p.M, BM), n_tiles = ceil_div(p.N, BN);
+  long long items = static_cast<long long>(m_tiles) * n_tiles * p.split_k * p.batch;
+  int grid = static_cast<int>(items < sm_count() ? items : sm_count());
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  ++g_launch_count;
+  UMD_CHECK_CUDA(cudaGetLastError());
+  return UMD_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                           cudaStream_t s) {
+  switch (epi) {
+    case UMD_EPI_BF16: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_BF16>(tmA, tmB, p, s);
+    case UMD_EPI_F32: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_F32>(tmA, tmB, p, s);
+    case UMD_EPI_ATOMIC: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_ATOMIC>(tmA, tmB, p, s);
+    default: break;
+  }
+  if (!A_MN) {
+    // fused activation tails only exist for activations-as-A (forward / dgrad) GEMMs
+    switch (epi) {
+      case UMD_EPI_GELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GELU>(tmA, tmB, p, s);
+      case UMD_EPI_GATE_RES: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GATE_RES>(tmA, tmB, p, s);
+      case UMD_EPI_DGELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_DGELU>(tmA, tmB, p, s);
+      default: break;
+    }
+  }
+  set_error("umd_gemm_bf16: unsupported epilogue %d for this operand layout", epi);
+  return UMD_ERR_UNSUPPORTED;
+}
+
+template <int BN>
+static int launch_gemm_bn(bool a_mn, bool b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && b_mn) return launch_gemm_epi<BN, false, true>(epi, tmA, tmB, p, s);
+  if (!a_mn && !b_mn) return launch_gemm_epi<BN, false, false>(epi, tmA, tmB, p, s);
+  if (a_mn && b_mn) return launch_gemm_epi<BN, true, true>(epi, tmA, tmB, p, s);
+  set_error("umd_gemm_bf16: A MN-major with B K-major is not instantiated");
+  return UMD_ERR_UNSUPPORTED;
+}
+
+int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
+  UMD_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "umd_gemm_bf16: empty problem M=%d N=%d K=%d batch=%d",
+              a.M, a.N, a.K, a.batch);
+  UMD_REQUIRE(a.N % 8 == 0, "umd_gemm_bf16: N=%d must be a multiple of 8", a.N);
+  UMD_REQUIRE(a.lda % 8 == 0 && a.ldb % 8 == 0, "umd_gemm_bf16: lda/ldb must be multiples of 8 elements");
+  UMD_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0,
+              "umd_gemm_bf16: operands must be 16-byte aligned");
+  const int split_k = a.split_k > 1 ? a.split_k : 1;
+  UMD_REQUIRE(split_k == 1 || a.epi == UMD_EPI_ATOMIC, "umd_gemm_bf16: split_k needs UMD_EPI_ATOMIC");
+  const int kb_total = ceil_div(a.K, BK);
+  GemmParams p;
+  p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
+  p.split_k = split_k < kb_total ? split_k : kb_total;
+  p.a_bcast = (a.a_bs == 0); p.b_bcast = (a.b_bs == 0);
+  p.out0 = a.out0; p.ld0 = a.ld0; p.bs0 = a.bs0;
+  p.out1 = a.out1; p.ld1 = a.ld1;
+  p.bias = a.bias; p.bias_bs = a.bias_bs;
+  p.aux = a.aux; p.ldaux = a.ldaux;
+  p.gate = a.gate; p.ldgate = a.ldgate;
+  p.rmap.split_row = a.split_row; p.rmap.s0 = a.s0 > 0 ? a.s0 : 1; p.rmap.s1 = a.s1 > 0 ? a.s1 : 1; p.rmap.n0 = a.n0;
+
+  int bn = 256;
+  if (a.N <= 64) bn = 64;
+  else if (a.N <= 128) bn = 128;
+  else if (a.N % 256 != 0 && a.N % 128 == 0 && a.N < 1024) bn = 128;
+
+  CUtensorMap tmA, tmB;
+  const uint64_t a_batch = p.a_bcast ? 1 : a.batch, b_batch = p.b_bcast ? 1 : a.batch;
+  if (!a.a_mn) UMD_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a_batch, a.lda, a.a_bs, BM));
+  else         UMD_TRY(make_tmap_bf16(&tmA, a.A, a.M, a.K, a_batch, a.lda, a.a_bs, BK));
+  if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, bn));
+  else         UMD_TRY(make_tmap_bf16(&tmB, a.B, a.N, a.K, b_batch, a.ldb, a.b_bs, BK));
+
+  switch (bn) {
+    case 256: return launch_gemm_bn<256>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
+    case 128: return launch_gemm_bn<128>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
+    default: return launch_gemm_bn<64>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
+  }
+}
+
+}  // namespace umd
+
+extern "C" int umd_gemm_bf16(const umd_gemm_args* args, umd_stream_t stream) {
+  if (!args) {
+    umd::set_error("umd_gemm_bf16: null args");
+    return UMD_ERR_INVALID;
+  }
+  return umd::gemm_bf16(*args, static_cast<cudaStream_t>(stream));
+}

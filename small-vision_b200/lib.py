@@ -1,0 +1,97 @@
+"""ctypes binding of libumd_b200.so (the C ABI declared in include/umd_b200.h).
+
+The product path never falls back to PyTorch or to the oracle: if the shared library is
+missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libumd_b200.so")
+
+
+class UmdError(RuntimeError):
+  pass
+
+
+class GemmArgs(C.Structure):
+  _fields_ = [
+      ("A", C.c_void_p), ("B", C.c_void_p),
+      ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
+      ("a_mn", C.c_int), ("b_mn", C.c_int),
+      ("lda", C.c_longlong), ("ldb", C.c_longlong),
+      ("a_bs", C.c_longlong), ("b_bs", C.c_longlong),
+      ("epi", C.c_int), ("split_k", C.c_int),
+      ("out0", C.c_void_p), ("ld0", C.c_longlong), ("bs0", C.c_longlong),
+      ("out1", C.c_void_p), ("ld1", C.c_longlong),
+      ("bias", C.c_void_p), ("bias_bs", C.c_longlong),
+      ("aux", C.c_void_p), ("ldaux", C.c_longlong),
+      ("gate", C.c_void_p), ("ldgate", C.c_longlong),
+      ("split_row", C.c_int), ("s0", C.c_int), ("s1", C.c_int), ("n0", C.c_int),
+  ]
+
+
+EPI_BF16, EPI_F32, EPI_GELU, EPI_GATE_RES, EPI_DGELU, EPI_ATOMIC = range(6)
+
+_lib = None
+
+
+def load():
+  """Loads the shared library once; raises UmdError when it has not been built."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise UmdError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(there is no CPU or PyTorch fallback for the UMD hot path)")
+  lib = C.CDLL(LIB_PATH)
+  lib.umd_last_error.restype = C.c_char_p
+  lib.umd_launch_count.restype = C.c_longlong
+  _lib = lib
+  return lib
+
+
+def check(rc, what=""):
+  if rc != 0:
+    msg = load().umd_last_error().decode("utf-8", "replace")
+    raise UmdError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+  return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def current_stream():
+  import torch
+  return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+  return int(load().umd_launch_count())
+
+
+def gemm(A, B, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, batch=1, a_bs=0, b_bs=0,
+         epi=EPI_BF16, split_k=1, out0=None, ld0=0, bs0=0, out1=None, ld1=0, bias=None, bias_bs=0,
+         aux=None, ldaux=0, gate=None, ldgate=0, rowmap=None):
+  """Thin wrapper over umd_gemm_bf16 for tests and host-side orchestration."""
+  lib = load()
+  a = GemmArgs()
+  a.A, a.B = ptr(A), ptr(B)
+  a.M, a.N, a.K, a.batch = M, N, K, batch
+  a.a_mn, a.b_mn = int(a_mn), int(b_mn)
+  a.lda = lda if lda is not None else (M if a_mn else K)
+  a.ldb = ldb if ldb is not None else (N if b_mn else K)
+  a.a_bs, a.b_bs = a_bs, b_bs
+  a.epi, a.split_k = epi, split_k
+  a.out0, a.ld0, a.bs0 = ptr(out0), ld0 or N, bs0
+  a.out1, a.ld1 = ptr(out1), ld1 or N
+  a.bias, a.bias_bs = ptr(bias), bias_bs
+  a.aux, a.ldaux = ptr(aux), ldaux or N
+  a.gate, a.ldgate = ptr(gate), ldgate
+  if rowmap is None:
+    rowmap = (M, M, 1, 1)
+  a.split_row, a.s0, a.s1, a.n0 = rowmap
+  check(lib.umd_gemm_bf16(C.byref(a), current_stream()), "umd_gemm_bf16")
