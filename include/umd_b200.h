@@ -75,9 +75,126 @@ typedef struct umd_gemm_args {
   long long ldgate;
   /* row -> sample map for the gate (two-segment ragged batch) */
   int split_row, s0, s1, n0;
+  /* b_mn = 0 only: the contraction is split over B's batch axis in chunks of b_kchunk elements (multiple of
+   * 64): B element (n, k) lives at B + (k / b_kchunk) * b_bs + n * ldb + (k % b_kchunk).  0 = off.  Used for
+   * dY0 = [dQ|dK|dV] [Wq|Wk|Wv]^T with the three kernels stored as separate leaves. */
+  int b_kchunk;
 } umd_gemm_args;
 
 int umd_gemm_bf16(const umd_gemm_args* args, umd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone pieces of the path that the reference exposes as functions of their own.
+ * ------------------------------------------------------------------------------------------ */
+/* gaussian_diffusion.py:85-98  q_sample: out = sqrt_ac[t[n]] * x0 + sqrt_1mac[t[n]] * noise (fp32). */
+int umd_qsample(const float* x0, const float* noise, const int* t, const float* sqrt_alphas_cumprod,
+                const float* sqrt_one_minus_alphas_cumprod, int n, int elems_per_sample, float* out,
+                umd_stream_t stream);
+/* models/ae.py:14-16,25-27  stable argsort of the mask noise, its inverse and the 0/1 sequence mask. */
+int umd_mask_argsort(const float* noise, int n, int L, int len_keep, int* ids_shuffle, int* ids_restore,
+                     float* mask_or_null, umd_stream_t stream);
+/* models/vit.py:82-87 attention over a packed qkv buffer [rows, 3*H*Dh] (two-segment ragged batch). */
+int umd_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
+                      umd_stream_t stream);
+int umd_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
+                      void* dqkv_bf16, int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream);
+/* models/vit.py:78-80 LayerNorm (+ adaLN modulate); out bf16 when out_is_bf16 else fp32 */
+int umd_ln_modulate_fwd(const float* x, const float* gamma, const float* beta, const float* shift, const float* scale,
+                        long long ldmod, int n0, int s0, int n1, int s1, int D, void* out, int out_is_bf16, float* mean,
+                        float* rstd, umd_stream_t stream);
+int umd_ln_modulate_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                        const float* gamma, const float* beta, const float* scale, long long ldmod, int n0, int s0,
+                        int n1, int s1, int D, float* dx, int accumulate, float* dshift, float* dscale, long long ldd,
+                        float* dgamma, float* dbeta, umd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser over the flat arena (train_ae.py:124-152,365-374): global-norm clip + AdamW (bf16 mu)
+ * + masked weight decay + optional EMA; also refreshes the bf16 shadow of the parameters.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct umd_adamw_args {
+  float* params;            /* [n] fp32 master */
+  const float* grads;       /* [n] fp32 (already all-reduced) */
+  void* mu;                 /* [n] bf16 */
+  float* nu;                /* [n] fp32 */
+  void* params_bf16;        /* [n] bf16 shadow or NULL */
+  float* ema;               /* [n] fp32 or NULL */
+  const uint8_t* wd_flags;  /* [n/64] 1 = decayed leaf */
+  long long n;              /* multiple of 64 */
+  float clip_norm, lr, b1, b2, eps, wd;
+  float bias_corr1, bias_corr2; /* 1 - b^count_inc */
+  float ema_decay;
+  float* scratch;           /* >= 3080 floats */
+  int scratch_floats;
+  float* measurements;      /* device float[3]: l2_params, l2_updates, grad_norm */
+} umd_adamw_args;
+int umd_adamw_step(const umd_adamw_args* args, umd_stream_t stream);
+int umd_sumsq(const float* x, long long n, float* scratch, int scratch_floats, float* out, umd_stream_t stream);
+/* bf16 shadow of the fp32 arena (n multiple of 4) */
+int umd_cast_f32_to_bf16(const float* x, long long n, void* out_bf16, umd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The model: big_vision/models/ae.py _ViTAE (embed -> encode -> decode) and the loss of
+ * trainers/train_ae.py:323-361, forward and backward, over a flat parameter arena.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct umd_model_cfg {
+  int img_size, patch, channels;
+  int width, depth, dec_depth, heads, mlp_dim;
+  int num_cls;
+  int num_classes;      /* 0 = no label path */
+  int adaln;
+  int flip_final_conv;  /* 1 = flax ConvTranspose(transpose_kernel=False) orientation */
+} umd_model_cfg;
+
+/* Leaves of the parameter tree.  offsets[] are element offsets into the arena
+ * (params / grads / bf16 shadow share one layout); -1 marks an absent leaf.  Stacked block leaves keep
+ * the Flax [depth, ...] layout. */
+enum {
+  UMD_P_CLS = 0, UMD_P_POS, UMD_P_DEC_POS, UMD_P_MASK_TOKEN, UMD_P_EMBED_W, UMD_P_EMBED_B,
+  UMD_P_TT_W0, UMD_P_TT_B0, UMD_P_TT_W1, UMD_P_TT_B1,
+  UMD_P_LABEL_TABLE, UMD_P_LT_W0, UMD_P_LT_B0, UMD_P_LT_W1, UMD_P_LT_B1,
+  UMD_P_FMOD_W, UMD_P_FMOD_B, UMD_P_FCONV_W, UMD_P_FCONV_B,
+  UMD_P_ENC_BASE,                       /* + UMD_S_* */
+  UMD_P_DEC_BASE = UMD_P_ENC_BASE + 20, /* + UMD_S_* */
+  UMD_P_COUNT = UMD_P_DEC_BASE + 20
+};
+enum {
+  UMD_S_ADA_W = 0, UMD_S_ADA_B, UMD_S_LN0_S, UMD_S_LN0_B, UMD_S_LN1_S, UMD_S_LN1_B,
+  UMD_S_Q_W, UMD_S_K_W, UMD_S_V_W, UMD_S_Q_B, UMD_S_K_B, UMD_S_V_B, UMD_S_O_W, UMD_S_O_B,
+  UMD_S_FC1_W, UMD_S_FC1_B, UMD_S_FC2_W, UMD_S_FC2_B, UMD_S_NORM_S, UMD_S_NORM_B
+};
+
+typedef struct umd_step_shape {
+  int n0, n1;           /* samples in the noise segment / the clean (MAE) segment */
+  int keep0, keep1;     /* kept patches per sample (L when the segment is not masked) */
+  int masked0, masked1; /* 1 = random masking applies to the segment */
+} umd_step_shape;
+
+typedef struct umd_io {
+  const float* image;       /* [n, H, W, C] model input (x_t for segment 0, x_0 for segment 1) */
+  const int* t;             /* [n] timestep as the model sees it (t+1, or 0) */
+  const int* labels;        /* [n] class ids after label-dropout / null substitution, or NULL */
+  const int* ids_shuffle;   /* [n, L] */
+  const int* ids_restore;   /* [n, L] */
+  const float* x0;          /* [n, H, W, C] loss target, or NULL (no loss) */
+  const float* noise;       /* [n0, H, W, C] loss target of the eps half */
+  float* pred;              /* [n, H, W, 2C] or NULL */
+  float* pre_logits;        /* [n, D] or NULL */
+  float* loss;              /* device scalar or NULL */
+} umd_io;
+
+typedef void (*umd_bucket_cb)(void* user, int bucket);
+
+size_t umd_workspace_bytes(const umd_model_cfg* cfg, const umd_step_shape* shape, int train);
+/* Forward.  train != 0 keeps every activation the backward needs in the workspace. */
+int umd_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const float* params,
+                const void* params_bf16, const umd_io* io, void* workspace, size_t workspace_bytes, int train,
+                umd_stream_t stream);
+/* Backward of the loss computed by the preceding umd_forward(train=1) on the same workspace; accumulates
+ * into grads (which the caller zeroes).  cb(user, k) is called on the host as soon as every kernel writing
+ * gradient bucket k (0 decoder side, 1 encoder, 2 embeddings/conditioning) has been enqueued. */
+int umd_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const float* params,
+                 const void* params_bf16, float* grads, const umd_io* io, void* workspace, size_t workspace_bytes,
+                 umd_bucket_cb cb, void* cb_user, umd_stream_t stream);
 
 #ifdef __cplusplus
 }

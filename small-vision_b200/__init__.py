@@ -7,3 +7,20 @@ Public surface mirrors the reference's Python seams:
   infer_sharding                    big_vision/sharding.py:33-55
 """
 __version__ = "0.1.0"
+
+from .config import ModelConfig, TrainConfig, decode_variant, make_model_config  # noqa: E402,F401
+from .sharding import infer_sharding, Mesh, PartitionSpec  # noqa: E402,F401
+
+
+def __getattr__(name):
+  # torch / CUDA dependent pieces are imported lazily so that host-only tooling can import the package
+  if name in ("Model", "ViTAE", "mask_argsort"):
+    from . import model as _m
+    return getattr(_m, name)
+  if name in ("create_gaussian_diffusion", "q_sample", "get_beta_schedule"):
+    from . import diffusion as _d
+    return getattr(_d, name)
+  if name in ("make_update_fn", "create_train_state"):
+    from . import train as _t
+    return getattr(_t, name)
+  raise AttributeError(name)

@@ -1,6 +1,7 @@
 // Shared host/device helpers for the UMD hot-path library.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

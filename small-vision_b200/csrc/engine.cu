@@ -1,0 +1,653 @@
+// Step engine: host-side orchestration of the UMD auto-encoder forward and backward over a flat
+// parameter arena and a caller-supplied workspace.  Follows big_vision/models/ae.py:99-197
+// (embed -> encode -> decode), big_vision/models/vit.py:60-163 (blocks) and the loss of
+// big_vision/trainers/train_ae.py:323-361; backward per SURVEY.md App. E.  Nothing here allocates or
+// synchronises; every kernel goes to the caller's stream.
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace umd {
+
+namespace {
+
+struct Bump {
+  uint8_t* base;
+  size_t off;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)), off(0) {}
+  template <typename T>
+  T* take(long long count) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += static_cast<size_t>(count < 0 ? 0 : count) * sizeof(T);
+    return p;
+  }
+};
+
+typedef __nv_bfloat16 bf16;
+
+struct LayerBufs {
+  bf16* y0; float* mean0; float* rstd0;
+  bf16* qkv; bf16* o; float* lse; bf16* a;
+  float* xmid;
+  bf16* y1; float* mean1; float* rstd1;
+  bf16* u; bf16* g; bf16* z;
+};
+
+struct Stack {
+  int depth, rows, nsamples;
+  RowMap rm;
+  int base;                 // leaf id base (UMD_P_ENC_BASE / UMD_P_DEC_BASE)
+  float* ada;               // [B, depth*6D] fp32 or null
+  float* dada;              // [B, depth*6D] fp32 gradient
+  bf16* dada_bf16;
+  std::vector<float*> x;    // depth+1 residual snapshots
+  std::vector<LayerBufs> L;
+  float* xf; float* meanf; float* rstdf;   // final LayerNorm (encoder: fp32 output; decoder: see Plan.xm)
+};
+
+struct Plan {
+  // geometry
+  int B, D, H, Dh, M4, L, p, C, NC, tok0, S0, S1, Sd, Te, Td, ncls;
+  int adaln, has_label;
+  // conditioning path
+  bf16* temb; float* th1; bf16* ta1; float* tc;
+  bf16* lemb; float* lh1; bf16* la1; float* yc;
+  float* s; float* cond; bf16* cond_bf16;
+  float* fmod; float* dfmod; bf16* dfmod_bf16;
+  Stack enc, dec;
+  // decoder tail
+  bf16* xm; float* meanF; float* rstdF;
+  bf16* Wf_mat; float* biasm; float* predp; bf16* dpredp; float* loss_partials; int n_loss_partials;
+  // backward scratch
+  float* dx_dec; float* dx_enc; float* dxf_enc;
+  bf16* dzb; bf16* dgb; bf16* dyb; bf16* dqkv;
+  float* dcond; bf16* ds; bf16* dta1; bf16* dth1; bf16* dla1; bf16* dlh1; float* dlemb;
+  float* dWf_mat; float* dbiasm;
+  size_t bytes;
+};
+
+int g_sm = 0;
+
+void carve_stack(Bump& b, Stack& s, const Plan& P, int depth, int rows, int nsamples, const RowMap& rm, int base,
+                 bool train) {
+  s.depth = depth; s.rows = rows; s.nsamples = nsamples; s.rm = rm; s.base = base;
+  const int D = P.D;
+  s.ada = P.adaln ? b.take<float>(static_cast<long long>(P.B) * depth * 6 * D) : nullptr;
+  s.dada = (P.adaln && train) ? b.take<float>(static_cast<long long>(P.B) * depth * 6 * D) : nullptr;
+  s.dada_bf16 = (P.adaln && train) ? b.take<bf16>(static_cast<long long>(P.B) * depth * 6 * D) : nullptr;
+  s.x.assign(depth + 1, nullptr);
+  s.L.assign(depth, LayerBufs());
+  const long long RD = static_cast<long long>(rows) * D;
+  if (train) {
+    for (int l = 0; l <= depth; ++l) s.x[l] = b.take<float>(RD);
+  } else {
+    float* x = b.take<float>(RD);
+    for (int l = 0; l <= depth; ++l) s.x[l] = x;  // GATE_RES epilogue is element-wise in place
+  }
+  for (int l = 0; l < depth; ++l) {
+    LayerBufs& lb = s.L[l];
+    if (train || l == 0) {
+      lb.y0 = b.take<bf16>(RD); lb.mean0 = b.take<float>(rows); lb.rstd0 = b.take<float>(rows);
+      lb.qkv = b.take<bf16>(3 * RD); lb.o = b.take<bf16>(RD);
+      lb.lse = b.take<float>(static_cast<long long>(rows) * P.H);
+      lb.a = b.take<bf16>(RD);
+      lb.xmid = train ? b.take<float>(RD) : s.x[0];
+      lb.y1 = b.take<bf16>(RD); lb.mean1 = b.take<float>(rows); lb.rstd1 = b.take<float>(rows);
+      lb.u = b.take<bf16>(static_cast<long long>(rows) * P.M4);
+      lb.g = b.take<bf16>(static_cast<long long>(rows) * P.M4);
+      lb.z = b.take<bf16>(RD);
+    } else {
+      lb = s.L[0];
+    }
+  }
+}
+
+int make_plan(Plan& P, const umd_model_cfg& c, const umd_step_shape& sh, void* ws, bool train) {
+  UMD_REQUIRE(c.width % 128 == 0 && c.width <= 1024, "width %d must be a multiple of 128 and <= 1024", c.width);
+  UMD_REQUIRE(c.width % c.heads == 0 && c.width / c.heads == 64, "head dim must be 64 (width %d, heads %d)", c.width, c.heads);
+  UMD_REQUIRE(c.img_size % c.patch == 0, "img_size %d not divisible by patch %d", c.img_size, c.patch);
+  UMD_REQUIRE(sh.n0 >= 0 && sh.n1 >= 0 && sh.n0 + sh.n1 > 0, "empty batch");
+  P.B = sh.n0 + sh.n1; P.D = c.width; P.H = c.heads; P.Dh = c.width / c.heads;
+  P.M4 = c.mlp_dim > 0 ? c.mlp_dim : 4 * c.width;
+  P.L = (c.img_size / c.patch) * (c.img_size / c.patch); P.p = c.patch; P.C = c.channels;
+  P.NC = c.patch * c.patch * 2 * c.channels;
+  UMD_REQUIRE(P.NC % 8 == 0, "patch*patch*2*channels = %d must be a multiple of 8", P.NC);
+  UMD_REQUIRE(P.M4 % 64 == 0, "mlp_dim %d must be a multiple of 64", P.M4);
+  P.adaln = c.adaln; P.has_label = c.num_classes > 0; P.ncls = c.num_cls;
+  P.tok0 = c.adaln ? 0 : 1;
+  UMD_REQUIRE(sh.keep0 <= P.L && sh.keep1 <= P.L && (sh.n0 == 0 || sh.keep0 > 0) && (sh.n1 == 0 || sh.keep1 > 0), "bad keep counts");
+  UMD_REQUIRE(sh.masked0 || sh.n0 == 0 || sh.keep0 == P.L, "unmasked segment 0 must keep all %d patches", P.L);
+  UMD_REQUIRE(sh.masked1 || sh.n1 == 0 || sh.keep1 == P.L, "unmasked segment 1 must keep all %d patches", P.L);
+  P.S0 = P.tok0 + c.num_cls + sh.keep0; P.S1 = P.tok0 + c.num_cls + sh.keep1;
+  P.Sd = P.tok0 + 1 + P.L;
+  P.Te = sh.n0 * P.S0 + sh.n1 * P.S1; P.Td = P.B * P.Sd;
+  const int B = P.B, D = P.D;
+  Bump b(ws);
+  P.temb = b.take<bf16>(static_cast<long long>(B) * D); P.th1 = b.take<float>(static_cast<long long>(B) * 2 * D);
+  P.ta1 = b.take<bf16>(static_cast<long long>(B) * 2 * D); P.tc = b.take<float>(static_cast<long long>(B) * D);
+  if (P.has_label) {
+    P.lemb = b.take<bf16>(static_cast<long long>(B) * D); P.lh1 = b.take<float>(static_cast<long long>(B) * 2 * D);
+    P.la1 = b.take<bf16>(static_cast<long long>(B) * 2 * D); P.yc = b.take<float>(static_cast<long long>(B) * D);
+  } else {
+    P.lemb = nullptr; P.lh1 = nullptr; P.la1 = nullptr; P.yc = nullptr;
+  }
+  P.s = b.take<float>(static_cast<long long>(B) * D); P.cond = b.take<float>(static_cast<long long>(B) * D);
+  P.cond_bf16 = b.take<bf16>(static_cast<long long>(B) * D);
+  P.fmod = P.adaln ? b.take<float>(static_cast<long long>(B) * 2 * D) : nullptr;
+  P.dfmod = (P.adaln && train) ? b.take<float>(static_cast<long long>(B) * 2 * D) : nullptr;
+  P.dfmod_bf16 = (P.adaln && train) ? b.take<bf16>(static_cast<long long>(B) * 2 * D) : nullptr;
+  carve_stack(b, P.enc, P, c.depth, P.Te, B, ragged_rowmap(sh.n0, P.S0, sh.n1, P.S1), UMD_P_ENC_BASE, train);
+  P.enc.xf = b.take<float>(static_cast<long long>(P.Te) * D);
+  P.enc.meanf = b.take<float>(P.Te); P.enc.rstdf = b.take<float>(P.Te);
+  carve_stack(b, P.dec, P, c.dec_depth, P.Td, B, uniform_rowmap(B, P.Sd), UMD_P_DEC_BASE, train);
+  P.dec.xf = nullptr; P.dec.meanf = nullptr; P.dec.rstdf = nullptr;
+  const long long BL = static_cast<long long>(B) * P.L;
+  P.xm = b.take<bf16>(BL * D); P.meanF = b.take<float>(BL); P.rstdF = b.take<float>(BL);
+  P.Wf_mat = b.take<bf16>(static_cast<long long>(D) * P.NC); P.biasm = b.take<float>(P.NC);
+  P.predp = b.take<float>(BL * P.NC);
+  P.dpredp = train ? b.take<bf16>(BL * P.NC) : nullptr;
+  P.n_loss_partials = static_cast<int>(ceil_div_ll(BL * P.p * P.p, 256));
+  P.loss_partials = b.take<float>(P.n_loss_partials);
+  if (train) {
+    const long long Tmax = P.Te > P.Td ? P.Te : P.Td;
+    P.dx_dec = b.take<float>(static_cast<long long>(P.Td) * D);
+    P.dx_enc = b.take<float>(static_cast<long long>(P.Te) * D);
+    P.dxf_enc = b.take<float>(static_cast<long long>(P.Te) * D);
+    P.dzb = b.take<bf16>(Tmax * D); P.dgb = b.take<bf16>(Tmax * P.M4); P.dyb = b.take<bf16>(Tmax * D);
+    P.dqkv = b.take<bf16>(Tmax * 3 * D);
+    P.dcond = b.take<float>(static_cast<long long>(B) * D); P.ds = b.take<bf16>(static_cast<long long>(B) * D);
+    P.dta1 = b.take<bf16>(static_cast<long long>(B) * 2 * D); P.dth1 = b.take<bf16>(static_cast<long long>(B) * 2 * D);
+    P.dla1 = P.has_label ? b.take<bf16>(static_cast<long long>(B) * 2 * D) : nullptr;
+    P.dlh1 = P.has_label ? b.take<bf16>(static_cast<long long>(B) * 2 * D) : nullptr;
+    P.dlemb = P.has_label ? b.take<float>(static_cast<long long>(B) * D) : nullptr;
+    P.dWf_mat = b.take<float>(static_cast<long long>(D) * P.NC); P.dbiasm = b.take<float>(P.NC);
+  }
+  P.bytes = (b.off + 255) & ~size_t(255);
+  return UMD_OK;
+}
+
+struct Ctx {
+  const umd_model_cfg* cfg;
+  const umd_step_shape* sh;
+  const long long* offs;
+  const float* pf;
+  const bf16* pb;
+  float* grads;
+  cudaStream_t st;
+  Plan P;
+  const float* W(int leaf, long long extra = 0) const { return pf + offs[leaf] + extra; }
+  const bf16* WB(int leaf, long long extra = 0) const { return pb + offs[leaf] + extra; }
+  float* G(int leaf, long long extra = 0) const { return grads + offs[leaf] + extra; }
+  bool has(int leaf) const { return offs[leaf] >= 0; }
+};
+
+umd_gemm_args gemm_base(const void* A, const void* B, int M, int N, int K) {
+  umd_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.A = A; g.B = B; g.M = M; g.N = N; g.K = K; g.batch = 1;
+  g.split_k = 1;
+  g.split_row = M; g.s0 = M > 0 ? M : 1; g.s1 = 1; g.n0 = 1;
+  return g;
+}
+void set_rowmap(umd_gemm_args& g, const RowMap& rm) {
+  g.split_row = rm.split_row; g.s0 = rm.s0; g.s1 = rm.s1; g.n0 = rm.n0;
+}
+int pick_split(int M, int N, int K, int batch) {
+  const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const long long tiles = static_cast<long long>(ceil_div(M, 128)) * ceil_div(N, bn) * batch;
+  if (g_sm == 0) g_sm = sm_count();
+  long long want = (2LL * g_sm + tiles - 1) / tiles;
+  const int kb = ceil_div(K, 64);
+  long long cap = kb / 4 > 0 ? kb / 4 : 1;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return static_cast<int>(want);
+}
+
+// Y[M,N] = X[M,K] W[K,N] (+bias) : forward Dense with the Flax [in,out] kernel as an MN-major B operand.
+int dense_fwd(const Ctx& c, const bf16* X, int M, int K, const bf16* Wk, int N, const float* bias, int epi, void* out0,
+              void* out1 = nullptr, const void* aux = nullptr, const float* gate = nullptr, long long ldgate = 0,
+              const RowMap* rm = nullptr) {
+  umd_gemm_args g = gemm_base(X, Wk, M, N, K);
+  g.a_mn = 0; g.b_mn = 1; g.lda = K; g.ldb = N;
+  g.epi = epi; g.out0 = out0; g.ld0 = N; g.out1 = out1; g.ld1 = N; g.bias = bias;
+  g.aux = aux; g.ldaux = N; g.gate = gate; g.ldgate = ldgate;
+  if (rm) set_rowmap(g, *rm);
+  return gemm_bf16(g, c.st);
+}
+// dX[M,K] = dY[M,N] W[K,N]^T : W in its native layout is a K-major B operand with N_gemm = K, K_gemm = N.
+int dense_dgrad(const Ctx& c, const bf16* dY, int M, int N, const bf16* Wk, int K, int epi, void* out0,
+                const void* aux = nullptr) {
+  umd_gemm_args g = gemm_base(dY, Wk, M, K, N);
+  g.a_mn = 0; g.b_mn = 0; g.lda = N; g.ldb = N;
+  g.epi = epi; g.out0 = out0; g.ld0 = K; g.aux = aux; g.ldaux = K;
+  return gemm_bf16(g, c.st);
+}
+// dW[K,N] += X[M,K]^T dY[M,N]
+int dense_wgrad(const Ctx& c, const bf16* X, int M, int K, const bf16* dY, int N, long long lddy, float* dW) {
+  umd_gemm_args g = gemm_base(X, dY, K, N, M);
+  g.a_mn = 1; g.b_mn = 1; g.lda = K; g.ldb = lddy;
+  g.epi = UMD_EPI_ATOMIC; g.out0 = dW; g.ld0 = N;
+  g.split_k = pick_split(K, N, M, 1);
+  return gemm_bf16(g, c.st);
+}
+
+// ------------------------------------------------------------------------------------------
+// conditioning (ae.py:105-124; embeddings.py)
+// ------------------------------------------------------------------------------------------
+int cond_forward(Ctx& c, const umd_io& io) {
+  Plan& P = c.P;
+  const int B = P.B, D = P.D;
+  UMD_TRY(time_embed(io.t, B, D, P.temb, c.st));
+  UMD_TRY(dense_fwd(c, P.temb, B, D, c.WB(UMD_P_TT_W0), 2 * D, c.W(UMD_P_TT_B0), UMD_EPI_F32, P.th1));
+  UMD_TRY(silu_cast(P.th1, static_cast<long long>(B) * 2 * D, P.ta1, c.st));
+  UMD_TRY(dense_fwd(c, P.ta1, B, 2 * D, c.WB(UMD_P_TT_W1), D, c.W(UMD_P_TT_B1), UMD_EPI_F32, P.tc));
+  if (P.has_label) {
+    UMD_REQUIRE(io.labels != nullptr, "labels are required when num_classes > 0 (pass the null class id for y=None)");
+    UMD_TRY(gather_rows(c.W(UMD_P_LABEL_TABLE), io.labels, B, D, P.lemb, c.st));
+    UMD_TRY(dense_fwd(c, P.lemb, B, D, c.WB(UMD_P_LT_W0), 2 * D, c.W(UMD_P_LT_B0), UMD_EPI_F32, P.lh1));
+    UMD_TRY(silu_cast(P.lh1, static_cast<long long>(B) * 2 * D, P.la1, c.st));
+    UMD_TRY(dense_fwd(c, P.la1, B, 2 * D, c.WB(UMD_P_LT_W1), D, c.W(UMD_P_LT_B1), UMD_EPI_F32, P.yc));
+  }
+  UMD_TRY(cond_combine(P.tc, P.yc, static_cast<long long>(B) * D, P.adaln, P.s, P.cond, P.cond_bf16, c.st));
+  if (P.adaln) {
+    // adaLN projections of every block in one batched GEMM per stack (vit.py:71-72), final modulation ae.py:167
+    Stack* stacks[2] = {&P.enc, &P.dec};
+    for (Stack* s : stacks) {
+      umd_gemm_args g = gemm_base(P.cond_bf16, c.WB(s->base + UMD_S_ADA_W), B, 6 * D, D);
+      g.b_mn = 1; g.lda = D; g.ldb = 6 * D; g.batch = s->depth; g.a_bs = 0; g.b_bs = static_cast<long long>(D) * 6 * D;
+      g.epi = UMD_EPI_F32; g.out0 = s->ada; g.ld0 = static_cast<long long>(s->depth) * 6 * D; g.bs0 = 6 * D;
+      g.bias = c.W(s->base + UMD_S_ADA_B); g.bias_bs = 6 * D;
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
+    UMD_TRY(dense_fwd(c, P.cond_bf16, B, D, c.WB(UMD_P_FMOD_W), 2 * D, c.W(UMD_P_FMOD_B), UMD_EPI_F32, P.fmod));
+  }
+  return UMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Encoder1DBlock stack forward (vit.py:60-163)
+// ------------------------------------------------------------------------------------------
+int stack_forward(Ctx& c, Stack& s) {
+  Plan& P = c.P;
+  const int D = P.D, T = s.rows, M4 = P.M4;
+  const long long ldada = static_cast<long long>(s.depth) * 6 * D;
+  const long long qkv_sp = c.offs[s.base + UMD_S_K_W] - c.offs[s.base + UMD_S_Q_W];
+  const long long qkvb_sp = c.offs[s.base + UMD_S_K_B] - c.offs[s.base + UMD_S_Q_B];
+  UMD_REQUIRE(c.offs[s.base + UMD_S_V_W] - c.offs[s.base + UMD_S_K_W] == qkv_sp &&
+                  c.offs[s.base + UMD_S_V_B] - c.offs[s.base + UMD_S_K_B] == qkvb_sp && qkv_sp > 0 && qkvb_sp > 0,
+              "query/key/value leaves must be equally spaced in the arena");
+  for (int l = 0; l < s.depth; ++l) {
+    LayerBufs& lb = s.L[l];
+    const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
+    if (!P.adaln) UMD_TRY(set_cond_row(s.x[l], P.cond, s.rm, s.nsamples, D, c.st));
+    LnFwdArgs ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = s.x[l]; ln.gamma = c.W(s.base + UMD_S_LN0_S, static_cast<long long>(l) * D);
+    ln.beta = c.W(s.base + UMD_S_LN0_B, static_cast<long long>(l) * D);
+    ln.shift = ada; ln.scale = ada ? ada + D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
+    ln.out = lb.y0; ln.mean = lb.mean0; ln.rstd = lb.rstd0; ln.rows_out = T;
+    UMD_TRY(ln_mod_fwd(ln, D, true, c.st));
+    {  // q, k, v projections as one batch-3 GEMM into the packed [T, 3D] buffer
+      umd_gemm_args g = gemm_base(lb.y0, c.WB(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D), T, D, D);
+      g.b_mn = 1; g.lda = D; g.ldb = D; g.batch = 3; g.a_bs = 0; g.b_bs = qkv_sp;
+      g.epi = UMD_EPI_BF16; g.out0 = lb.qkv; g.ld0 = 3 * D; g.bs0 = D;
+      g.bias = c.W(s.base + UMD_S_Q_B, static_cast<long long>(l) * D); g.bias_bs = qkvb_sp;
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
+    AttnArgs at;
+    at.qkv = lb.qkv; at.out = lb.o; at.lse = lb.lse; at.rm = s.rm; at.nsamples = s.nsamples; at.H = P.H; at.Dh = P.Dh;
+    at.scale = 1.0f / sqrtf(static_cast<float>(P.Dh));
+    UMD_TRY(attention_fwd(at, c.st));
+    UMD_TRY(dense_fwd(c, lb.o, T, D, c.WB(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D), D,
+                      c.W(s.base + UMD_S_O_B, static_cast<long long>(l) * D), UMD_EPI_GATE_RES, lb.a, lb.xmid, s.x[l],
+                      ada ? ada + 2 * D : nullptr, ldada, &s.rm));
+    ln.x = lb.xmid; ln.gamma = c.W(s.base + UMD_S_LN1_S, static_cast<long long>(l) * D);
+    ln.beta = c.W(s.base + UMD_S_LN1_B, static_cast<long long>(l) * D);
+    ln.shift = ada ? ada + 3 * D : nullptr; ln.scale = ada ? ada + 4 * D : nullptr;
+    ln.out = lb.y1; ln.mean = lb.mean1; ln.rstd = lb.rstd1;
+    UMD_TRY(ln_mod_fwd(ln, D, true, c.st));
+    UMD_TRY(dense_fwd(c, lb.y1, T, D, c.WB(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4), M4,
+                      c.W(s.base + UMD_S_FC1_B, static_cast<long long>(l) * M4), UMD_EPI_GELU, lb.u, lb.g));
+    UMD_TRY(dense_fwd(c, lb.g, T, M4, c.WB(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D), D,
+                      c.W(s.base + UMD_S_FC2_B, static_cast<long long>(l) * D), UMD_EPI_GATE_RES, lb.z, s.x[l + 1], lb.xmid,
+                      ada ? ada + 5 * D : nullptr, ldada, &s.rm));
+  }
+  return UMD_OK;
+}
+
+// Backward of the stack; dx holds d x[depth] on entry and d x[0] on exit (App. E steps 1-10).
+int stack_backward(Ctx& c, Stack& s, float* dx) {
+  Plan& P = c.P;
+  const int D = P.D, T = s.rows, M4 = P.M4;
+  const long long ldada = static_cast<long long>(s.depth) * 6 * D;
+  const long long qkv_sp = c.offs[s.base + UMD_S_K_W] - c.offs[s.base + UMD_S_Q_W];
+  const long long qkvb_sp = c.offs[s.base + UMD_S_K_B] - c.offs[s.base + UMD_S_Q_B];
+  for (int l = s.depth - 1; l >= 0; --l) {
+    LayerBufs& lb = s.L[l];
+    const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
+    float* dada = s.dada ? s.dada + static_cast<long long>(l) * 6 * D : nullptr;
+    const long long lD = static_cast<long long>(l) * D;
+    // ---- MLP branch
+    GateBwdArgs gb;
+    gb.dx = dx; gb.z = lb.z; gb.gate = ada ? ada + 5 * D : nullptr; gb.ldgate = ldada; gb.rm = s.rm; gb.dz = P.dzb;
+    gb.dgate = dada ? dada + 5 * D : nullptr; gb.lddgate = ldada; gb.dbias = c.G(s.base + UMD_S_FC2_B, lD);
+    UMD_TRY(gate_bwd(gb, D, s.nsamples, c.st));
+    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D), M4, UMD_EPI_DGELU,
+                        P.dgb, lb.u));
+    UMD_TRY(dense_wgrad(c, lb.g, T, M4, P.dzb, D, D, c.G(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D)));
+    UMD_TRY(colsum_bf16(P.dgb, M4, T, M4, c.G(s.base + UMD_S_FC1_B, static_cast<long long>(l) * M4), c.st));
+    UMD_TRY(dense_dgrad(c, P.dgb, T, M4, c.WB(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4), D, UMD_EPI_BF16,
+                        P.dyb));
+    UMD_TRY(dense_wgrad(c, lb.y1, T, D, P.dgb, M4, M4, c.G(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4)));
+    LnBwdArgs lnb;
+    memset(&lnb, 0, sizeof(lnb));
+    lnb.dy = P.dyb; lnb.x = lb.xmid; lnb.mean = lb.mean1; lnb.rstd = lb.rstd1;
+    lnb.gamma = c.W(s.base + UMD_S_LN1_S, lD); lnb.beta = c.W(s.base + UMD_S_LN1_B, lD);
+    lnb.scale = ada ? ada + 4 * D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
+    lnb.dshift = dada ? dada + 3 * D : nullptr; lnb.dscale = dada ? dada + 4 * D : nullptr; lnb.ldd = ldada;
+    lnb.dgamma = c.G(s.base + UMD_S_LN1_S, lD); lnb.dbeta = c.G(s.base + UMD_S_LN1_B, lD);
+    UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
+    // ---- attention branch
+    gb.z = lb.a; gb.gate = ada ? ada + 2 * D : nullptr; gb.dgate = dada ? dada + 2 * D : nullptr;
+    gb.dbias = c.G(s.base + UMD_S_O_B, lD);
+    UMD_TRY(gate_bwd(gb, D, s.nsamples, c.st));
+    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D), D, UMD_EPI_BF16, P.dyb));
+    UMD_TRY(dense_wgrad(c, lb.o, T, D, P.dzb, D, D, c.G(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D)));
+    AttnBwdArgs ab;
+    ab.qkv = lb.qkv; ab.out = lb.o; ab.dout = P.dyb; ab.lse = lb.lse; ab.dqkv = P.dqkv; ab.rm = s.rm;
+    ab.nsamples = s.nsamples; ab.H = P.H; ab.Dh = P.Dh; ab.scale = 1.0f / sqrtf(static_cast<float>(P.Dh));
+    UMD_TRY(attention_bwd(ab, c.st));
+    {  // dWq, dWk, dWv as one batch-3 wgrad GEMM
+      umd_gemm_args g = gemm_base(lb.y0, P.dqkv, D, D, T);
+      g.a_mn = 1; g.b_mn = 1; g.lda = D; g.ldb = 3 * D; g.batch = 3; g.a_bs = 0; g.b_bs = D;
+      g.epi = UMD_EPI_ATOMIC; g.out0 = c.G(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D); g.ld0 = D; g.bs0 = qkv_sp;
+      g.split_k = pick_split(D, D, T, 3);
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
+    for (int j = 0; j < 3; ++j)
+      UMD_TRY(colsum_bf16(P.dqkv + j * D, 3 * D, T, D, c.G(s.base + UMD_S_Q_B, lD + j * qkvb_sp), c.st));
+    {  // dY0 = [dQ|dK|dV] [Wq|Wk|Wv]^T, contraction chunked over the three kernels
+      umd_gemm_args g = gemm_base(P.dqkv, c.WB(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D), T, D, 3 * D);
+      g.a_mn = 0; g.b_mn = 0; g.lda = 3 * D; g.ldb = D; g.b_bs = qkv_sp; g.b_kchunk = D;
+      g.epi = UMD_EPI_BF16; g.out0 = P.dyb; g.ld0 = D;
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
+    lnb.dy = P.dyb; lnb.x = s.x[l]; lnb.mean = lb.mean0; lnb.rstd = lb.rstd0;
+    lnb.gamma = c.W(s.base + UMD_S_LN0_S, lD); lnb.beta = c.W(s.base + UMD_S_LN0_B, lD);
+    lnb.scale = ada ? ada + D : nullptr;
+    lnb.dshift = dada ? dada : nullptr; lnb.dscale = dada ? dada + D : nullptr;
+    lnb.dgamma = c.G(s.base + UMD_S_LN0_S, lD); lnb.dbeta = c.G(s.base + UMD_S_LN0_B, lD);
+    UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
+    if (!P.adaln) UMD_TRY(cond_row_bwd(dx, P.dcond, s.rm, s.nsamples, D, c.st));
+  }
+  if (P.adaln) {
+    // adaLN projection backward, all blocks of the stack at once (App. E step 10)
+    const int B = P.B;
+    const long long n = static_cast<long long>(B) * s.depth * 6 * D;
+    UMD_TRY(cast_bf16(s.dada, n, s.dada_bf16, c.st));
+    UMD_TRY(colsum_f32(s.dada, ldada, B, s.depth * 6 * D, c.G(s.base + UMD_S_ADA_B), c.st));
+    {
+      umd_gemm_args g = gemm_base(P.cond_bf16, s.dada_bf16, D, 6 * D, B);
+      g.a_mn = 1; g.b_mn = 1; g.lda = D; g.ldb = ldada; g.batch = s.depth; g.a_bs = 0; g.b_bs = 6 * D;
+      g.epi = UMD_EPI_ATOMIC; g.out0 = c.G(s.base + UMD_S_ADA_W); g.ld0 = 6 * D; g.bs0 = static_cast<long long>(D) * 6 * D;
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
+    {
+      umd_gemm_args g = gemm_base(s.dada_bf16, c.WB(s.base + UMD_S_ADA_W), B, D, 6 * D);
+      g.a_mn = 0; g.b_mn = 0; g.lda = ldada; g.ldb = 6 * D; g.batch = s.depth; g.a_bs = 6 * D;
+      g.b_bs = static_cast<long long>(D) * 6 * D;
+      g.epi = UMD_EPI_ATOMIC; g.out0 = P.dcond; g.ld0 = D; g.bs0 = 0;
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
+  }
+  return UMD_OK;
+}
+
+EmbedArgs embed_args(const Ctx& c, const umd_io& io) {
+  const Plan& P = c.P;
+  EmbedArgs e;
+  e.image = io.image; e.ids_keep = io.ids_shuffle; e.W = c.W(UMD_P_EMBED_W); e.bias = c.W(UMD_P_EMBED_B);
+  e.pos = c.W(UMD_P_POS); e.cls = c.W(UMD_P_CLS); e.x = P.enc.x[0]; e.rm = P.enc.rm; e.n1 = c.sh->n1;
+  e.keep0 = c.sh->keep0; e.keep1 = c.sh->keep1; e.masked0 = c.sh->masked0; e.masked1 = c.sh->masked1;
+  e.img = c.cfg->img_size; e.patch = P.p; e.C = P.C; e.D = P.D; e.L = P.L; e.num_cls = P.ncls; e.tok0 = P.tok0;
+  return e;
+}
+DecInArgs decin_args(const Ctx& c, const umd_io& io) {
+  const Plan& P = c.P;
+  DecInArgs d;
+  d.enc = P.enc.xf; d.ids_restore = io.ids_restore; d.ids_keep = io.ids_shuffle; d.mask_token = c.W(UMD_P_MASK_TOKEN);
+  d.dec_pos = c.W(UMD_P_DEC_POS); d.xd = P.dec.x[0]; d.rep = io.pre_logits; d.rm_enc = P.enc.rm;
+  d.keep0 = c.sh->keep0; d.keep1 = c.sh->keep1; d.masked0 = c.sh->masked0; d.masked1 = c.sh->masked1;
+  d.D = P.D; d.L = P.L; d.num_cls = P.ncls; d.tok0 = P.tok0; d.S_d = P.Sd;
+  return d;
+}
+LossArgs loss_args(const Ctx& c, const umd_io& io, bool with_grad) {
+  const Plan& P = c.P;
+  const umd_step_shape& sh = *c.sh;
+  LossArgs a;
+  a.predp = P.predp; a.x0 = io.x0; a.noise = io.noise; a.ids_restore = io.ids_restore;
+  a.dpredp = with_grad ? P.dpredp : nullptr; a.partials = P.loss_partials;
+  a.n0 = sh.n0; a.n1 = sh.n1; a.keep0 = sh.keep0; a.keep1 = sh.keep1; a.masked0 = sh.masked0; a.masked1 = sh.masked1;
+  a.img = c.cfg->img_size; a.patch = P.p; a.C = P.C; a.L = P.L; a.grad_scale = 1.f;
+  // train_ae.py:333-335,352-360: loss = dit*(1 - n1/B) + mae*(n1/B); each mean()/mean(mask) ratio reduces to a
+  // sum divided by C * (number of selected pixels) because every sample masks the same number of patches.
+  const double Bt = sh.n0 + sh.n1, pp = static_cast<double>(P.p) * P.p, C = P.C;
+  const double wn = 1.0 - sh.n1 / Bt, wm = sh.n1 / Bt;
+  a.w_x0_0 = a.w_eps_0 = a.w_x0_1 = 0.f;
+  if (sh.n0 > 0) {
+    if (sh.masked0) {
+      a.w_x0_0 = static_cast<float>(0.5 * wn / (C * sh.n0 * (P.L - sh.keep0) * pp));
+      a.w_eps_0 = static_cast<float>(0.5 * wn / (C * sh.n0 * sh.keep0 * pp));
+    } else {
+      a.w_x0_0 = a.w_eps_0 = static_cast<float>(0.5 * wn / (C * sh.n0 * P.L * pp));
+    }
+  }
+  if (sh.n1 > 0) a.w_x0_1 = static_cast<float>(wm / (C * sh.n1 * (P.L - sh.keep1) * pp));
+  return a;
+}
+
+int check_common(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const void* params,
+                 const void* params_bf16, const umd_io* io, void* ws) {
+  UMD_REQUIRE(cfg && shape && offsets && params && params_bf16 && io && ws, "null argument");
+  UMD_REQUIRE(io->image && io->t, "image and t are required");
+  UMD_REQUIRE(!((shape->masked0 && shape->n0 > 0) || (shape->masked1 && shape->n1 > 0)) ||
+                  (io->ids_shuffle && io->ids_restore),
+              "ids_shuffle / ids_restore are required for masked segments");
+  UMD_REQUIRE(shape->n1 == 0 || shape->masked1, "the clean (MAE) segment must be masked (train_ae.py:335 divides by mean(mask))");
+  return UMD_OK;
+}
+
+}  // namespace
+
+int engine_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const float* params,
+                   const void* params_bf16, const umd_io* io, void* ws, size_t ws_bytes, int train, cudaStream_t st) {
+  UMD_TRY(check_common(cfg, shape, offsets, params, params_bf16, io, ws));
+  Ctx c;
+  c.cfg = cfg; c.sh = shape; c.offs = offsets; c.pf = params; c.pb = static_cast<const bf16*>(params_bf16);
+  c.grads = nullptr; c.st = st;
+  UMD_TRY(make_plan(c.P, *cfg, *shape, ws, train != 0));
+  UMD_REQUIRE(c.P.bytes <= ws_bytes, "workspace too small: need %zu bytes, have %zu", c.P.bytes, ws_bytes);
+  Plan& P = c.P;
+  const int D = P.D, B = P.B;
+  UMD_TRY(cond_forward(c, *io));
+  UMD_TRY(embed_fwd(embed_args(c, *io), B, st));
+  UMD_TRY(stack_forward(c, P.enc));
+  {  // encoder_norm (vit.py:163), fp32 out
+    LnFwdArgs ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = P.enc.x[P.enc.depth]; ln.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); ln.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
+    ln.rm = P.enc.rm; ln.out = P.enc.xf; ln.mean = P.enc.meanf; ln.rstd = P.enc.rstdf; ln.rows_out = P.Te;
+    UMD_TRY(ln_mod_fwd(ln, D, false, st));
+  }
+  UMD_TRY(decoder_input_fwd(decin_args(c, *io), B, st));
+  UMD_TRY(stack_forward(c, P.dec));
+  {  // decoder encoder_norm + drop the rep row + final modulation (ae.py:163-170) -> bf16 GEMM operand
+    LnFwdArgs ln;
+    memset(&ln, 0, sizeof(ln));
+    ln.x = P.dec.x[P.dec.depth]; ln.gamma = c.W(UMD_P_DEC_BASE + UMD_S_NORM_S); ln.beta = c.W(UMD_P_DEC_BASE + UMD_S_NORM_B);
+    ln.shift = P.fmod; ln.scale = P.fmod ? P.fmod + D : nullptr; ln.ldmod = 2 * D; ln.rm = P.dec.rm;
+    ln.out = P.xm; ln.mean = P.meanF; ln.rstd = P.rstdF; ln.rows_out = B * P.L; ln.gather_L = P.L; ln.gather_off = P.tok0 + 1;
+    UMD_TRY(ln_mod_fwd(ln, D, true, st));
+  }
+  UMD_TRY(pack_final_conv(c.W(UMD_P_FCONV_W), c.W(UMD_P_FCONV_B), P.p, D, 2 * P.C, cfg->flip_final_conv, P.Wf_mat, P.biasm, st));
+  UMD_TRY(dense_fwd(c, P.xm, B * P.L, D, P.Wf_mat, P.NC, P.biasm, UMD_EPI_F32, P.predp));
+  if (io->pred) UMD_TRY(unpatchify(P.predp, B, cfg->img_size, P.p, 2 * P.C, io->pred, st));
+  if (io->x0 && io->loss) {
+    UMD_REQUIRE(shape->n0 == 0 || io->noise, "noise targets are required for the noise segment");
+    UMD_TRY(loss_fwd_bwd(loss_args(c, *io, train != 0), io->loss, st));
+  }
+  return UMD_OK;
+}
+
+int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const float* params,
+                    const void* params_bf16, float* grads, const umd_io* io, void* ws, size_t ws_bytes, umd_bucket_cb cb,
+                    void* cb_user, cudaStream_t st) {
+  UMD_TRY(check_common(cfg, shape, offsets, params, params_bf16, io, ws));
+  UMD_REQUIRE(grads != nullptr, "grads is null");
+  Ctx c;
+  c.cfg = cfg; c.sh = shape; c.offs = offsets; c.pf = params; c.pb = static_cast<const bf16*>(params_bf16);
+  c.grads = grads; c.st = st;
+  UMD_TRY(make_plan(c.P, *cfg, *shape, ws, true));
+  UMD_REQUIRE(c.P.bytes <= ws_bytes, "workspace too small: need %zu bytes, have %zu", c.P.bytes, ws_bytes);
+  Plan& P = c.P;
+  const int D = P.D, B = P.B, BL = B * P.L;
+  UMD_CHECK_CUDA(cudaMemsetAsync(P.dcond, 0, static_cast<size_t>(B) * D * sizeof(float), st));
+  UMD_CHECK_CUDA(cudaMemsetAsync(P.dWf_mat, 0, static_cast<size_t>(D) * P.NC * sizeof(float), st));
+  UMD_CHECK_CUDA(cudaMemsetAsync(P.dbiasm, 0, static_cast<size_t>(P.NC) * sizeof(float), st));
+  // ---- un-patchify (final_conv) backward
+  UMD_TRY(dense_wgrad(c, P.xm, BL, D, P.dpredp, P.NC, P.NC, P.dWf_mat));
+  UMD_TRY(colsum_bf16(P.dpredp, P.NC, BL, P.NC, P.dbiasm, st));
+  UMD_TRY(unpack_final_conv_grad(P.dWf_mat, P.dbiasm, P.p, D, 2 * P.C, cfg->flip_final_conv, c.G(UMD_P_FCONV_W),
+                                 c.G(UMD_P_FCONV_B), st));
+  UMD_TRY(dense_dgrad(c, P.dpredp, BL, P.NC, P.Wf_mat, D, UMD_EPI_BF16, P.dyb));
+  {  // decoder encoder_norm + final modulation backward
+    LnBwdArgs lnb;
+    memset(&lnb, 0, sizeof(lnb));
+    lnb.dy = P.dyb; lnb.x = P.dec.x[P.dec.depth]; lnb.mean = P.meanF; lnb.rstd = P.rstdF;
+    lnb.gamma = c.W(UMD_P_DEC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_DEC_BASE + UMD_S_NORM_B);
+    lnb.scale = P.fmod ? P.fmod + D : nullptr; lnb.ldmod = 2 * D; lnb.rm = P.dec.rm; lnb.dx = P.dx_dec; lnb.accumulate = 0;
+    lnb.dshift = P.dfmod; lnb.dscale = P.dfmod ? P.dfmod + D : nullptr; lnb.ldd = 2 * D;
+    lnb.dgamma = c.G(UMD_P_DEC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_DEC_BASE + UMD_S_NORM_B);
+    lnb.gather_L = P.L; lnb.gather_off = P.tok0 + 1;
+    UMD_TRY(ln_mod_bwd(lnb, D, B, true, st));
+  }
+  if (P.adaln) {  // final_modulation Dense backward
+    UMD_TRY(cast_bf16(P.dfmod, static_cast<long long>(B) * 2 * D, P.dfmod_bf16, st));
+    UMD_TRY(colsum_f32(P.dfmod, 2 * D, B, 2 * D, c.G(UMD_P_FMOD_B), st));
+    UMD_TRY(dense_wgrad(c, P.cond_bf16, B, D, P.dfmod_bf16, 2 * D, 2 * D, c.G(UMD_P_FMOD_W)));
+    umd_gemm_args g = gemm_base(P.dfmod_bf16, c.WB(UMD_P_FMOD_W), B, D, 2 * D);
+    g.lda = 2 * D; g.ldb = 2 * D; g.epi = UMD_EPI_ATOMIC; g.out0 = P.dcond; g.ld0 = D;
+    UMD_TRY(gemm_bf16(g, st));
+  }
+  UMD_TRY(stack_backward(c, P.dec, P.dx_dec));
+  UMD_TRY(decoder_input_bwd(decin_args(c, *io), B, P.Te, P.dx_dec, P.dxf_enc, c.G(UMD_P_DEC_POS), c.G(UMD_P_MASK_TOKEN), st));
+  if (cb) cb(cb_user, 0);
+  {  // encoder_norm backward
+    LnBwdArgs lnb;
+    memset(&lnb, 0, sizeof(lnb));
+    lnb.dy = P.dxf_enc; lnb.x = P.enc.x[P.enc.depth]; lnb.mean = P.enc.meanf; lnb.rstd = P.enc.rstdf;
+    lnb.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
+    lnb.rm = P.enc.rm; lnb.dx = P.dx_enc; lnb.accumulate = 0;
+    lnb.dgamma = c.G(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_ENC_BASE + UMD_S_NORM_B);
+    UMD_TRY(ln_mod_bwd(lnb, D, B, false, st));
+  }
+  UMD_TRY(stack_backward(c, P.enc, P.dx_enc));
+  if (cb) cb(cb_user, 1);
+  UMD_TRY(embed_bwd(embed_args(c, *io), B, P.dx_enc, c.G(UMD_P_EMBED_W), c.G(UMD_P_EMBED_B), c.G(UMD_P_POS),
+                    c.G(UMD_P_CLS), st));
+  // ---- conditioning path backward (ae.py:121-124, embeddings.py:50-59)
+  UMD_TRY(cond_combine_bwd(P.dcond, P.s, static_cast<long long>(B) * D, P.adaln, P.ds, st));
+  struct Trunk { int w0, b0, w1, b1; const bf16* in; const float* h1; const bf16* a1; bf16* da1; bf16* dh1; };
+  Trunk trunks[2] = {{UMD_P_TT_W0, UMD_P_TT_B0, UMD_P_TT_W1, UMD_P_TT_B1, P.temb, P.th1, P.ta1, P.dta1, P.dth1},
+                     {UMD_P_LT_W0, UMD_P_LT_B0, UMD_P_LT_W1, UMD_P_LT_B1, P.lemb, P.lh1, P.la1, P.dla1, P.dlh1}};
+  for (int k = 0; k < (P.has_label ? 2 : 1); ++k) {
+    const Trunk& t = trunks[k];
+    UMD_TRY(colsum_bf16(P.ds, D, B, D, c.G(t.b1), st));
+    UMD_TRY(dense_wgrad(c, t.a1, B, 2 * D, P.ds, D, D, c.G(t.w1)));
+    UMD_TRY(dense_dgrad(c, P.ds, B, D, c.WB(t.w1), 2 * D, UMD_EPI_BF16, t.da1));
+    UMD_TRY(silu_bwd(t.da1, t.h1, static_cast<long long>(B) * 2 * D, t.dh1, st));
+    UMD_TRY(colsum_bf16(t.dh1, 2 * D, B, 2 * D, c.G(t.b0), st));
+    UMD_TRY(dense_wgrad(c, t.in, B, D, t.dh1, 2 * D, 2 * D, c.G(t.w0)));
+    if (k == 1) {  // label embedding table (embeddings.py:47)
+      umd_gemm_args g = gemm_base(t.dh1, c.WB(t.w0), B, D, 2 * D);
+      g.lda = 2 * D; g.ldb = 2 * D; g.epi = UMD_EPI_F32; g.out0 = P.dlemb; g.ld0 = D;
+      UMD_TRY(gemm_bf16(g, st));
+      UMD_TRY(scatter_add_rows(P.dlemb, io->labels, B, D, c.G(UMD_P_LABEL_TABLE), st));
+    }
+  }
+  if (cb) cb(cb_user, 2);
+  return UMD_OK;
+}
+
+}  // namespace umd
+
+using namespace umd;
+
+extern "C" size_t umd_workspace_bytes(const umd_model_cfg* cfg, const umd_step_shape* shape, int train) {
+  if (!cfg || !shape) return 0;
+  Plan P;
+  if (make_plan(P, *cfg, *shape, nullptr, train != 0) != UMD_OK) return 0;
+  return P.bytes;
+}
+extern "C" int umd_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets,
+                           const float* params, const void* params_bf16, const umd_io* io, void* workspace,
+                           size_t workspace_bytes, int train, umd_stream_t stream) {
+  return engine_forward(cfg, shape, offsets, params, params_bf16, io, workspace, workspace_bytes, train,
+                        static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets,
+                            const float* params, const void* params_bf16, float* grads, const umd_io* io, void* workspace,
+                            size_t workspace_bytes, umd_bucket_cb cb, void* cb_user, umd_stream_t stream) {
+  return engine_backward(cfg, shape, offsets, params, params_bf16, grads, io, workspace, workspace_bytes, cb, cb_user,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int umd_qsample(const float* x0, const float* noise, const int* t, const float* sa, const float* sb, int n,
+                           int per_sample, float* out, umd_stream_t stream) {
+  return qsample(x0, noise, t, sa, sb, n, per_sample, out, static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_mask_argsort(const float* noise, int n, int L, int len_keep, int* ids_shuffle, int* ids_restore,
+                                float* mask, umd_stream_t stream) {
+  return mask_argsort(noise, n, L, len_keep, ids_shuffle, ids_restore, mask, static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_attention_fwd(const void* qkv, void* out, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
+                                 umd_stream_t stream) {
+  AttnArgs a;
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.out = static_cast<__nv_bfloat16*>(out); a.lse = lse;
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.nsamples = n0 + n1; a.H = H; a.Dh = Dh; a.scale = 1.0f / sqrtf(static_cast<float>(Dh));
+  return attention_fwd(a, static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n0,
+                                 int s0, int n1, int s1, int H, int Dh, umd_stream_t stream) {
+  AttnBwdArgs a;
+  a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.out = static_cast<const __nv_bfloat16*>(out);
+  a.dout = static_cast<const __nv_bfloat16*>(dout); a.lse = lse; a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.nsamples = n0 + n1; a.H = H; a.Dh = Dh; a.scale = 1.0f / sqrtf(static_cast<float>(Dh));
+  return attention_bwd(a, static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_ln_modulate_fwd(const float* x, const float* gamma, const float* beta, const float* shift,
+                                   const float* scale, long long ldmod, int n0, int s0, int n1, int s1, int D, void* out,
+                                   int out_is_bf16, float* mean, float* rstd, umd_stream_t stream) {
+  LnFwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.gamma = gamma; a.beta = beta; a.shift = shift; a.scale = scale; a.ldmod = ldmod;
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.out = out; a.mean = mean; a.rstd = rstd; a.rows_out = n0 * s0 + n1 * s1;
+  return ln_mod_fwd(a, D, out_is_bf16 != 0, static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_ln_modulate_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                   const float* gamma, const float* beta, const float* scale, long long ldmod, int n0,
+                                   int s0, int n1, int s1, int D, float* dx, int accumulate, float* dshift, float* dscale,
+                                   long long ldd, float* dgamma, float* dbeta, umd_stream_t stream) {
+  LnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dy = dy; a.x = x; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.scale = scale; a.ldmod = ldmod;
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.dx = dx; a.accumulate = accumulate; a.dshift = dshift; a.dscale = dscale;
+  a.ldd = ldd; a.dgamma = dgamma; a.dbeta = dbeta;
+  return ln_mod_bwd(a, D, n0 + n1, dy_is_bf16 != 0, static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_cast_f32_to_bf16(const float* x, long long n, void* out, umd_stream_t stream) {
+  return cast_bf16(x, n, out, static_cast<cudaStream_t>(stream));
+}

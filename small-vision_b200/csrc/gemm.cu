@@ -21,7 +21,7 @@ constexpr int GEMM_THREADS = 384;
 
 struct GemmParams {
   int M, N, K, batch, split_k;
-  int a_bcast, b_bcast;
+  int a_bcast, b_bcast, b_kchunk;
   void* out0;
   long long ld0, bs0;
   void* out1;
@@ -55,6 +55,26 @@ __device__ __forceinline__ float gelu_tanh_grad(float u) {
   float inner = k0 * (u + k1 * u * u2);
   float t = tanh_fast(inner);
   return 0.5f * (1.f + t) + 0.5f * u * (1.f - t * t) * k0 * (1.f + 3.f * k1 * u2);
+}
+
+struct WorkItem {
+  int m0, n0, b, kb0, kb1;
+};
+// item order: n fastest, then batch, then k-split, then m — CTAs running concurrently share the A row-panel.
+template <int BN>
+__device__ __forceinline__ WorkItem decode_item(long long item, int n_tiles, int batch, int split_k, int kb_total) {
+  WorkItem w;
+  const int n = static_cast<int>(item % n_tiles);
+  long long r = item / n_tiles;
+  w.b = static_cast<int>(r % batch);
+  r /= batch;
+  const int ks = static_cast<int>(r % split_k);
+  const int m = static_cast<int>(r / split_k);
+  w.m0 = m * BM;
+  w.n0 = n * BN;
+  w.kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / split_k);
+  w.kb1 = static_cast<int>(static_cast<long long>(ks + 1) * kb_total / split_k);
+  return w;
 }
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
@@ -111,14 +131,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0;
     uint32_t phase = 0;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int tile = static_cast<int>(item % tiles_mn);
-      const int rest = static_cast<int>(item / tiles_mn);
-      const int ks = rest % p.split_k;
-      const int b = rest / p.split_k;
-      const int m0 = (tile / n_tiles) * BM;
-      const int n0 = (tile % n_tiles) * BN;
-      const int kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / p.split_k);
-      const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * kb_total / p.split_k);
+      const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const int m0 = w.m0, n0 = w.n0, b = w.b, kb0 = w.kb0, kb1 = w.kb1;
       const int ba = p.a_bcast ? 0 : b;
       const int bb = p.b_bcast ? 0 : b;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -134,7 +148,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], m0 + 64 * i, k0, ba);
         }
         if (!B_MN) {
-          tma_load_3d(sb, &tmB, &full_bar[stage], k0, n0, bb);
+          if (p.b_kchunk) {
+            const int chunk = k0 / p.b_kchunk;
+            tma_load_3d(sb, &tmB, &full_bar[stage], k0 - chunk * p.b_kchunk, n0, chunk);
+          } else {
+            tma_load_3d(sb, &tmB, &full_bar[stage], k0, n0, bb);
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + 64 * i, k0, bb);
@@ -156,10 +175,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int it = 0;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const int rest = static_cast<int>(item / tiles_mn);
-      const int ks = rest % p.split_k;
-      const int kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / p.split_k);
-      const int kb1 = static_cast<int>(static_cast<long long>(ks + 1) * kb_total / p.split_k);
+      const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const int kb0 = w.kb0, kb1 = w.kb1;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -192,11 +209,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int HALF_COLS = BN / 2;
     int it = 0;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const int tile = static_cast<int>(item % tiles_mn);
-      const int rest = static_cast<int>(item / tiles_mn);
-      const int b = rest / p.split_k;
-      const int m0 = (tile / n_tiles) * BM;
-      const int n0 = (tile % n_tiles) * BN;
+      const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const int m0 = w.m0, n0 = w.n0, b = w.b;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
@@ -405,6 +419,12 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   p.M = a.M; p.N = a.N; p.K = a.K; p.batch = a.batch;
   p.split_k = split_k < kb_total ? split_k : kb_total;
   p.a_bcast = (a.a_bs == 0); p.b_bcast = (a.b_bs == 0);
+  p.b_kchunk = a.b_kchunk;
+  if (a.b_kchunk) {
+    UMD_REQUIRE(!a.b_mn && a.batch == 1 && a.b_kchunk % BK == 0 && a.K % a.b_kchunk == 0 && a.b_bs > 0,
+                "umd_gemm_bf16: b_kchunk needs K-major B, batch 1, chunk %% 64 == 0, K %% chunk == 0");
+    p.b_bcast = 0;
+  }
   p.out0 = a.out0; p.ld0 = a.ld0; p.bs0 = a.bs0;
   p.out1 = a.out1; p.ld1 = a.ld1;
   p.bias = a.bias; p.bias_bs = a.bias_bs;
@@ -421,7 +441,8 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   const uint64_t a_batch = p.a_bcast ? 1 : a.batch, b_batch = p.b_bcast ? 1 : a.batch;
   if (!a.a_mn) UMD_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a_batch, a.lda, a.a_bs, BM));
   else         UMD_TRY(make_tmap_bf16(&tmA, a.A, a.M, a.K, a_batch, a.lda, a.a_bs, BK));
-  if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, bn));
+  if (a.b_kchunk) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.b_kchunk, a.N, a.K / a.b_kchunk, a.ldb, a.b_bs, bn));
+  else if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, bn));
   else         UMD_TRY(make_tmap_bf16(&tmB, a.B, a.N, a.K, b_batch, a.ldb, a.b_bs, BK));
 
   switch (bn) {

@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
       ("aux", C.c_void_p), ("ldaux", C.c_longlong),
       ("gate", C.c_void_p), ("ldgate", C.c_longlong),
       ("split_row", C.c_int), ("s0", C.c_int), ("s1", C.c_int), ("n0", C.c_int),
+      ("b_kchunk", C.c_int),
   ]
 
 
@@ -75,7 +76,7 @@ def launch_count():
 
 def gemm(A, B, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, batch=1, a_bs=0, b_bs=0,
          epi=EPI_BF16, split_k=1, out0=None, ld0=0, bs0=0, out1=None, ld1=0, bias=None, bias_bs=0,
-         aux=None, ldaux=0, gate=None, ldgate=0, rowmap=None):
+         aux=None, ldaux=0, gate=None, ldgate=0, rowmap=None, b_kchunk=0):
   """Thin wrapper over umd_gemm_bf16 for tests and host-side orchestration."""
   lib = load()
   a = GemmArgs()
@@ -94,4 +95,57 @@ def gemm(A, B, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, batch=1, 
   if rowmap is None:
     rowmap = (M, M, 1, 1)
   a.split_row, a.s0, a.s1, a.n0 = rowmap
+  a.b_kchunk = b_kchunk
   check(lib.umd_gemm_bf16(C.byref(a), current_stream()), "umd_gemm_bf16")
+
+
+class ModelCfg(C.Structure):
+  _fields_ = [(k, C.c_int) for k in ("img_size", "patch", "channels", "width", "depth", "dec_depth", "heads", "mlp_dim",
+                                      "num_cls", "num_classes", "adaln", "flip_final_conv")]
+
+
+class StepShape(C.Structure):
+  _fields_ = [(k, C.c_int) for k in ("n0", "n1", "keep0", "keep1", "masked0", "masked1")]
+
+
+class IO(C.Structure):
+  _fields_ = [(k, C.c_void_p) for k in ("image", "t", "labels", "ids_shuffle", "ids_restore", "x0", "noise", "pred",
+                                        "pre_logits", "loss")]
+
+
+class AdamwArgs(C.Structure):
+  _fields_ = [
+      ("params", C.c_void_p), ("grads", C.c_void_p), ("mu", C.c_void_p), ("nu", C.c_void_p),
+      ("params_bf16", C.c_void_p), ("ema", C.c_void_p), ("wd_flags", C.c_void_p), ("n", C.c_longlong),
+      ("clip_norm", C.c_float), ("lr", C.c_float), ("b1", C.c_float), ("b2", C.c_float), ("eps", C.c_float),
+      ("wd", C.c_float), ("bias_corr1", C.c_float), ("bias_corr2", C.c_float), ("ema_decay", C.c_float),
+      ("scratch", C.c_void_p), ("scratch_floats", C.c_int), ("measurements", C.c_void_p),
+  ]
+
+
+BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
+
+
+def model_cfg_struct(cfg):
+  m = ModelCfg()
+  m.img_size, m.patch, m.channels = cfg.img_size, cfg.patch, cfg.channels
+  m.width, m.depth, m.dec_depth, m.heads, m.mlp_dim = cfg.width, cfg.depth, cfg.dec_depth, cfg.num_heads, cfg.mlp
+  m.num_cls = cfg.num_cls
+  m.num_classes = cfg.num_classes or 0
+  m.adaln = int(cfg.adaln)
+  m.flip_final_conv = int(cfg.flip_final_conv)
+  return m
+
+
+def workspace_bytes(mcfg, shape, train):
+  lib = load()
+  lib.umd_workspace_bytes.restype = C.c_size_t
+  n = lib.umd_workspace_bytes(C.byref(mcfg), C.byref(shape), C.c_int(int(train)))
+  if n == 0:
+    raise UmdError("umd_workspace_bytes: " + lib.umd_last_error().decode())
+  return int(n)
+
+
+def cast_bf16(src, dst):
+  lib = load()
+  check(lib.umd_cast_f32_to_bf16(ptr(src), C.c_longlong(src.numel()), ptr(dst), current_stream()), "umd_cast_f32_to_bf16")
