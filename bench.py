@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Headline benchmark: training images/sec of the UMD auto-encoder step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload umd_b4|...]
+
+One "step" = one call of update_fn (train_ae.py:287-382) on one synthetic batch: draws, q_sample, forward of
+both branches, loss, backward, gradient all-reduce (N > 1), global-norm clip + AdamW.  Weak scaling: 512 images
+per GPU (256 noised + 256 clean-MAE), the per-GPU share of the reference recipe's global batch 4096 on 8 GPUs.
+Prints ONE JSON line on rank 0 (see README / DESIGN.md for the keys).
+
+--impl reference times the CPU restatement of the reference step (oracle/umd_oracle.py) on the host cores:
+the reference itself is JAX/Flax/Optax code and none of those can be installed in this image.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = "train images/sec (UMD-B/4 64x64)"
+
+WORKLOADS = {
+    # name: (model kwargs, train kwargs, per-GPU batch)
+    "umd_b4": (dict(variant="B/4", adaln=True, num_classes=None, channels=3, img_size=64),
+               dict(no_noise_prob=0.5, mask_ratio=0.375, mask_ratio_no_noise=0.75, use_labels=False), 512),
+    "umd_s4": (dict(variant="S/4", adaln=True, num_classes=None, channels=3, img_size=64),
+               dict(no_noise_prob=0.5, mask_ratio=0.375, mask_ratio_no_noise=0.75, use_labels=False), 512),
+    "mae_b4": (dict(variant="B/4", adaln=False, num_classes=None, channels=3, img_size=64),
+               dict(no_noise_prob=0.5, mask_ratio=0.375, mask_ratio_no_noise=0.75, use_labels=False), 512),
+    "dit_b4": (dict(variant="B/4", adaln=True, num_classes=1000, channels=3, img_size=64),
+               dict(no_noise_prob=0.0, mask_ratio=0.0, mask_ratio_no_noise=0.75, use_labels=True), 256),
+    "latent_umd_l2": (dict(variant="L/2", adaln=True, num_classes=None, channels=4, img_size=32),
+                      dict(no_noise_prob=0.5, mask_ratio=0.375, mask_ratio_no_noise=0.75, use_labels=False,
+                           beta_schedule="linear", diffusion_space=(32, 32, 4)), 128),
+}
+
+
+def step_flops_per_image(cfg, tkw):
+  """Algorithmic FLOPs of one training step per image: 3 x forward, 2MNK per GEMM,
+  4 S^2 D per attention layer; no rematerialisation."""
+  D, M = cfg.width, cfg.mlp
+  L, p, C = cfg.num_patches, cfg.patch, cfg.channels
+  ad = 1 if cfg.adaln else 0
+  tok0 = 0 if cfg.adaln else 1
+  Sd = L + 1 + tok0
+
+  def fwd(keep):
+    Se = keep + cfg.num_cls + tok0
+    enc = cfg.depth * (Se * (8 * D * D + 4 * D * M) + 4 * Se * Se * D + 12 * D * D * ad)
+    dec = cfg.dec_depth * (Sd * (8 * D * D + 4 * D * M) + 4 * Sd * Sd * D + 12 * D * D * ad)
+    return enc + dec + L * 2 * (p * p * C) * D + L * 2 * D * (2 * p * p * C) + 8 * D * D + 4 * D * D * ad
+
+  pn = tkw["no_noise_prob"]
+  k0 = cfg.len_keep(tkw["mask_ratio"]) if tkw["mask_ratio"] > 0 else L
+  k1 = cfg.len_keep(tkw["mask_ratio_no_noise"])
+  return 3.0 * ((1 - pn) * fwd(k0) + pn * fwd(k1))
+
+
+def load_peaks():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    with open(p) as f:
+      d = json.load(f)
+    return dict(hbm=d.get("hbm_gbs", 6650.0), tf_burst=d.get("bf16_tflops", 1590.0),
+                tf_sustained=d.get("bf16_tflops_sustained", 1400.0), source="measured")
+  return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+  """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.idx = gpu_index
+    self.proc = None
+    self.path = None
+
+  def start(self):
+    try:
+      fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+      os.close(fd)
+      self.f = open(self.path, "w")
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                    "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+    except Exception:  # nvidia-smi missing
+      self.proc = None
+
+  def stop(self):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if self.proc is None:
+      return out
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    self.f.close()
+    sm, mx, pw, reasons = [], [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    with open(self.path) as f:
+      for line in f:
+        parts = [x.strip() for x in line.split(",")]
+        if len(parts) < 8:
+          continue
+        try:
+          sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+        except ValueError:
+          continue
+        for nm, v in zip(names, parts[4:8]):
+          if v.lower().startswith("active"):
+            reasons.add(nm)
+    os.unlink(self.path)
+    if sm:
+      s = sorted(sm)
+      out.update(sm_mhz=s[len(s) // 2], sm_max_mhz=max(mx), power_w_max=max(pw), reasons=sorted(reasons), samples=len(sm))
+    return out
+
+
+def run_reference(args):
+  """CPU restatement of the reference step on the host cores (rank 0 only)."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import torch
+  from oracle import umd_oracle as O
+  from small_vision_b200.config import TrainConfig, make_model_config
+  from small_vision_b200.diffusion import create_gaussian_diffusion
+  from tests import util as U
+  mkw, tkw, per_gpu = WORKLOADS[args.workload]
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  B = args.cpu_batch
+  model, ocfg = U.make_models(mkw["variant"], adaln=mkw["adaln"], num_classes=mkw["num_classes"],
+                              img_size=mkw["img_size"], channels=mkw["channels"])
+  params = U.cpu_tree(U.perturb_init(model, 0, "cpu"))
+  tcfg = TrainConfig(batch_size=B, total_steps=1000, warmup_steps=0, **{k: v for k, v in tkw.items()})
+  state = {"params": params, "gd": create_gaussian_diffusion(tkw.get("beta_schedule", "cosine"), 1000)}
+  state["opt"] = O.init_opt_state(params)
+  hp = U.oracle_hp(tcfg)
+  n_clean = int(B * tkw["no_noise_prob"])
+  times = []
+  for s in range(args.warmup + args.steps):
+    b, rand = U.make_batch(model, B, n_noise=B - n_clean, seed=s, use_labels=tkw["use_labels"])
+    t0 = time.perf_counter()
+    state, meas, _ = O.update_step(state, b, ocfg, tkw, hp, rand)
+    dt = time.perf_counter() - t0
+    if s >= args.warmup:
+      times.append(dt)
+  ms = 1e3 * sum(times) / len(times)
+  v = B / (ms / 1e3)
+  sample = f"{args.steps} steps of batch {B} ({B - n_clean} noised + {n_clean} clean) after {args.warmup} warm-up, fp32, torch-CPU"
+  line = {"metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+          "data": "synthetic", "impl": "reference",
+          "config": {"workload": f"{args.workload}: {mkw['variant']} {mkw['img_size']}x{mkw['img_size']} one update_fn step",
+                     "global_batch": B, "note": "CPU restatement of the reference step (oracle port; JAX is not installable here)"},
+          "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
+          "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0}
+  print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, mkw, tkw):
+  """Bounded oracle sample on the host cores (rank 0, N = 1): one warm-up + two timed steps at batch 8."""
+  import torch
+  from oracle import umd_oracle as O
+  from small_vision_b200.config import TrainConfig
+  from small_vision_b200.diffusion import create_gaussian_diffusion
+  from tests import util as U
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  B = args.cpu_batch
+  model, ocfg = U.make_models(mkw["variant"], adaln=mkw["adaln"], num_classes=mkw["num_classes"],
+                              img_size=mkw["img_size"], channels=mkw["channels"])
+  params = U.cpu_tree(U.perturb_init(model, 0, "cpu"))
+  tcfg = TrainConfig(batch_size=B, total_steps=1000, warmup_steps=0, **tkw)
+  state = {"params": params, "gd": create_gaussian_diffusion(tkw.get("beta_schedule", "cosine"), 1000)}
+  state["opt"] = O.init_opt_state(params)
+  hp = U.oracle_hp(tcfg)
+  n_clean = int(B * tkw["no_noise_prob"])
+  times = []
+  for s in range(3):
+    b, rand = U.make_batch(model, B, n_noise=B - n_clean, seed=s, use_labels=tkw["use_labels"])
+    t0 = time.perf_counter()
+    state, _, _ = O.update_step(state, b, ocfg, tkw, hp, rand)
+    if s >= 1:
+      times.append(time.perf_counter() - t0)
+  dt = sum(times) / len(times)
+  return {"value": B / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+          "sample": f"2 steps of batch {B} after 1 warm-up, fp32 torch-CPU restatement of update_fn (oracle/umd_oracle.py)"}
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--workload", default="umd_b4", choices=sorted(WORKLOADS))
+  ap.add_argument("--per-gpu-batch", type=int, default=None)
+  ap.add_argument("--cpu-batch", type=int, default=8)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 1)
+  if args.impl == "reference":
+    run_reference(args)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from small_vision_b200 import lib
+  from small_vision_b200.config import TrainConfig
+  from small_vision_b200.model import Model
+  from small_vision_b200.train import create_train_state, make_update_fn
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device: the UMD hot path has no CPU fallback")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  pg = None
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD
+  assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+  mkw, tkw, per_gpu = WORKLOADS[args.workload]
+  if args.per_gpu_batch:
+    per_gpu = args.per_gpu_batch
+  model = Model(**mkw)
+  cfg = model.cfg
+  B_global = per_gpu * world
+  tcfg = TrainConfig(batch_size=B_global, **tkw)
+  state = create_train_state(model, tcfg, seed=0, device=dev, nonzero_adaln=True)
+  # start the optimiser past the lr(0) = 0 warm-up step so that every timed step really moves the parameters
+  state["opt"]["count"] = 10
+  update_fn = make_update_fn(model, tcfg, process_group=pg)
+
+  H, C = cfg.img_size, cfg.channels
+  g = torch.Generator(device=dev).manual_seed(1 + rank)
+  n_dev_batches = 4   # 4 x 25 MB of inputs; activations written per step (tens of GB) flush the 126 MB L2 anyway
+  dev_batches = [{"image": torch.rand(per_gpu, H, H, C, device=dev, generator=g) * 2 - 1,
+                  "label": torch.randint(0, max(cfg.num_classes or 1, 1), (per_gpu,), device=dev, generator=g)}
+                 for _ in range(n_dev_batches)]
+  host_batches = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in dev_batches]
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+      fn(s)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    return ms
+
+  losses = []
+
+  def step_resident(s):
+    nonlocal state
+    state, meas = update_fn(state, dev_batches[s % n_dev_batches])
+    losses.append(meas["training_loss"])
+
+  e2e_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+  def step_e2e(s):
+    nonlocal state
+    hb = host_batches[s % n_dev_batches]
+    b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+    state, meas = update_fn(state, b)
+    e2e_loss.copy_(meas["training_loss"].reshape(1), non_blocking=False)   # device -> host read of the step's loss
+
+  for s in range(args.warmup):
+    step_resident(s)
+  L = lib.load()
+  import ctypes as Ct
+  ncat = L.umd_profile_num_categories()
+  L.umd_profile_category_name.restype = Ct.c_char_p
+  launches0 = lib.launch_count()
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  L.umd_profile_enable(1)
+  ms_total = timed(step_resident, args.steps)
+  L.umd_profile_enable(0)
+  launches = lib.launch_count() - launches0
+  prof_ms = (Ct.c_float * ncat)()
+  prof_work = (Ct.c_double * ncat)()
+  prof_n = (Ct.c_longlong * ncat)()
+  dropped = L.umd_profile_read(prof_ms, prof_work, prof_n, ncat)
+  e2e = None
+  if not args.no_e2e:
+    for s in range(2):
+      step_e2e(s)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = {"value": B_global * args.steps / (ms_e2e / 1e3), "unit": "images/sec",
+           "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host_batches[0].values()) * world,
+           "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps}
+  clocks = sampler.stop() if rank == 0 else None
+  final_loss = float(losses[-1])
+  if not math.isfinite(final_loss):
+    raise SystemExit(f"non-finite training loss {final_loss}")
+
+  if rank == 0:
+    peaks = load_peaks()
+    ms_step = ms_total / args.steps
+    value = B_global * args.steps / (ms_total / 1e3)
+    fl_img = step_flops_per_image(cfg, tkw)
+    cats = {}
+    for i in range(ncat):
+      nm = L.umd_profile_category_name(i).decode()
+      cats[nm] = {"ms_per_step": prof_ms[i] / args.steps, "work_per_step": prof_work[i] / args.steps,
+                  "launches_per_step": prof_n[i] / args.steps}
+    gm = cats["gemm"]
+    gemm_tf = gm["work_per_step"] / (gm["ms_per_step"] * 1e-3) / 1e12 if gm["ms_per_step"] > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 forward/dgrad GEMMs)", "achieved": gemm_tf,
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
+                "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches_per_step": gm["launches_per_step"], "share_of_step": gm["ms_per_step"] / ms_step}
+    breakdown = {}
+    for nm, c in cats.items():
+      if c["ms_per_step"] <= 0:
+        continue
+      tensor = nm.startswith("gemm") or nm.startswith("attention")
+      rate = c["work_per_step"] / (c["ms_per_step"] * 1e-3)
+      breakdown[nm] = {"ms": round(c["ms_per_step"], 3), "share": round(c["ms_per_step"] / ms_step, 4),
+                       "launches": c["launches_per_step"],
+                       ("tflops" if tensor else "gbs"): round(rate / (1e12 if tensor else 1e9), 1),
+                       "frac_of_peak": round(rate / ((peaks["tf_sustained"] * 1e12) if tensor else (peaks["hbm"] * 1e9)), 3)}
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {mkw['variant']} {H}x{H}x{C} update_fn step, {per_gpu} img/GPU "
+                               f"({per_gpu - int(per_gpu * tkw['no_noise_prob'])} noised + {int(per_gpu * tkw['no_noise_prob'])} clean)",
+                   "global_batch": B_global, "per_gpu_batch": per_gpu, "parallelism": f"dp{world}",
+                   "params": model.layout.num_params, "l2": "inputs rotate over 4 batches; each step writes > 10 GB of activations (>> 126 MB L2)",
+                   "precision": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / loss / AdamW (bf16 mu)"},
+        "step_tflops": fl_img * value / 1e12, "step_frac_of_bf16_peak": fl_img * value / 1e12 / peaks["tf_sustained"],
+        "flops_per_image": fl_img, "final_loss": final_loss,
+        "roofline": roofline, "breakdown": breakdown, "profile_scopes_dropped": dropped,
+        "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      line["cpu_baseline"] = cpu_baseline(args, mkw, tkw)
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -37,6 +37,15 @@ int umd_version(void);
 /* number of kernels this library has launched since load (all streams); bench.py reads it */
 long long umd_launch_count(void);
 
+/* Optional live per-category device timing (bench.py roofline): while enabled the launchers bracket their
+ * kernels with CUDA events on the launching stream and account algorithmic FLOPs (tensor-bound categories)
+ * or bytes (HBM-bound ones).  umd_profile_read sums and clears; call it after a device synchronise.
+ * Returns the number of scopes that could not be read. */
+void umd_profile_enable(int on);
+int umd_profile_num_categories(void);
+const char* umd_profile_category_name(int category);
+int umd_profile_read(float* ms, double* work, long long* scopes, int ncat);
+
 /* ------------------------------------------------------------------------------------------
  * Dense bf16 GEMM on tcgen05/TMEM fed by TMA (models/vit.py:54,57,71,82-87; ae.py:64,94,95).
  *   D[b] = op(A[b]) * op(B[b])   (fp32 accumulate), b = 0..batch-1
@@ -98,6 +107,11 @@ int umd_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int n0, 
                       umd_stream_t stream);
 int umd_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
                       void* dqkv_bf16, int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream);
+/* same contract on the CUDA-core kernels (the in-library checker of the tcgen05 attention path) */
+int umd_attention_fwd_simt(const void* qkv_bf16, void* out_bf16, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
+                           umd_stream_t stream);
+int umd_attention_bwd_simt(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
+                           void* dqkv_bf16, int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream);
 /* models/vit.py:78-80 LayerNorm (+ adaLN modulate); out bf16 when out_is_bf16 else fp32 */
 int umd_ln_modulate_fwd(const float* x, const float* gamma, const float* beta, const float* shift, const float* scale,
                         long long ldmod, int n0, int s0, int n1, int s1, int D, void* out, int out_is_bf16, float* mean,

@@ -456,7 +456,7 @@ def update_step(state, batch, cfg, tc, hp, rand, dtype=torch.float32):
   loss.backward()
   grads = unflatten_tree({k: v.grad.float() if v.grad is not None else torch.zeros_like(v) for k, v in leaves.items()})
   new_params, new_opt, upd, gnorm = optimizer_update(grads, state["opt"], state["params"], hp)
-  meas = {"training_loss": float(loss),
+  meas = {"training_loss": float(loss.detach()),
           "l2_params": math.sqrt(sum(float((p.double() ** 2).sum()) for p in flatten_tree(new_params).values())),
           "l2_updates": math.sqrt(sum(float((u.double() ** 2).sum()) for u in upd.values())),
           "grad_norm": gnorm}

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <vector>
 
 namespace umd {
 
@@ -83,7 +84,71 @@ int sm_count() {
   return n;
 }
 
+// ---- profiling scopes ---------------------------------------------------------------------
+bool g_prof_on = false;
+namespace {
+struct ProfRec { cudaEvent_t e0, e1; int cat; double work; };
+std::vector<ProfRec> g_recs;
+std::vector<cudaEvent_t> g_pool;
+size_t g_pool_used = 0;
+int g_depth = 0;
+constexpr size_t kMaxEvents = 1 << 17;
+cudaEvent_t take_event() {
+  if (g_pool_used == g_pool.size()) {
+    if (g_pool.size() >= kMaxEvents) return nullptr;
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    g_pool.push_back(e);
+  }
+  return g_pool[g_pool_used++];
+}
+}  // namespace
+void prof_open(int cat, double work, cudaStream_t st) {
+  if (g_depth++ > 0) return;  // only the outermost scope records
+  ProfRec r;
+  r.e0 = take_event();
+  r.e1 = take_event();
+  r.cat = cat;
+  r.work = work;
+  if (!r.e0 || !r.e1) { r.e0 = r.e1 = nullptr; }
+  else cudaEventRecord(r.e0, st);
+  g_recs.push_back(r);
+}
+void prof_close(cudaStream_t st) {
+  if (--g_depth > 0) return;
+  if (!g_recs.empty() && g_recs.back().e1) cudaEventRecord(g_recs.back().e1, st);
+}
+
 }  // namespace umd
+
+extern "C" void umd_profile_enable(int on) {
+  umd::g_prof_on = on != 0;
+  umd::g_depth = 0;
+}
+extern "C" int umd_profile_num_categories(void) { return umd::PC_COUNT; }
+extern "C" const char* umd_profile_category_name(int c) {
+  static const char* names[umd::PC_COUNT] = {"gemm", "gemm_wgrad", "attention_fwd", "attention_bwd", "ln_modulate_fwd",
+                                            "ln_modulate_bwd", "gate_bwd", "colsum", "optimizer"};
+  return (c >= 0 && c < umd::PC_COUNT) ? names[c] : "?";
+}
+// Sums the recorded scopes per category (the caller has synchronised the device) and clears them.
+extern "C" int umd_profile_read(float* ms, double* work, long long* scopes, int ncat) {
+  using namespace umd;
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0.f; work[i] = 0.0; scopes[i] = 0; }
+  int dropped = 0;
+  for (const ProfRec& r : g_recs) {
+    if (r.cat < 0 || r.cat >= ncat) continue;
+    float t = 0.f;
+    if (!r.e0 || cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) { ++dropped; continue; }
+    ms[r.cat] += t;
+    work[r.cat] += r.work;
+    scopes[r.cat] += 1;
+  }
+  g_recs.clear();
+  g_pool_used = 0;
+  cudaGetLastError();
+  return dropped;
+}
 
 extern "C" const char* umd_last_error(void) { return umd::g_err; }
 extern "C" int umd_version(void) { return 100; }

@@ -92,6 +92,37 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t 
 
 int sm_count();
 
+// ---------------------------------------------------------------------------
+// Optional per-category device timing (bench.py's live roofline): when enabled, the leaf launchers
+// bracket their kernels with CUDA events on the launching stream and account the algorithmic work
+// (FLOPs for tensor-bound categories, bytes for HBM-bound ones).  Off by default; costs nothing then.
+// ---------------------------------------------------------------------------
+enum ProfCat {
+  PC_GEMM = 0,      // forward / dgrad GEMMs (activations as the A operand)
+  PC_GEMM_WGRAD,    // weight-gradient GEMMs (both operands MN-major, split-K)
+  PC_ATTN_FWD,
+  PC_ATTN_BWD,
+  PC_LN_FWD,
+  PC_LN_BWD,
+  PC_GATE_BWD,
+  PC_COLSUM,
+  PC_OPTIMIZER,
+  PC_COUNT
+};
+extern bool g_prof_on;
+void prof_open(int cat, double work, cudaStream_t st);
+void prof_close(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cat, double work, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (on) prof_open(cat, work, s);
+  }
+  ~ProfScope() {
+    if (on) prof_close(st);
+  }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

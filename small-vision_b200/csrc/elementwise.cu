@@ -118,6 +118,8 @@ static int ln_fwd_dispatch(const LnFwdArgs& a, int D, cudaStream_t st) {
 int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
   if (a.rows_out <= 0) return UMD_OK;
   UMD_REQUIRE(D % 128 == 0 && D <= 1024, "ln_mod_fwd: width %d unsupported", D);
+  // algorithmic bytes: fp32 row in, bf16/fp32 row out
+  ProfScope prof(PC_LN_FWD, static_cast<double>(a.rows_out) * D * (4 + (out_bf16 ? 2 : 4)), st);
   return out_bf16 ? ln_fwd_dispatch<__nv_bfloat16>(a, D, st) : ln_fwd_dispatch<float>(a, D, st);
 }
 
@@ -241,6 +243,12 @@ static int ln_bwd_dispatch(const LnBwdArgs& a, int D, int nsamples, cudaStream_t
 int ln_mod_bwd(const LnBwdArgs& a, int D, int nsamples, bool dy_bf16, cudaStream_t st) {
   if (nsamples <= 0) return UMD_OK;
   UMD_REQUIRE(D % 128 == 0 && D <= 1024, "ln_mod_bwd: width %d unsupported", D);
+  {
+    // algorithmic bytes: dy in, x in, dx read-modify-write (fp32)
+    const double rows = static_cast<double>(a.rm.split_row) + static_cast<double>(nsamples - a.rm.n0) * a.rm.s1;
+    ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + 4 + (a.accumulate ? 8 : 4)), st);
+    return dy_bf16 ? ln_bwd_dispatch<__nv_bfloat16>(a, D, nsamples, st) : ln_bwd_dispatch<float>(a, D, nsamples, st);
+  }
   return dy_bf16 ? ln_bwd_dispatch<__nv_bfloat16>(a, D, nsamples, st) : ln_bwd_dispatch<float>(a, D, nsamples, st);
 }
 
@@ -283,6 +291,8 @@ __global__ void __launch_bounds__(1024) gate_bwd_kernel(GateBwdArgs a, int D) {
 int gate_bwd(const GateBwdArgs& a, int D, int nsamples, cudaStream_t st) {
   if (nsamples <= 0) return UMD_OK;
   UMD_REQUIRE(D % 4 == 0 && D <= 1024, "gate_bwd: width %d unsupported", D);
+  const double rows = static_cast<double>(a.rm.split_row) + static_cast<double>(nsamples - a.rm.n0) * a.rm.s1;
+  ProfScope prof(PC_GATE_BWD, rows * D * (4 + 2 + (a.dgate ? 2 : 0)), st);  // dx in, dz out, z in
   gate_bwd_kernel<<<nsamples, D, 8 * D * sizeof(float), st>>>(a, D);
   UMD_LAUNCH_CHECK();
   return UMD_OK;
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 int colsum_bf16(const void* x, long long ld, int rows, int N, float* out, cudaStream_t st) {
   if (rows <= 0) return UMD_OK;
   UMD_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8");
+  ProfScope prof(PC_COLSUM, static_cast<double>(rows) * N * 2, st);
   const int rpc = 512;
   dim3 grid(ceil_div(N, 256), ceil_div(rows, rpc));
   colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, N, out, rpc);

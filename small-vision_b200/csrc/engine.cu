@@ -613,20 +613,35 @@ extern "C" int umd_mask_argsort(const float* noise, int n, int L, int len_keep, 
                                 float* mask, umd_stream_t stream) {
   return mask_argsort(noise, n, L, len_keep, ids_shuffle, ids_restore, mask, static_cast<cudaStream_t>(stream));
 }
-extern "C" int umd_attention_fwd(const void* qkv, void* out, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
-                                 umd_stream_t stream) {
+static AttnArgs mk_attn(const void* qkv, void* out, float* lse, int n0, int s0, int n1, int s1, int H, int Dh) {
   AttnArgs a;
   a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.out = static_cast<__nv_bfloat16*>(out); a.lse = lse;
   a.rm = ragged_rowmap(n0, s0, n1, s1); a.nsamples = n0 + n1; a.H = H; a.Dh = Dh; a.scale = 1.0f / sqrtf(static_cast<float>(Dh));
-  return attention_fwd(a, static_cast<cudaStream_t>(stream));
+  return a;
 }
-extern "C" int umd_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n0,
-                                 int s0, int n1, int s1, int H, int Dh, umd_stream_t stream) {
+static AttnBwdArgs mk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n0,
+                               int s0, int n1, int s1, int H, int Dh) {
   AttnBwdArgs a;
   a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.out = static_cast<const __nv_bfloat16*>(out);
   a.dout = static_cast<const __nv_bfloat16*>(dout); a.lse = lse; a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   a.rm = ragged_rowmap(n0, s0, n1, s1); a.nsamples = n0 + n1; a.H = H; a.Dh = Dh; a.scale = 1.0f / sqrtf(static_cast<float>(Dh));
-  return attention_bwd(a, static_cast<cudaStream_t>(stream));
+  return a;
+}
+extern "C" int umd_attention_fwd(const void* qkv, void* out, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
+                                 umd_stream_t stream) {
+  return attention_fwd(mk_attn(qkv, out, lse, n0, s0, n1, s1, H, Dh), static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n0,
+                                 int s0, int n1, int s1, int H, int Dh, umd_stream_t stream) {
+  return attention_bwd(mk_attn_bwd(qkv, out, dout, lse, dqkv, n0, s0, n1, s1, H, Dh), static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_attention_fwd_simt(const void* qkv, void* out, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
+                                      umd_stream_t stream) {
+  return attention_fwd_simt(mk_attn(qkv, out, lse, n0, s0, n1, s1, H, Dh), static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_attention_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                                      int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream) {
+  return attention_bwd_simt(mk_attn_bwd(qkv, out, dout, lse, dqkv, n0, s0, n1, s1, H, Dh), static_cast<cudaStream_t>(stream));
 }
 extern "C" int umd_ln_modulate_fwd(const float* x, const float* gamma, const float* beta, const float* shift,
                                    const float* scale, long long ldmod, int n0, int s0, int n1, int s1, int D, void* out,

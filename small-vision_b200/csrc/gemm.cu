@@ -445,6 +445,7 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   else if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, bn));
   else         UMD_TRY(make_tmap_bf16(&tmB, a.B, a.N, a.K, b_batch, a.ldb, a.b_bs, BK));
 
+  ProfScope prof(a.a_mn ? PC_GEMM_WGRAD : PC_GEMM, 2.0 * a.M * static_cast<double>(a.N) * a.K * a.batch, stream);
   switch (bn) {
     case 256: return launch_gemm_bn<256>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
     case 128: return launch_gemm_bn<128>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);

@@ -156,6 +156,9 @@ struct AttnBwdArgs {
 };
 int attention_fwd(const AttnArgs& a, cudaStream_t st);
 int attention_bwd(const AttnBwdArgs& a, cudaStream_t st);
+// CUDA-core kernels: in-library checker of the tensor-core path and fallback for shapes it does not cover
+int attention_fwd_simt(const AttnArgs& a, cudaStream_t st);
+int attention_bwd_simt(const AttnBwdArgs& a, cudaStream_t st);
 
 // ---- optimiser (optimizer.cu) -----------------------------------------------------------
 int sumsq(const float* x, long long n, float* partials, int max_partials, float* out, cudaStream_t st);

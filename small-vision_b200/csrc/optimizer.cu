@@ -139,6 +139,8 @@ extern "C" int umd_adamw_step(const umd_adamw_args* a, umd_stream_t stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   UMD_REQUIRE(a && a->n > 0 && a->n % 64 == 0, "umd_adamw_step: arena size must be a positive multiple of 64");
   UMD_REQUIRE(a->scratch_floats >= 3 * 1024 + 8, "umd_adamw_step: scratch too small (need >= 3080 floats)");
+  // algorithmic bytes per parameter: g r 4 (twice: norm + update), p rw 8, mu rw 4, nu rw 8, bf16 shadow w 2, ema rw 8
+  ProfScope prof(PC_OPTIMIZER, static_cast<double>(a->n) * (8 + 8 + 4 + 8 + (a->params_bf16 ? 2 : 0) + (a->ema ? 8 : 0)), st);
   float* part_g = a->scratch;
   float* part_u = a->scratch + 1024;
   float* part_p = a->scratch + 2048;
