@@ -1,16 +1,630 @@
-// tcgen05/TMEM fused attention (forward, backward).  Placeholder until the kernels land: reports
-// "unsupported" so that the dispatcher in attention.cu uses the CUDA-core kernels.
+// Fused multi-head self-attention on tcgen05 / TMEM for sm_100a, forward and backward.
+//
+// Semantics: flax MultiHeadDotProductAttention as called at big_vision/models/vit.py:82-87 —
+// softmax((q / sqrt(Dh)) k^T) v per (sample, head), no mask, no dropout; backward per SURVEY.md App. E step 7.
+// Every recipe of the reference has at most 260 tokens per sample, so one CTA owns one
+// (sample, head): Q, K, V (and dO) of that head are fetched once by TMA into 128B-swizzled shared memory and
+// the S x S score matrix never leaves the SM.
+//
+//   forward : per 128-query tile  S = Q K^T -> TMEM;  softmax warps (thread = TMEM lane = query row) read S,
+//             write P (bf16) to shared memory in the canonical K-major swizzled layout;  O = P V -> TMEM;
+//             epilogue scales by 1 / rowsum and stores O (bf16) and the log-sum-exp.
+//   backward: per 128-key tile j and 128-query tile i (in 64-query halves):  S^T = K_j Q_i^T and
+//             dP^T = V_j dO_i^T -> TMEM;  the softmax warps (thread = key row) form P^T and
+//             dS^T = P^T (dP^T - delta) and write both (bf16) to shared memory;  dV_j += P^T dO_i,
+//             dK_j += dS^T Q_i (K-major A) and dQ_i += dS K_j (the same tile read as an MN-major A) accumulate
+//             in TMEM; dK/dV leave after the query loop, dQ after the key loop.
+//
+// Warp roles (256 threads): warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator,
+// warps 4..7 softmax / epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace umd {
-bool attention_tc_supported(const RowMap&, int, int, int) { return false; }
-int attention_fwd_tc(const AttnArgs&, cudaStream_t) {
-  set_error("attention_fwd_tc: not built");
-  return UMD_ERR_UNSUPPORTED;
+
+extern long long g_launch_count;
+
+namespace {
+
+constexpr int AT_DH = 64;
+constexpr int AT_MAX_S = 272;
+constexpr int AT_ROW = 128;            // bytes per 64-element bf16 row
+constexpr int AT_SLAB = 128 * AT_ROW;  // [128 rows][64 cols] bf16 = 16 KB
+constexpr int AT_THREADS = 256;
+constexpr int AT_STAT_N = 384;         // per-query statistics padded to three 128-query tiles
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-int attention_bwd_tc(const AttnBwdArgs&, cudaStream_t) {
-  set_error("attention_bwd_tc: not built");
-  return UMD_ERR_UNSUPPORTED;
+__device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// 16-byte chunk `chunk` (0..7) of row r of a [rows][64] bf16 slab in the 128B-swizzled layout TMA / UMMA use.
+__device__ __forceinline__ void st_swz(uint8_t* slab, int r, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(slab + r * AT_ROW + ((chunk ^ (r & 7)) << 4)) = v;
 }
+
+__device__ __forceinline__ void load_rows(uint8_t* dst, const CUtensorMap* tm128, const CUtensorMap* tm16, uint64_t* bar,
+                                          int col, int row0, int rows) {
+  int r = 0;
+  for (; r + 128 <= rows; r += 128) tma_load_3d(dst + r * AT_ROW, tm128, bar, col, row0 + r, 0);
+  for (; r < rows; r += 16) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, row0 + r, 0);
+}
+
+struct FwdParams {
+  __nv_bfloat16* out;
+  float* lse;
+  int row_base;  // first row of the segment
+  int S, SP, nqt, H;
+  int o_col, tmem_cols;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.S, SP = p.SP, nqt = p.nqt;
+  const int D = p.H * AT_DH;
+  const int h = blockIdx.x % p.H;
+  const int row0 = p.row_base + (blockIdx.x / p.H) * S;
+  const int nslab = (SP + 63) >> 6;
+  uint8_t* sQ = smem;                      // nqt * 128 rows (rows >= SP stay unwritten: they only feed unused lanes)
+  uint8_t* sK = sQ + nqt * 128 * AT_ROW;   // SP rows
+  uint8_t* sV = sK + SP * AT_ROW;          // SP rows
+  uint8_t* sP = sV + SP * AT_ROW;          // nslab slabs [128 q][64 kv]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + nslab * AT_SLAB);
+  uint64_t* bar_kv = bars + 0;
+  uint64_t* bar_s = bars + 1;
+  uint64_t* bar_p = bars + 2;
+  uint64_t* bar_o = bars + 3;
+  uint64_t* bar_free = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm128);
+    tma_prefetch_desc(&tm16);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_p, 128);
+    mbar_init(bar_o, 1);
+    mbar_init(bar_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    mbar_expect_tx(bar_kv, 3u * SP * AT_ROW);
+    load_rows(sK, &tm128, &tm16, bar_kv, D + h * AT_DH, row0, SP);
+    load_rows(sQ, &tm128, &tm16, bar_kv, h * AT_DH, row0, SP);
+    load_rows(sV, &tm128, &tm16, bar_kv, 2 * D + h * AT_DH, row0, SP);
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+    mbar_wait(bar_kv, 0);
+    tc_fence_after();
+    for (int i = 0; i < nqt; ++i) {
+      if (i > 0) {
+        mbar_wait(bar_free, (i - 1) & 1);
+        tc_fence_after();
+      }
+      const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + i * 128 * AT_ROW), 0, 1024);
+      for (int n0 = 0; n0 < SP; n0 += 256) {
+        const int n = min(256, SP - n0);
+        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + n0 * AT_ROW), 0, 1024);
+        const uint32_t idesc = make_idesc_bf16(128, n, false, false);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + n0, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
+      mbar_wait(bar_p, i & 1);
+      tc_fence_after();
+      const int ksteps = SP >> 4;
+      for (int kk = 0; kk < ksteps; ++kk) {
+        const uint64_t pa = make_smem_desc_sw128(smem_u32(sP + (kk >> 2) * AT_SLAB + (kk & 3) * 32), 0, 1024);
+        const uint64_t vb = make_smem_desc_sw128(smem_u32(sV + kk * 16 * AT_ROW), 8192, 1024);
+        umma_f16_ss(tmem_base + p.o_col, pa, vb, idesc_pv, kk > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_o);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + epilogue
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // row inside the query tile = TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float sl2 = p.scale_log2;
+    for (int i = 0; i < nqt; ++i) {
+      mbar_wait(bar_s, i & 1);
+      tc_fence_after();
+      // pass 1: row maximum of the raw logits
+      float m = -INFINITY;
+      for (int c = 0; c < SP; c += 32) {
+        if (c + 32 <= SP) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_lane + c, v);
+          tmem_ld_wait();
+          if (c + 32 <= S) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, (c + j < S) ? __uint_as_float(v[j]) : -INFINITY);
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x16(t_lane + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m = fmaxf(m, (c + j < S) ? __uint_as_float(v[j]) : -INFINITY);
+        }
+      }
+      const float ms = m * sl2;
+      // pass 2: p = exp2(s * scale*log2e - max), row sum, bf16 P -> shared memory
+      float sum = 0.f;
+      for (int c = 0; c < SP; c += 32) {
+        uint32_t v[32];
+        const bool full = (c + 32 <= SP);
+        if (full) {
+          tmem_ld_32x32(t_lane + c, v);
+        } else {
+          uint32_t w[16];
+          tmem_ld_32x16(t_lane + c, w);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = w[j];
+#pragma unroll
+          for (int j = 16; j < 32; ++j) v[j] = 0;
+        }
+        tmem_ld_wait();
+        uint8_t* slab = sP + (c >> 6) * AT_SLAB;
+        const int chunk0 = (c & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (full || j < 16) {
+            float e[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float x = ex2(__uint_as_float(v[j + q]) * sl2 - ms);
+              e[q] = (c + j + q < S) ? x : 0.f;
+              sum += e[q];
+            }
+            st_swz(slab, r, chunk0 + (j >> 3),
+                   make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7])));
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_p);
+      // epilogue: O / rowsum
+      mbar_wait(bar_o, i & 1);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32(t_lane + p.o_col, o0);
+      tmem_ld_32x32(t_lane + p.o_col + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_free);
+      const int row = i * 128 + r;
+      if (row < S) {
+        const float inv = 1.f / sum;
+        __nv_bfloat16* op = p.out + static_cast<long long>(row0 + row) * D + h * AT_DH;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          *reinterpret_cast<uint4*>(op + j) = make_uint4(
+              pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
+              pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
+              pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
+              pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          *reinterpret_cast<uint4*>(op + 32 + j) = make_uint4(
+              pack_bf16x2(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv),
+              pack_bf16x2(__uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv),
+              pack_bf16x2(__uint_as_float(o1[j + 4]) * inv, __uint_as_float(o1[j + 5]) * inv),
+              pack_bf16x2(__uint_as_float(o1[j + 6]) * inv, __uint_as_float(o1[j + 7]) * inv));
+        }
+        if (p.lse) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BwdParams {
+  const __nv_bfloat16* out;
+  const __nv_bfloat16* dout;
+  const float* lse;
+  __nv_bfloat16* dqkv;
+  int row_base;
+  int S, SP, nt, H;
+  int nbuf;  // TMEM score buffers (2 when nt <= 2)
+  float scale, scale_log2;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_constant__ CUtensorMap tq16,
+                   const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16, const BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.S, SP = p.SP, nt = p.nt, nbuf = p.nbuf;
+  const int D = p.H * AT_DH;
+  const int h = blockIdx.x % p.H;
+  const int row0 = p.row_base + (blockIdx.x / p.H) * S;
+  // K and V are also read as 128-row A operands: the reads past row SP of K land in V, those of V in the
+  // P^T tile — allocated memory whose content only reaches TMEM lanes that are masked below.
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + SP * AT_ROW;
+  uint8_t* sK = sdO + SP * AT_ROW;
+  uint8_t* sV = sK + SP * AT_ROW;
+  uint8_t* sPt = sV + SP * AT_ROW;   // [128 kv][128 q] as two slabs of 64 q
+  uint8_t* sdSt = sPt + 2 * AT_SLAB;
+  float* sLse = reinterpret_cast<float*>(sdSt + 2 * AT_SLAB);  // [SP] lse * log2e
+  float* sDelta = sLse + AT_STAT_N;                           // [SP] rowsum(dO * O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + AT_STAT_N);
+  uint64_t* bar_ld = bars + 0;
+  uint64_t* bar_s = bars + 1;       // [2]
+  uint64_t* bar_sfree = bars + 3;   // [2]
+  uint64_t* bar_p = bars + 5;       // [2] one per 64-query half
+  uint64_t* bar_tfree = bars + 7;
+  uint64_t* bar_acc = bars + 8;
+  uint64_t* bar_accfree = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tq128);
+    tma_prefetch_desc(&tq16);
+    tma_prefetch_desc(&td128);
+    tma_prefetch_desc(&td16);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_ld, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_sfree[i], 128);
+      mbar_init(&bar_p[i], 128);
+    }
+    mbar_init(bar_tfree, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_accfree, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t col_dv = nbuf * 128, col_dk = col_dv + 64, col_dq = col_dv + 128;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    mbar_expect_tx(bar_ld, 4u * SP * AT_ROW);
+    load_rows(sK, &tq128, &tq16, bar_ld, D + h * AT_DH, row0, SP);
+    load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, row0, SP);
+    load_rows(sV, &tq128, &tq16, bar_ld, 2 * D + h * AT_DH, row0, SP);
+    load_rows(sdO, &td128, &td16, bar_ld, h * AT_DH, row0, SP);
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_kt = make_idesc_bf16(128, 64, false, true);   // A K-major (P^T / dS^T), B MN-major (dO / Q)
+    constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, true, true);    // A MN-major (dS), B MN-major (K)
+    mbar_wait(bar_ld, 0);
+    tc_fence_after();
+    int step = 0, blk = 0;
+    uint32_t cnt_p[2] = {0, 0};
+    for (int j = 0; j < nt; ++j) {
+      const int nkv = min(128, SP - 128 * j);
+      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + j * 128 * AT_ROW), 0, 1024);
+      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + j * 128 * AT_ROW), 0, 1024);
+      for (int i = 0; i < nt; ++i) {
+        const int nq = min(128, SP - 128 * i);
+        const int nh = (nq + 63) >> 6;
+        for (int hh = 0; hh < nh; ++hh, ++step) {
+          const int b = step % nbuf, u = step / nbuf;
+          if (u > 0) {
+            mbar_wait(&bar_sfree[b], (u - 1) & 1);
+            tc_fence_after();
+          }
+          const int nqh = min(64, nq - 64 * hh);
+          const uint32_t idesc = make_idesc_bf16(128, nqh, false, false);
+          const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + (i * 128 + hh * 64) * AT_ROW), 0, 1024);
+          const uint64_t odesc = make_smem_desc_sw128(smem_u32(sdO + (i * 128 + hh * 64) * AT_ROW), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128, kdesc + 2 * k, qdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + b * 128 + 64, vdesc + 2 * k, odesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[b]);
+        }
+        for (int hh = 0; hh < nh; ++hh) {
+          mbar_wait(&bar_p[hh], cnt_p[hh] & 1);
+          ++cnt_p[hh];
+        }
+        tc_fence_after();
+        if (i == 0 && j > 0) {
+          mbar_wait(bar_accfree, (j - 1) & 1);
+          tc_fence_after();
+        }
+        const int kq = nq >> 4;
+        for (int kk = 0; kk < kq; ++kk) {   // dV_j += P^T dO_i
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sPt + (kk >> 2) * AT_SLAB + (kk & 3) * 32), 0, 1024);
+          const uint64_t bb = make_smem_desc_sw128(smem_u32(sdO + (i * 128 + kk * 16) * AT_ROW), 8192, 1024);
+          umma_f16_ss(tmem_base + col_dv, a, bb, idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        for (int kk = 0; kk < kq; ++kk) {   // dK_j += dS^T Q_i
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sdSt + (kk >> 2) * AT_SLAB + (kk & 3) * 32), 0, 1024);
+          const uint64_t bb = make_smem_desc_sw128(smem_u32(sQ + (i * 128 + kk * 16) * AT_ROW), 8192, 1024);
+          umma_f16_ss(tmem_base + col_dk, a, bb, idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        const int kkv = nkv >> 4;
+        for (int kk = 0; kk < kkv; ++kk) {  // dQ_i += dS K_j   (dS^T tile read as an MN-major A operand)
+          const uint64_t a = make_smem_desc_sw128(smem_u32(sdSt + kk * 16 * AT_ROW), AT_SLAB, 1024);
+          const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + (j * 128 + kk * 16) * AT_ROW), 8192, 1024);
+          umma_f16_ss(tmem_base + col_dq + 64 * i, a, bb, idesc_mn, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_tfree);
+        ++blk;
+      }
+      umma_commit(bar_acc);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax backward + epilogues
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;  // key row inside the key tile (TMEM lane); query row in the dQ epilogue
+    const int tid = threadIdx.x - 128;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    // delta = rowsum(dO * O), lse in log2 units
+    for (int q = tid; q < SP; q += 128) {
+      float dl = 0.f, l2 = 0.f;
+      if (q < S) {
+        const uint4* po = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(row0 + q) * D + h * AT_DH);
+        const uint4* pg = reinterpret_cast<const uint4*>(p.dout + static_cast<long long>(row0 + q) * D + h * AT_DH);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 a = po[c], g = pg[c];
+          dl += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+                bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+                bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+        }
+        l2 = p.lse[static_cast<long long>(row0 + q) * p.H + h] * LOG2E;
+      }
+      sDelta[q] = dl;
+      sLse[q] = l2;
+    }
+    bar_softmax();
+    const float sl2 = p.scale_log2;
+    int step = 0, blk = 0;
+    for (int j = 0; j < nt; ++j) {
+      const int kv = j * 128 + r;
+      const bool kv_ok = kv < S;
+      for (int i = 0; i < nt; ++i) {
+        const int nq = min(128, SP - 128 * i);
+        const int nh = (nq + 63) >> 6;
+        for (int hh = 0; hh < nh; ++hh, ++step) {
+          const int b = step % nbuf, u = step / nbuf;
+          mbar_wait(&bar_s[b], u & 1);
+          tc_fence_after();
+          uint32_t s0[32], s1[32], d0[32], d1[32];
+          tmem_ld_32x32(t_lane + b * 128, s0);
+          tmem_ld_32x32(t_lane + b * 128 + 32, s1);
+          tmem_ld_32x32(t_lane + b * 128 + 64, d0);
+          tmem_ld_32x32(t_lane + b * 128 + 96, d1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(&bar_sfree[b]);
+          if (hh == 0 && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
+          const int q0 = i * 128 + hh * 64;
+          uint8_t* slabP = sPt + hh * AT_SLAB;
+          uint8_t* slabS = sdSt + hh * AT_SLAB;
+#pragma unroll
+          for (int c = 0; c < 64; c += 8) {
+            float pe[8], de[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int q = q0 + c + e;
+              const float sv = __uint_as_float(c + e < 32 ? s0[(c + e) & 31] : s1[(c + e) & 31]);
+              const float dv = __uint_as_float(c + e < 32 ? d0[(c + e) & 31] : d1[(c + e) & 31]);
+              const bool ok = kv_ok && (q < S);
+              const float l2 = sLse[q];
+              const float dl = sDelta[q];
+              const float pv = ex2(sv * sl2 - l2);
+              pe[e] = ok ? pv : 0.f;
+              de[e] = ok ? pv * (dv - dl) : 0.f;
+            }
+            st_swz(slabP, r, c >> 3,
+                   make_uint4(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7])));
+            st_swz(slabS, r, c >> 3,
+                   make_uint4(pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7])));
+          }
+          fence_proxy_async();
+          mbar_arrive(&bar_p[hh]);
+        }
+        ++blk;
+      }
+      // dK_j, dV_j
+      mbar_wait(bar_acc, j & 1);
+      tc_fence_after();
+      {
+        uint32_t a0[32], a1[32];
+        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + kv) * (3 * D) + h * AT_DH;
+        tmem_ld_32x32(t_lane + col_dv, a0);
+        tmem_ld_32x32(t_lane + col_dv + 32, a1);
+        tmem_ld_wait();
+        if (kv_ok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            *reinterpret_cast<uint4*>(dst + 2 * D + c) = make_uint4(
+                pack_bf16x2(__uint_as_float(a0[c]), __uint_as_float(a0[c + 1])), pack_bf16x2(__uint_as_float(a0[c + 2]), __uint_as_float(a0[c + 3])),
+                pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7])));
+            *reinterpret_cast<uint4*>(dst + 2 * D + 32 + c) = make_uint4(
+                pack_bf16x2(__uint_as_float(a1[c]), __uint_as_float(a1[c + 1])), pack_bf16x2(__uint_as_float(a1[c + 2]), __uint_as_float(a1[c + 3])),
+                pack_bf16x2(__uint_as_float(a1[c + 4]), __uint_as_float(a1[c + 5])), pack_bf16x2(__uint_as_float(a1[c + 6]), __uint_as_float(a1[c + 7])));
+          }
+        }
+        tmem_ld_32x32(t_lane + col_dk, a0);
+        tmem_ld_32x32(t_lane + col_dk + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(bar_accfree);
+        if (kv_ok) {
+          const float sc = p.scale;
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            *reinterpret_cast<uint4*>(dst + D + c) = make_uint4(
+                pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
+                pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc));
+            *reinterpret_cast<uint4*>(dst + D + 32 + c) = make_uint4(
+                pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
+                pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc));
+          }
+        }
+      }
+    }
+    // dQ_i (the last bar_acc phase covers every MMA issued)
+    for (int i = 0; i < nt; ++i) {
+      uint32_t a0[32], a1[32];
+      tmem_ld_32x32(t_lane + col_dq + 64 * i, a0);
+      tmem_ld_32x32(t_lane + col_dq + 64 * i + 32, a1);
+      tmem_ld_wait();
+      const int q = i * 128 + r;
+      if (q < S) {
+        const float sc = p.scale;
+        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + q) * (3 * D) + h * AT_DH;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          *reinterpret_cast<uint4*>(dst + c) = make_uint4(
+              pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
+              pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc));
+          *reinterpret_cast<uint4*>(dst + 32 + c) = make_uint4(
+              pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
+              pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc));
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+struct Segment {
+  int n, S, row_base;
+};
+int segments(const RowMap& rm, int nsamples, Segment (&seg)[2]) {
+  int k = 0;
+  const int n0 = rm.n0 < nsamples ? rm.n0 : nsamples;
+  if (n0 > 0) seg[k++] = Segment{n0, rm.s0, 0};
+  if (nsamples > n0) seg[k++] = Segment{nsamples - n0, rm.s1, rm.split_row};
+  return k;
+}
+int total_rows(const RowMap& rm, int nsamples) {
+  const int n0 = rm.n0 < nsamples ? rm.n0 : nsamples;
+  return n0 * rm.s0 + (nsamples - n0) * rm.s1;
+}
+
+}  // namespace
+
+bool attention_tc_supported(const RowMap& rm, int nsamples, int H, int Dh) {
+  if (Dh != AT_DH || nsamples <= 0 || H <= 0) return false;
+  Segment seg[2];
+  const int ns = segments(rm, nsamples, seg);
+  for (int k = 0; k < ns; ++k)
+    if (seg[k].S < 1 || seg[k].S > AT_MAX_S) return false;
+  return true;
+}
+
+int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
+  Segment seg[2];
+  const int ns = segments(a.rm, a.nsamples, seg);
+  const int rows = total_rows(a.rm, a.nsamples);
+  const int D = a.H * AT_DH;
+  CUtensorMap tm128, tm16;
+  UMD_TRY(make_tmap_bf16(&tm128, a.qkv, 3 * D, rows, 1, 3 * D, 0, 128));
+  UMD_TRY(make_tmap_bf16(&tm16, a.qkv, 3 * D, rows, 1, 3 * D, 0, 16));
+  static bool cfg = false;
+  if (!cfg) {
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg = true;
+  }
+  for (int k = 0; k < ns; ++k) {
+    FwdParams p;
+    p.out = a.out; p.lse = a.lse; p.row_base = seg[k].row_base;
+    p.S = seg[k].S; p.SP = (p.S + 15) & ~15; p.nqt = (p.S + 127) / 128; p.H = a.H;
+    p.o_col = (p.SP + 31) & ~31;
+    p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
+    p.scale_log2 = a.scale * LOG2E;
+    const int nslab = (p.SP + 63) / 64;
+    int smem = (p.nqt * 128 + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 256 + 1024;
+    // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
+    if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
+    if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;
+    attn_fwd_tc_kernel<<<seg[k].n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, p);
+    ++g_launch_count;
+    UMD_CHECK_CUDA(cudaGetLastError());
+  }
+  return UMD_OK;
+}
+
+int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
+  Segment seg[2];
+  const int ns = segments(a.rm, a.nsamples, seg);
+  const int rows = total_rows(a.rm, a.nsamples);
+  const int D = a.H * AT_DH;
+  CUtensorMap tq128, tq16, td128, td16;
+  UMD_TRY(make_tmap_bf16(&tq128, a.qkv, 3 * D, rows, 1, 3 * D, 0, 128));
+  UMD_TRY(make_tmap_bf16(&tq16, a.qkv, 3 * D, rows, 1, 3 * D, 0, 16));
+  UMD_TRY(make_tmap_bf16(&td128, a.dout, D, rows, 1, D, 0, 128));
+  UMD_TRY(make_tmap_bf16(&td16, a.dout, D, rows, 1, D, 0, 16));
+  static bool cfg = false;
+  if (!cfg) {
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cfg = true;
+  }
+  for (int k = 0; k < ns; ++k) {
+    BwdParams p;
+    p.out = a.out; p.dout = a.dout; p.lse = a.lse; p.dqkv = a.dqkv; p.row_base = seg[k].row_base;
+    p.S = seg[k].S; p.SP = (p.S + 15) & ~15; p.nt = (p.S + 127) / 128; p.H = a.H;
+    p.nbuf = p.nt <= 2 ? 2 : 1;
+    p.scale = a.scale; p.scale_log2 = a.scale * LOG2E;
+    int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 2 * AT_STAT_N * 4 + 256 + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
+    attn_bwd_tc_kernel<<<seg[k].n * a.H, AT_THREADS, smem, st>>>(tq128, tq16, td128, td16, p);
+    ++g_launch_count;
+    UMD_CHECK_CUDA(cudaGetLastError());
+  }
+  return UMD_OK;
+}
+
 }  // namespace umd
