@@ -1,0 +1,190 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol declared in
+include/umd_b200.h, argument validation fails loudly (no compute without a GPU), and the host-side mirror of
+the reference interface (config, parameter tree, sharding declarations) matches SURVEY.md App. B/C."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from small_vision_b200 import lib
+from small_vision_b200.config import TrainConfig, decode_variant, make_model_config
+from small_vision_b200.params import ArenaLayout, arena_from_tree, init_arena, tree_from_arena
+from small_vision_b200.sharding import Mesh, PartitionSpec, infer_sharding, local_batch_slice, check_batch_divisible
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "umd_b200.h")
+
+
+@pytest.fixture(scope="module")
+def L():
+  if not os.path.exists(lib.LIB_PATH):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "small-vision_b200", "csrc"), "-j", "8"], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+  return lib.load()
+
+
+def _declared_functions():
+  src = open(HEADER).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  return sorted(set(re.findall(r"\b(umd_[a-z0-9_]+)\s*\(", src)) - {"umd_bucket_cb"})
+
+
+def test_library_exports_every_declared_symbol(L):
+  names = _declared_functions()
+  assert len(names) >= 20, names
+  missing = [n for n in names if not hasattr(L, n)]
+  assert not missing, f"declared in include/umd_b200.h but not exported: {missing}"
+
+
+def test_library_is_sm100a_native():
+  """cuobjdump shows tcgen05 / TMA SASS mnemonics (B200_PROFILING.md 'What proves a Blackwell-native kernel')."""
+  exe = "/usr/local/cuda/bin/cuobjdump"
+  if not (os.path.exists(exe) and os.path.exists(lib.LIB_PATH)):
+    pytest.skip("cuobjdump or library not present")
+  sass = subprocess.run([exe, "-sass", lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+  assert "sm_100a" in sass
+  for mnem in ("UTCHMMA", "UTMALDG", "LDTM"):
+    assert mnem in sass, mnem
+
+
+def test_error_paths_without_a_gpu(L):
+  assert L.umd_version() >= 100
+  assert L.umd_gemm_bf16(None, None) == 1                      # UMD_ERR_INVALID
+  assert b"null args" in L.umd_last_error()
+  a = lib.GemmArgs()
+  a.M, a.N, a.K, a.batch = 128, 12, 64, 1                      # N not a multiple of 8
+  assert L.umd_gemm_bf16(C.byref(a), None) == 1 and b"multiple of 8" in L.umd_last_error()
+  assert lib.launch_count() >= 0
+
+
+def test_workspace_bytes_is_host_arithmetic(L):
+  cfg = make_model_config(variant="B/4", adaln=True)
+  m = lib.model_cfg_struct(cfg)
+  sh = lib.StepShape(256, 256, 160, 64, 1, 1)
+  train = lib.workspace_bytes(m, sh, True)
+  infer = lib.workspace_bytes(m, sh, False)
+  assert 20e9 < train < 80e9 and infer < train / 4            # no remat: every activation of 16 blocks is kept (F9)
+  bad = lib.StepShape(256, 256, 300, 64, 1, 1)
+  with pytest.raises(lib.UmdError):
+    lib.workspace_bytes(m, bad, True)
+  m.width = 100
+  with pytest.raises(lib.UmdError, match="width"):
+    lib.workspace_bytes(m, sh, True)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+  monkeypatch.setattr(lib, "_lib", None)
+  monkeypatch.setattr(lib, "LIB_PATH", "/nonexistent/libumd_b200.so")
+  with pytest.raises(lib.UmdError, match="no CPU or PyTorch fallback"):
+    lib.load()
+
+
+def test_product_path_never_imports_the_oracle():
+  pkg = os.path.join(ROOT, "small-vision_b200")
+  for dp, _, fs in os.walk(pkg):
+    for f in fs:
+      if f.endswith((".py", ".cu", ".cuh")):
+        txt = open(os.path.join(dp, f)).read()
+        assert "umd_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+# ------------------------------------------------------------------------------------------ config / variants
+def test_decode_variant_and_len_keep():
+  assert decode_variant("B/4") == dict(width=768, depth=12, dec_depth=4, num_heads=12, patch_size=(4, 4))
+  assert decode_variant("L") == dict(width=1024, depth=24, dec_depth=8, num_heads=16)
+  with pytest.raises(KeyError):
+    decode_variant(":B/4")          # README.md:37 writes "variant=:B/4"; ae.py:205-215 rejects it the same way
+  cfg = make_model_config(variant="B/4", adaln=True)
+  assert (cfg.num_patches, cfg.len_keep(0.375), cfg.len_keep(0.75), cfg.len_keep(0.0)) == (256, 160, 64, 256)
+  assert make_model_config(variant="L/2", img_size=32, channels=4).num_patches == 256
+  assert make_model_config(variant="B/16", img_size=256).num_patches == 256
+
+
+def test_train_config_schedule_constants():
+  t = TrainConfig(batch_size=4096).resolved()
+  assert t.scaled_peak_lr == pytest.approx(15e-5 * 16)
+  assert t.total_steps == int(800 * 1_268_355 / 4096) and t.warmup_steps == 40 * 1_268_355 // 4096
+
+
+@pytest.mark.parametrize("kw,count", [
+    (dict(variant="S/4", adaln=True), 43.73e6), (dict(variant="B/4", adaln=True), 174.16e6),
+    (dict(variant="B/4", adaln=False), 116.28e6), (dict(variant="B/4", adaln=True, num_classes=1000), 177.29e6),
+    (dict(variant="L/2", adaln=True, img_size=32, channels=4), 611.48e6)])
+def test_parameter_counts_match_survey_appendix_b(kw, count):
+  lay = ArenaLayout(make_model_config(**kw))
+  assert lay.num_params == pytest.approx(count, rel=2e-4)
+
+
+def test_parameter_tree_is_the_flax_layout():
+  cfg = make_model_config(variant="S/4", adaln=True, num_classes=10)
+  lay = ArenaLayout(cfg)
+  tree = tree_from_arena(lay, init_arena(lay, 0, "cpu"))
+  D, H = 384, 6
+  blk = tree["Encoder"]["ScanCheckpointEncoder1DBlock_0"]
+  assert tuple(tree["cls"].shape) == (1, 4, D) and tuple(tree["pos_embedding"].shape) == (1, 256, D)
+  assert tuple(tree["embedding"]["kernel"].shape) == (4, 4, 3, D)
+  assert tuple(blk["Dense_0"]["kernel"].shape) == (12, D, 6 * D)
+  assert tuple(blk["MultiHeadDotProductAttention_0"]["query"]["kernel"].shape) == (12, D, H, 64)
+  assert tuple(blk["MultiHeadDotProductAttention_0"]["out"]["kernel"].shape) == (12, H, 64, D)
+  assert tuple(blk["MlpBlock_0"]["Dense_1"]["kernel"].shape) == (12, 4 * D, D)
+  assert tuple(tree["Decoder"]["encoder_norm"]["scale"].shape) == (D,)
+  assert tuple(tree["final_modulation"]["kernel"].shape) == (D, 2 * D)
+  assert tuple(tree["final_conv"]["kernel"].shape) == (4, 4, D, 6)
+  assert tuple(tree["label_emb"]["embedding"]["embedding"].shape) == (11, D)
+  # zero-init leaves (vit.py:71, ae.py:94) and identity LayerNorm
+  assert float(blk["Dense_0"]["kernel"].abs().max()) == 0 and float(tree["final_modulation"]["kernel"].abs().max()) == 0
+  assert float(blk["LayerNorm_0"]["scale"].min()) == 1
+  # leaves are views: writing the tree writes the arena; a re-named scan block still packs (flax-version dependent name)
+  tree["cls"].fill_(2.0)
+  lf = lay.by_path[("cls",)]
+  assert float(tree.arena[lf.offset]) == 2.0
+  plain = {k: v for k, v in tree.items()}
+  plain["Encoder"] = {"SomeOtherScanName_0": tree["Encoder"]["ScanCheckpointEncoder1DBlock_0"],
+                      "encoder_norm": tree["Encoder"]["encoder_norm"]}
+  again = arena_from_tree(lay, plain, "cpu")
+  assert torch.equal(again, tree.arena)
+  with pytest.raises(ValueError):
+    bad = dict(plain); bad["cls"] = torch.zeros(1, 3, D)
+    arena_from_tree(lay, bad, "cpu")
+
+
+def test_weight_decay_flags_follow_no_decay_list():
+  cfg = make_model_config(variant="S/4", adaln=True)
+  lay = ArenaLayout(cfg)
+  dec = {"/".join(lf.path): lay.decay(lf) for lf in lay.leaves}
+  assert dec["cls"] is False and dec["image_mask_embedding"] is False and dec["pos_embedding"] is True
+  assert dec["Encoder/ScanCheckpointEncoder1DBlock_0/LayerNorm_0/scale"] is True      # LN scale IS decayed (a17)
+  assert dec["Encoder/ScanCheckpointEncoder1DBlock_0/LayerNorm_0/bias"] is False
+  assert dec["final_conv/kernel"] is True and dec["final_conv/bias"] is False
+  flags = lay.wd_flags("cpu")
+  assert flags.numel() * 64 == lay.total
+  for lf in lay.leaves:
+    assert int(flags[lf.offset // 64]) == int(lay.decay(lf))
+  # buckets partition the arena in backward order: decoder side, encoder, embeddings
+  b = lay.bucket_bounds
+  assert len(b) == 3 and b[0][0] == 0 and b[0][1] == b[1][0] and b[1][1] == b[2][0] and b[2][1] == lay.total
+
+
+# ------------------------------------------------------------------------------------------ sharding.py
+def test_infer_sharding_strategies():
+  mesh = Mesh(list(range(8)), ("data",))
+  params = {"a": {"kernel": torch.zeros(768, 3072), "bias": torch.zeros(3072)}, "pos": torch.zeros(1, 256, 768),
+            "odd": torch.zeros(1001, 769)}
+  rep = infer_sharding(params, mesh, "data", "replicated", {})
+  assert rep == {"a": {"kernel": PartitionSpec(), "bias": PartitionSpec()}, "pos": PartitionSpec(), "odd": PartitionSpec()}
+  fs = infer_sharding(params, mesh, "data", "fully_sharded", {})
+  assert fs["a"]["kernel"] == PartitionSpec(None, "data")     # largest divisible dim (sharding.py:70-76)
+  assert fs["a"]["bias"] == PartitionSpec()                   # below the 2**18 threshold
+  assert fs["pos"] == PartitionSpec()
+  assert fs["odd"] == PartitionSpec()                         # no dim divisible by 8
+  with pytest.raises(KeyError):
+    infer_sharding(params, mesh, "data", "nope", {})
+
+
+def test_batch_partition_rules():
+  assert local_batch_slice(4096, 3, 8) == slice(1536, 2048)
+  with pytest.raises(ValueError, match="divisible"):
+    check_batch_divisible(100, 8)
