@@ -41,7 +41,9 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging: one [32 rows][64 bf16] swizzled chunk per epilogue warp, drained by TMA stores
+  static constexpr int STAGE_OUT_BYTES = (BN >= 128) ? 8 * 4096 : 0;
+  static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGE_OUT_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_tanh(float u) {
@@ -79,19 +81,26 @@ __device__ __forceinline__ WorkItem decode_item(long long item, int n_tiles, int
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+            const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
+  uint8_t* smem_out = smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_out + Cfg::STAGE_OUT_BYTES);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* aux_bar = bars + 2 * STAGES + 4;      // [8] one per epilogue warp (DGELU operand tiles)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
+  // bf16 results leave through swizzled shared memory and TMA stores (full 128-byte lines, M/N tails clipped by
+  // the tensor map) instead of one 16-byte store per lane per row
+  constexpr bool STAGED = (BN >= 128) && (EPI == UMD_EPI_BF16 || EPI == UMD_EPI_GELU || EPI == UMD_EPI_DGELU);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +108,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (STAGED) {
+      tma_prefetch_desc(&tmO0);
+      if (EPI == UMD_EPI_GELU) tma_prefetch_desc(&tmO1);
+      if (EPI == UMD_EPI_DGELU) tma_prefetch_desc(&tmAux);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -109,6 +123,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 8);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -207,6 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int half = ew >> 2;           // which half of the BN columns
     constexpr int HALF_COLS = BN / 2;
+    uint32_t aux_uses = 0;
     int it = 0;
     for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
       const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
@@ -222,6 +238,91 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int sample = 0;
       if (EPI == UMD_EPI_GATE_RES && p.gate && row_ok) sample = sample_of(p.rmap, row);
 
+      if constexpr (STAGED) {
+        uint8_t* sbuf = smem_out + ew * 4096;
+        const int srow = quad * 32 + lane;
+        uint8_t* my_row = sbuf + lane * 128;
+        const int sw = lane & 7;
+        const int trow = m0 + quad * 32;   // first row of this warp's 32-row slab
+#pragma unroll 1
+        for (int c = 0; c < HALF_COLS; c += 64) {
+          const int col0 = n0 + half * HALF_COLS + c;
+          const bool active = col0 < p.N;  // warp-uniform
+          if (EPI == UMD_EPI_DGELU && active && lane == 0) {
+            bulk_wait_read<0>();
+            mbar_expect_tx(&aux_bar[ew], 4096);
+            tma_load_3d(sbuf, &tmAux, &aux_bar[ew], col0, trow, 0);
+          }
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_row + c, r0);
+          tmem_ld_32x32(t_row + c + 32, r1);
+          tmem_ld_wait();
+          if (active) {
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r0[j]);
+              v[32 + j] = __uint_as_float(r1[j]);
+            }
+            if (EPI != UMD_EPI_DGELU && bias) {
+#pragma unroll
+              for (int j = 0; j < 64; j += 4) {
+                if (col0 + j < p.N) {
+                  const float4 bv = *reinterpret_cast<const float4*>(bias + col0 + j);
+                  v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+                }
+              }
+            }
+            if (EPI == UMD_EPI_DGELU) {
+              mbar_wait(&aux_bar[ew], (aux_uses++) & 1);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 uu = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
+                const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  v[8 * j + 2 * q] *= gelu_tanh_grad(bf16_lo(uw[q]));
+                  v[8 * j + 2 * q + 1] *= gelu_tanh_grad(bf16_hi(uw[q]));
+                }
+              }
+            } else {
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmO0, sbuf, col0, trow, b);
+              bulk_commit();
+            }
+            if (EPI == UMD_EPI_GELU) {
+              if (lane == 0) bulk_wait_read<0>();
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float g[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) g[q] = gelu_tanh(v[8 * j + q]);
+                *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
+                    make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmO1, sbuf, col0, trow, b);
+                bulk_commit();
+              }
+            }
+          }
+          (void)srow;
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < HALF_COLS; c += 32) {
         uint32_t r[32];
@@ -335,10 +436,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }  // row_ok && col0 < N
         __syncwarp();
       }
+      }  // !STAGED
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (STAGED && lane == 0) bulk_wait<0>();  // the staging buffer must outlive the last TMA store's read
+    (void)aux_uses;
   }
 
   __syncwarp();
@@ -356,7 +460,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 extern long long g_launch_count;
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm_t(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
+  const CUtensorMap &tmA = tm[0], &tmB = tm[1];
   using Cfg = GemmCfg<BN>;
   auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
   static bool configured = false;
@@ -367,27 +472,26 @@ static int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   const int m_tiles = ceil_div(p.M, BM), n_tiles = ceil_div(p.N, BN);
   long long items = static_cast<long long>(m_tiles) * n_tiles * p.split_k * p.batch;
   int grid = static_cast<int>(items < sm_count() ? items : sm_count());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tm[2], tm[3], tm[4], p);
   ++g_launch_count;
   UMD_CHECK_CUDA(cudaGetLastError());
   return UMD_OK;
 }
 
 template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                           cudaStream_t s) {
+static int launch_gemm_epi(int epi, const CUtensorMap* tm, const GemmParams& p, cudaStream_t s) {
   switch (epi) {
-    case UMD_EPI_BF16: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_BF16>(tmA, tmB, p, s);
-    case UMD_EPI_F32: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_F32>(tmA, tmB, p, s);
-    case UMD_EPI_ATOMIC: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_ATOMIC>(tmA, tmB, p, s);
+    case UMD_EPI_BF16: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_BF16>(tm, p, s);
+    case UMD_EPI_F32: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_F32>(tm, p, s);
+    case UMD_EPI_ATOMIC: return launch_gemm_t<BN, A_MN, B_MN, UMD_EPI_ATOMIC>(tm, p, s);
     default: break;
   }
   if (!A_MN) {
     // fused activation tails only exist for activations-as-A (forward / dgrad) GEMMs
     switch (epi) {
-      case UMD_EPI_GELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GELU>(tmA, tmB, p, s);
-      case UMD_EPI_GATE_RES: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GATE_RES>(tmA, tmB, p, s);
-      case UMD_EPI_DGELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_DGELU>(tmA, tmB, p, s);
+      case UMD_EPI_GELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GELU>(tm, p, s);
+      case UMD_EPI_GATE_RES: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GATE_RES>(tm, p, s);
+      case UMD_EPI_DGELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_DGELU>(tm, p, s);
       default: break;
     }
   }
@@ -396,11 +500,10 @@ static int launch_gemm_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& t
 }
 
 template <int BN>
-static int launch_gemm_bn(bool a_mn, bool b_mn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                          const GemmParams& p, cudaStream_t s) {
-  if (!a_mn && b_mn) return launch_gemm_epi<BN, false, true>(epi, tmA, tmB, p, s);
-  if (!a_mn && !b_mn) return launch_gemm_epi<BN, false, false>(epi, tmA, tmB, p, s);
-  if (a_mn && b_mn) return launch_gemm_epi<BN, true, true>(epi, tmA, tmB, p, s);
+static int launch_gemm_bn(bool a_mn, bool b_mn, int epi, const CUtensorMap* tm, const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && b_mn) return launch_gemm_epi<BN, false, true>(epi, tm, p, s);
+  if (!a_mn && !b_mn) return launch_gemm_epi<BN, false, false>(epi, tm, p, s);
+  if (a_mn && b_mn) return launch_gemm_epi<BN, true, true>(epi, tm, p, s);
   set_error("umd_gemm_bf16: A MN-major with B K-major is not instantiated");
   return UMD_ERR_UNSUPPORTED;
 }
@@ -437,7 +540,8 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   else if (a.N <= 128) bn = 128;
   else if (a.N % 256 != 0 && a.N % 128 == 0 && a.N < 1024) bn = 128;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tm[5];
+  CUtensorMap &tmA = tm[0], &tmB = tm[1];
   const uint64_t a_batch = p.a_bcast ? 1 : a.batch, b_batch = p.b_bcast ? 1 : a.batch;
   if (!a.a_mn) UMD_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a_batch, a.lda, a.a_bs, BM));
   else         UMD_TRY(make_tmap_bf16(&tmA, a.A, a.M, a.K, a_batch, a.lda, a.a_bs, BK));
@@ -445,11 +549,27 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   else if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, bn));
   else         UMD_TRY(make_tmap_bf16(&tmB, a.B, a.N, a.K, b_batch, a.ldb, a.b_bs, BK));
 
+  tm[2] = tm[3] = tm[4] = tmA;  // placeholders for the epilogues that do not use them
+  if (bn >= 128 && (a.epi == UMD_EPI_BF16 || a.epi == UMD_EPI_GELU || a.epi == UMD_EPI_DGELU)) {
+    UMD_REQUIRE(a.out0 && (reinterpret_cast<uintptr_t>(a.out0) & 15) == 0 && a.ld0 % 8 == 0 && a.bs0 % 8 == 0,
+                "umd_gemm_bf16: bf16 outputs must be 16-byte aligned with ld0 / bs0 multiples of 8");
+    UMD_TRY(make_tmap_bf16(&tm[2], a.out0, a.N, a.M, a.batch, a.ld0, a.bs0, 32));
+    if (a.epi == UMD_EPI_GELU) {
+      UMD_REQUIRE(a.out1 && (reinterpret_cast<uintptr_t>(a.out1) & 15) == 0 && a.ld1 % 8 == 0 && a.batch == 1,
+                  "umd_gemm_bf16: GELU epilogue needs an aligned out1 with ld1 %% 8 == 0 and batch 1");
+      UMD_TRY(make_tmap_bf16(&tm[3], a.out1, a.N, a.M, 1, a.ld1, 0, 32));
+    }
+    if (a.epi == UMD_EPI_DGELU) {
+      UMD_REQUIRE(a.aux && (reinterpret_cast<uintptr_t>(a.aux) & 15) == 0 && a.ldaux % 8 == 0 && a.batch == 1,
+                  "umd_gemm_bf16: DGELU epilogue needs an aligned aux with ldaux %% 8 == 0 and batch 1");
+      UMD_TRY(make_tmap_bf16(&tm[4], a.aux, a.N, a.M, 1, a.ldaux, 0, 32));
+    }
+  }
   ProfScope prof(a.a_mn ? PC_GEMM_WGRAD : PC_GEMM, 2.0 * a.M * static_cast<double>(a.N) * a.K * a.batch, stream);
   switch (bn) {
-    case 256: return launch_gemm_bn<256>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
-    case 128: return launch_gemm_bn<128>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
-    default: return launch_gemm_bn<64>(a.a_mn, a.b_mn, a.epi, tmA, tmB, p, stream);
+    case 256: return launch_gemm_bn<256>(a.a_mn, a.b_mn, a.epi, tm, p, stream);
+    case 128: return launch_gemm_bn<128>(a.a_mn, a.b_mn, a.epi, tm, p, stream);
+    default: return launch_gemm_bn<64>(a.a_mn, a.b_mn, a.epi, tm, p, stream);
   }
 }
 
