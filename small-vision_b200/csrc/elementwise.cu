@@ -63,9 +63,33 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_kernel(LnFwdArgs a) {
   const float* xp = a.x + static_cast<long long>(in_row) * D;
   float4 v[NV];
   float s = 0.f, s2 = 0.f;
+  if (a.res_branch || a.cond_row || a.x_out) {
+    if (a.gather_L <= 0) sample = sample_of(a.rm, r);
+    const bool is_cond = a.cond_row && token_of(a.rm, in_row) == 0;
+    const __nv_bfloat16* bp = a.res_branch ? a.res_branch + static_cast<long long>(in_row) * D : nullptr;
+    const float* gp = a.res_gate ? a.res_gate + static_cast<long long>(sample) * a.ldgate : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane * 4 + 128 * i;
+      if (is_cond) {
+        v[i] = *reinterpret_cast<const float4*>(a.cond_row + static_cast<long long>(sample) * D + c);
+      } else {
+        v[i] = *reinterpret_cast<const float4*>(xp + c);
+        if (bp) {
+          const float4 bv = load_row4(bp + c);
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (gp) g = *reinterpret_cast<const float4*>(gp + c);
+          v[i].x += g.x * bv.x; v[i].y += g.y * bv.y; v[i].z += g.z * bv.z; v[i].w += g.w * bv.w;
+        }
+      }
+      if (a.x_out) *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(in_row) * D + c) = v[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xp + lane * 4 + 128 * i);
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    v[i] = *reinterpret_cast<const float4*>(xp + lane * 4 + 128 * i);
     s += v[i].x + v[i].y + v[i].z + v[i].w;
     s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
   }
@@ -119,7 +143,8 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
   if (a.rows_out <= 0) return UMD_OK;
   UMD_REQUIRE(D % 128 == 0 && D <= 1024, "ln_mod_fwd: width %d unsupported", D);
   // algorithmic bytes: fp32 row in, bf16/fp32 row out
-  ProfScope prof(PC_LN_FWD, static_cast<double>(a.rows_out) * D * (4 + (out_bf16 ? 2 : 4)), st);
+  ProfScope prof(PC_LN_FWD, static_cast<double>(a.rows_out) * D *
+                     (4 + (out_bf16 ? 2 : 4) + (a.res_branch ? 2 : 0) + (a.x_out ? 4 : 0)), st);
   return out_bf16 ? ln_fwd_dispatch<__nv_bfloat16>(a, D, st) : ln_fwd_dispatch<float>(a, D, st);
 }
 

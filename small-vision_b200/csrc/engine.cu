@@ -36,7 +36,7 @@ struct LayerBufs {
 };
 
 struct Stack {
-  int depth, rows, nsamples;
+  int depth, rows, nsamples, D;
   RowMap rm;
   int base;                 // leaf id base (UMD_P_ENC_BASE / UMD_P_DEC_BASE)
   float* ada;               // [B, depth*6D] fp32 or null
@@ -74,6 +74,7 @@ void carve_stack(Bump& b, Stack& s, const Plan& P, int depth, int rows, int nsam
                  bool train) {
   s.depth = depth; s.rows = rows; s.nsamples = nsamples; s.rm = rm; s.base = base;
   const int D = P.D;
+  s.D = D;
   s.ada = P.adaln ? b.take<float>(static_cast<long long>(P.B) * depth * 6 * D) : nullptr;
   s.dada = (P.adaln && train) ? b.take<float>(static_cast<long long>(P.B) * depth * 6 * D) : nullptr;
   s.dada_bf16 = (P.adaln && train) ? b.take<bf16>(static_cast<long long>(P.B) * depth * 6 * D) : nullptr;
@@ -108,6 +109,7 @@ int make_plan(Plan& P, const umd_model_cfg& c, const umd_step_shape& sh, void* w
   UMD_REQUIRE(c.width % 128 == 0 && c.width <= 1024, "width %d must be a multiple of 128 and <= 1024", c.width);
   UMD_REQUIRE(c.width % c.heads == 0 && c.width / c.heads == 64, "head dim must be 64 (width %d, heads %d)", c.width, c.heads);
   UMD_REQUIRE(c.img_size % c.patch == 0, "img_size %d not divisible by patch %d", c.img_size, c.patch);
+  UMD_REQUIRE(c.depth >= 1 && c.dec_depth >= 1, "depth %d / dec_depth %d must be at least 1", c.depth, c.dec_depth);
   UMD_REQUIRE(sh.n0 >= 0 && sh.n1 >= 0 && sh.n0 + sh.n1 > 0, "empty batch");
   P.B = sh.n0 + sh.n1; P.D = c.width; P.H = c.heads; P.Dh = c.width / c.heads;
   P.M4 = c.mlp_dim > 0 ? c.mlp_dim : 4 * c.width;
@@ -270,6 +272,17 @@ int cond_forward(Ctx& c, const umd_io& io) {
 // ------------------------------------------------------------------------------------------
 // Encoder1DBlock stack forward (vit.py:60-163)
 // ------------------------------------------------------------------------------------------
+// The residual update that closes block l, x[l+1] = xmid[l] + gate1[l] * z[l] (vit.py:106-108), is not run as a
+// pass of its own: the LayerNorm that consumes x[l+1] performs it on the way in and writes x[l+1] to x_out.
+void pending_residual(LnFwdArgs& ln, const Stack& s, int l, float* x_out) {
+  const LayerBufs& lb = s.L[l];
+  ln.x = lb.xmid;
+  ln.res_branch = lb.z;
+  ln.res_gate = s.ada ? s.ada + static_cast<long long>(l) * 6 * s.D + 5 * s.D : nullptr;
+  ln.ldgate = static_cast<long long>(s.depth) * 6 * s.D;
+  ln.x_out = x_out;
+}
+
 int stack_forward(Ctx& c, Stack& s) {
   Plan& P = c.P;
   const int D = P.D, T = s.rows, M4 = P.M4;
@@ -282,10 +295,17 @@ int stack_forward(Ctx& c, Stack& s) {
   for (int l = 0; l < s.depth; ++l) {
     LayerBufs& lb = s.L[l];
     const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
-    if (!P.adaln) UMD_TRY(set_cond_row(s.x[l], P.cond, s.rm, s.nsamples, D, c.st));
     LnFwdArgs ln;
     memset(&ln, 0, sizeof(ln));
-    ln.x = s.x[l]; ln.gamma = c.W(s.base + UMD_S_LN0_S, static_cast<long long>(l) * D);
+    // LayerNorm_0 (+ modulate); for l > 0 it first forms x[l] = xmid[l-1] + gate1[l-1] * z[l-1] (vit.py:106-108),
+    // and for adaln=False it plants the conditioning token in row 0 of every sample (vit.py:73-74)
+    if (l == 0) {
+      ln.x = s.x[0];
+    } else {
+      pending_residual(ln, s, l - 1, s.x[l]);
+    }
+    if (!P.adaln) { ln.cond_row = P.cond; ln.x_out = s.x[l]; }
+    ln.gamma = c.W(s.base + UMD_S_LN0_S, static_cast<long long>(l) * D);
     ln.beta = c.W(s.base + UMD_S_LN0_B, static_cast<long long>(l) * D);
     ln.shift = ada; ln.scale = ada ? ada + D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
     ln.out = lb.y0; ln.mean = lb.mean0; ln.rstd = lb.rstd0; ln.rows_out = T;
@@ -302,18 +322,20 @@ int stack_forward(Ctx& c, Stack& s) {
     at.scale = 1.0f / sqrtf(static_cast<float>(P.Dh));
     UMD_TRY(attention_fwd(at, c.st));
     UMD_TRY(dense_fwd(c, lb.o, T, D, c.WB(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D), D,
-                      c.W(s.base + UMD_S_O_B, static_cast<long long>(l) * D), UMD_EPI_GATE_RES, lb.a, lb.xmid, s.x[l],
-                      ada ? ada + 2 * D : nullptr, ldada, &s.rm));
-    ln.x = lb.xmid; ln.gamma = c.W(s.base + UMD_S_LN1_S, static_cast<long long>(l) * D);
+                      c.W(s.base + UMD_S_O_B, static_cast<long long>(l) * D), UMD_EPI_BF16, lb.a));
+    // LayerNorm_1 (+ modulate) on xmid = x[l] + gate0 * a (vit.py:89-98)
+    memset(&ln, 0, sizeof(ln));
+    ln.x = s.x[l]; ln.res_branch = lb.a; ln.res_gate = ada ? ada + 2 * D : nullptr; ln.ldgate = ldada; ln.x_out = lb.xmid;
+    ln.gamma = c.W(s.base + UMD_S_LN1_S, static_cast<long long>(l) * D);
     ln.beta = c.W(s.base + UMD_S_LN1_B, static_cast<long long>(l) * D);
-    ln.shift = ada ? ada + 3 * D : nullptr; ln.scale = ada ? ada + 4 * D : nullptr;
-    ln.out = lb.y1; ln.mean = lb.mean1; ln.rstd = lb.rstd1;
+    ln.shift = ada ? ada + 3 * D : nullptr; ln.scale = ada ? ada + 4 * D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
+    ln.out = lb.y1; ln.mean = lb.mean1; ln.rstd = lb.rstd1; ln.rows_out = T;
     UMD_TRY(ln_mod_fwd(ln, D, true, c.st));
     UMD_TRY(dense_fwd(c, lb.y1, T, D, c.WB(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4), M4,
                       c.W(s.base + UMD_S_FC1_B, static_cast<long long>(l) * M4), UMD_EPI_GELU, lb.u, lb.g));
     UMD_TRY(dense_fwd(c, lb.g, T, M4, c.WB(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D), D,
-                      c.W(s.base + UMD_S_FC2_B, static_cast<long long>(l) * D), UMD_EPI_GATE_RES, lb.z, s.x[l + 1], lb.xmid,
-                      ada ? ada + 5 * D : nullptr, ldada, &s.rm));
+                      c.W(s.base + UMD_S_FC2_B, static_cast<long long>(l) * D), UMD_EPI_BF16, lb.z));
+    // x[l+1] = xmid + gate1 * z is formed by whichever LayerNorm reads it next (pending_residual)
   }
   return UMD_OK;
 }
@@ -478,7 +500,8 @@ int engine_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const 
   {  // encoder_norm (vit.py:163), fp32 out
     LnFwdArgs ln;
     memset(&ln, 0, sizeof(ln));
-    ln.x = P.enc.x[P.enc.depth]; ln.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); ln.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
+    pending_residual(ln, P.enc, P.enc.depth - 1, P.enc.x[P.enc.depth]);
+    ln.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); ln.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
     ln.rm = P.enc.rm; ln.out = P.enc.xf; ln.mean = P.enc.meanf; ln.rstd = P.enc.rstdf; ln.rows_out = P.Te;
     UMD_TRY(ln_mod_fwd(ln, D, false, st));
   }
@@ -487,7 +510,8 @@ int engine_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const 
   {  // decoder encoder_norm + drop the rep row + final modulation (ae.py:163-170) -> bf16 GEMM operand
     LnFwdArgs ln;
     memset(&ln, 0, sizeof(ln));
-    ln.x = P.dec.x[P.dec.depth]; ln.gamma = c.W(UMD_P_DEC_BASE + UMD_S_NORM_S); ln.beta = c.W(UMD_P_DEC_BASE + UMD_S_NORM_B);
+    pending_residual(ln, P.dec, P.dec.depth - 1, P.dec.x[P.dec.depth]);
+    ln.gamma = c.W(UMD_P_DEC_BASE + UMD_S_NORM_S); ln.beta = c.W(UMD_P_DEC_BASE + UMD_S_NORM_B);
     ln.shift = P.fmod; ln.scale = P.fmod ? P.fmod + D : nullptr; ln.ldmod = 2 * D; ln.rm = P.dec.rm;
     ln.out = P.xm; ln.mean = P.meanF; ln.rstd = P.rstdF; ln.rows_out = B * P.L; ln.gather_L = P.L; ln.gather_off = P.tok0 + 1;
     UMD_TRY(ln_mod_fwd(ln, D, true, st));

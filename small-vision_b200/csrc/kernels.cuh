@@ -22,6 +22,14 @@ struct LnFwdArgs {
   int rows_out;
   int gather_L;            // >0: out row (n, j<gather_L) reads x row (n, gather_off + j)
   int gather_off;
+  // Optional fused residual update (vit.py:89-94,106-108) in front of the LayerNorm:
+  //   x_new = x + res_gate[sample] * res_branch   (res_gate null = 1),   written to x_out (may alias x)
+  const __nv_bfloat16* res_branch;  // [rows_in, D] or null
+  const float* res_gate;            // per-sample rows (stride ldgate) or null
+  long long ldgate;
+  float* x_out;                     // [rows_in, D] or null
+  // adaln=False (vit.py:73-74): token 0 of every sample is replaced by cond_row[sample] before the norm
+  const float* cond_row;            // [nsamples, D] or null
 };
 int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st);
 
