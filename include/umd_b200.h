@@ -116,6 +116,8 @@ int umd_attention_bwd_simt(const void* qkv_bf16, const void* out_bf16, const voi
 int umd_ln_modulate_fwd(const float* x, const float* gamma, const float* beta, const float* shift, const float* scale,
                         long long ldmod, int n0, int s0, int n1, int s1, int D, void* out, int out_is_bf16, float* mean,
                         float* rstd, umd_stream_t stream);
+/* backward: dx is written (accumulate = 0) or += (accumulate = 1); dshift, dscale (per sample), dgamma, dbeta are
+ * accumulated with atomic adds — zero them first */
 int umd_ln_modulate_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
                         const float* gamma, const float* beta, const float* scale, long long ldmod, int n0, int s0,
                         int n1, int s1, int D, float* dx, int accumulate, float* dshift, float* dscale, long long ldd,

@@ -15,8 +15,9 @@
 //             dK_j += dS^T Q_i (K-major A) and dQ_i += dS K_j (the same tile read as an MN-major A) accumulate
 //             in TMEM; dK/dV leave after the query loop, dQ after the key loop.
 //
-// Warp roles (256 threads): warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator,
-// warps 4..7 softmax / epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
+// Warp roles (384 threads): warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator,
+// warps 4..11 softmax / epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the score columns, so
+// every SM sub-partition runs two softmax warps (latency hiding) and each row's work is split over two threads.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -31,7 +32,8 @@ constexpr int AT_DH = 64;
 constexpr int AT_MAX_S = 272;
 constexpr int AT_ROW = 128;            // bytes per 64-element bf16 row
 constexpr int AT_SLAB = 128 * AT_ROW;  // [128 rows][64 cols] bf16 = 16 KB
-constexpr int AT_THREADS = 256;
+constexpr int AT_THREADS = 384;         // 4 control warps + 8 softmax warps (two per TMEM lane quadrant)
+constexpr int AT_SM_THREADS = 256;      // softmax / epilogue threads
 constexpr int AT_STAT_N = 384;         // per-query statistics padded to three 128-query tiles
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -41,7 +43,7 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // 16-byte chunk `chunk` (0..7) of row r of a [rows][64] bf16 slab in the 128B-swizzled layout TMA / UMMA use.
 __device__ __forceinline__ void st_swz(uint8_t* slab, int r, int chunk, uint4 v) {
@@ -51,7 +53,9 @@ __device__ __forceinline__ void st_swz(uint8_t* slab, int r, int chunk, uint4 v)
 __device__ __forceinline__ void load_rows(uint8_t* dst, const CUtensorMap* tm128, const CUtensorMap* tm16, uint64_t* bar,
                                           int col, int row0, int rows) {
   int r = 0;
+#pragma unroll 1
   for (; r + 128 <= rows; r += 128) tma_load_3d(dst + r * AT_ROW, tm128, bar, col, row0 + r, 0);
+#pragma unroll 1
   for (; r < rows; r += 16) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, row0 + r, 0);
 }
 
@@ -77,7 +81,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint8_t* sK = sQ + nqt * 128 * AT_ROW;   // SP rows
   uint8_t* sV = sK + SP * AT_ROW;          // SP rows
   uint8_t* sP = sV + SP * AT_ROW;          // nslab slabs [128 q][64 kv]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + nslab * AT_SLAB);
+  float* sMax = reinterpret_cast<float*>(sP + nslab * AT_SLAB);    // [2 halves][128 rows]
+  float* sSum = sMax + 256;                                        // [2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);
   uint64_t* bar_kv = bars + 0;
   uint64_t* bar_s = bars + 1;
   uint64_t* bar_p = bars + 2;
@@ -93,9 +99,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   if (warp == 1 && lane == 0) {
     mbar_init(bar_kv, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, 128);
+    mbar_init(bar_p, AT_SM_THREADS);
     mbar_init(bar_o, 1);
-    mbar_init(bar_free, 128);
+    mbar_init(bar_free, AT_SM_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -145,16 +151,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
     const int quad = warp & 3;
+    const int hf = (warp - 4) >> 2;  // which half of the score columns (and of the 64 output columns)
     const int r = quad * 32 + lane;  // row inside the query tile = TMEM lane
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const float sl2 = p.scale_log2;
+    const int csplit = ((SP >> 4) + 1) / 2 * 16;          // columns [0, csplit) -> half 0, [csplit, SP) -> half 1
+    const int cb = hf ? csplit : 0, ce = hf ? SP : csplit;
     for (int i = 0; i < nqt; ++i) {
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
-      // pass 1: row maximum of the raw logits
+      // pass 1: maximum of the raw logits over this thread's columns
       float m = -INFINITY;
-      for (int c = 0; c < SP; c += 32) {
-        if (c + 32 <= SP) {
+      for (int c = cb; c < ce; c += 32) {
+        if (c + 32 <= ce) {
           uint32_t v[32];
           tmem_ld_32x32(t_lane + c, v);
           tmem_ld_wait();
@@ -173,12 +182,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           for (int j = 0; j < 16; ++j) m = fmaxf(m, (c + j < S) ? __uint_as_float(v[j]) : -INFINITY);
         }
       }
+      sMax[hf * 128 + r] = m;
+      bar_softmax();
+      m = fmaxf(m, sMax[(hf ^ 1) * 128 + r]);
       const float ms = m * sl2;
-      // pass 2: p = exp2(s * scale*log2e - max), row sum, bf16 P -> shared memory
+      // pass 2: p = exp2(s * scale*log2e - max), partial row sum, bf16 P -> shared memory
       float sum = 0.f;
-      for (int c = 0; c < SP; c += 32) {
+      for (int c = cb; c < ce; c += 32) {
         uint32_t v[32];
-        const bool full = (c + 32 <= SP);
+        const bool full = (c + 32 <= ce);
         if (full) {
           tmem_ld_32x32(t_lane + c, v);
         } else {
@@ -190,8 +202,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
           for (int j = 16; j < 32; ++j) v[j] = 0;
         }
         tmem_ld_wait();
-        uint8_t* slab = sP + (c >> 6) * AT_SLAB;
-        const int chunk0 = (c & 63) >> 3;
+        const bool nomask = (c + 32 <= S);
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           if (full || j < 16) {
@@ -199,29 +210,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const float x = ex2(__uint_as_float(v[j + q]) * sl2 - ms);
-              e[q] = (c + j + q < S) ? x : 0.f;
+              e[q] = (nomask || c + j + q < S) ? x : 0.f;
               sum += e[q];
             }
-            st_swz(slab, r, chunk0 + (j >> 3),
+            const int cc = c + j;
+            st_swz(sP + (cc >> 6) * AT_SLAB, r, (cc & 63) >> 3,
                    make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7])));
           }
         }
       }
+      sSum[hf * 128 + r] = sum;
       fence_proxy_async();
       mbar_arrive(bar_p);
-      // epilogue: O / rowsum
+      // epilogue: O / rowsum; each half owns 32 of the 64 output columns
       mbar_wait(bar_o, i & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32(t_lane + p.o_col, o0);
-      tmem_ld_32x32(t_lane + p.o_col + 32, o1);
+      uint32_t o0[32];
+      tmem_ld_32x32(t_lane + p.o_col + 32 * hf, o0);
       tmem_ld_wait();
       tc_fence_before();
+      bar_softmax();                     // partial sums of both halves are visible
+      sum += sSum[(hf ^ 1) * 128 + r];
       mbar_arrive(bar_free);
       const int row = i * 128 + r;
       if (row < S) {
         const float inv = 1.f / sum;
-        __nv_bfloat16* op = p.out + static_cast<long long>(row0 + row) * D + h * AT_DH;
+        __nv_bfloat16* op = p.out + static_cast<long long>(row0 + row) * D + h * AT_DH + 32 * hf;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           *reinterpret_cast<uint4*>(op + j) = make_uint4(
@@ -230,15 +244,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
               pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
               pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
         }
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          *reinterpret_cast<uint4*>(op + 32 + j) = make_uint4(
-              pack_bf16x2(__uint_as_float(o1[j]) * inv, __uint_as_float(o1[j + 1]) * inv),
-              pack_bf16x2(__uint_as_float(o1[j + 2]) * inv, __uint_as_float(o1[j + 3]) * inv),
-              pack_bf16x2(__uint_as_float(o1[j + 4]) * inv, __uint_as_float(o1[j + 5]) * inv),
-              pack_bf16x2(__uint_as_float(o1[j + 6]) * inv, __uint_as_float(o1[j + 7]) * inv));
-        }
-        if (p.lse) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
+        if (p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
       }
     }
   }
@@ -306,12 +312,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     mbar_init(bar_ld, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_sfree[i], 128);
-      mbar_init(&bar_p[i], 128);
+      mbar_init(&bar_sfree[i], AT_SM_THREADS);
+      mbar_init(&bar_p[i], AT_SM_THREADS);
     }
     mbar_init(bar_tfree, 1);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, 128);
+    mbar_init(bar_accfree, AT_SM_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -397,11 +403,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax backward + epilogues
     const int quad = warp & 3;
+    const int hf = (warp - 4) >> 2;  // which 32 of the 64 columns of a score half / of an output tile
     const int r = quad * 32 + lane;  // key row inside the key tile (TMEM lane); query row in the dQ epilogue
     const int tid = threadIdx.x - 128;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     // delta = rowsum(dO * O), lse in log2 units
-    for (int q = tid; q < SP; q += 128) {
+    for (int q = tid; q < SP; q += AT_SM_THREADS) {
       float dl = 0.f, l2 = 0.f;
       if (q < S) {
         const uint4* po = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(row0 + q) * D + h * AT_DH);
@@ -431,36 +438,35 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           const int b = step % nbuf, u = step / nbuf;
           mbar_wait(&bar_s[b], u & 1);
           tc_fence_after();
-          uint32_t s0[32], s1[32], d0[32], d1[32];
-          tmem_ld_32x32(t_lane + b * 128, s0);
-          tmem_ld_32x32(t_lane + b * 128 + 32, s1);
-          tmem_ld_32x32(t_lane + b * 128 + 64, d0);
-          tmem_ld_32x32(t_lane + b * 128 + 96, d1);
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32(t_lane + b * 128 + 32 * hf, sv);
+          tmem_ld_32x32(t_lane + b * 128 + 64 + 32 * hf, dv);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&bar_sfree[b]);
           if (hh == 0 && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
-          const int q0 = i * 128 + hh * 64;
+          const int q0 = i * 128 + hh * 64 + 32 * hf;
           uint8_t* slabP = sPt + hh * AT_SLAB;
           uint8_t* slabS = sdSt + hh * AT_SLAB;
 #pragma unroll
-          for (int c = 0; c < 64; c += 8) {
+          for (int c = 0; c < 32; c += 8) {
             float pe[8], de[8];
+            const float4 la = *reinterpret_cast<const float4*>(&sLse[q0 + c]);
+            const float4 lb = *reinterpret_cast<const float4*>(&sLse[q0 + c + 4]);
+            const float4 da = *reinterpret_cast<const float4*>(&sDelta[q0 + c]);
+            const float4 db = *reinterpret_cast<const float4*>(&sDelta[q0 + c + 4]);
+            const float l2[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+            const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const int q = q0 + c + e;
-              const float sv = __uint_as_float(c + e < 32 ? s0[(c + e) & 31] : s1[(c + e) & 31]);
-              const float dv = __uint_as_float(c + e < 32 ? d0[(c + e) & 31] : d1[(c + e) & 31]);
-              const bool ok = kv_ok && (q < S);
-              const float l2 = sLse[q];
-              const float dl = sDelta[q];
-              const float pv = ex2(sv * sl2 - l2);
+              const bool ok = kv_ok && (q0 + c + e < S);
+              const float pv = ex2(__uint_as_float(sv[c + e]) * sl2 - l2[e]);
               pe[e] = ok ? pv : 0.f;
-              de[e] = ok ? pv * (dv - dl) : 0.f;
+              de[e] = ok ? pv * (__uint_as_float(dv[c + e]) - dl[e]) : 0.f;
             }
-            st_swz(slabP, r, c >> 3,
+            st_swz(slabP, r, 4 * hf + (c >> 3),
                    make_uint4(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7])));
-            st_swz(slabS, r, c >> 3,
+            st_swz(slabS, r, 4 * hf + (c >> 3),
                    make_uint4(pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7])));
           }
           fence_proxy_async();
@@ -468,28 +474,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
         }
         ++blk;
       }
-      // dK_j, dV_j
+      // dK_j, dV_j: each half owns 32 of the 64 head-dim columns
       mbar_wait(bar_acc, j & 1);
       tc_fence_after();
       {
         uint32_t a0[32], a1[32];
-        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + kv) * (3 * D) + h * AT_DH;
-        tmem_ld_32x32(t_lane + col_dv, a0);
-        tmem_ld_32x32(t_lane + col_dv + 32, a1);
-        tmem_ld_wait();
-        if (kv_ok) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            *reinterpret_cast<uint4*>(dst + 2 * D + c) = make_uint4(
-                pack_bf16x2(__uint_as_float(a0[c]), __uint_as_float(a0[c + 1])), pack_bf16x2(__uint_as_float(a0[c + 2]), __uint_as_float(a0[c + 3])),
-                pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7])));
-            *reinterpret_cast<uint4*>(dst + 2 * D + 32 + c) = make_uint4(
-                pack_bf16x2(__uint_as_float(a1[c]), __uint_as_float(a1[c + 1])), pack_bf16x2(__uint_as_float(a1[c + 2]), __uint_as_float(a1[c + 3])),
-                pack_bf16x2(__uint_as_float(a1[c + 4]), __uint_as_float(a1[c + 5])), pack_bf16x2(__uint_as_float(a1[c + 6]), __uint_as_float(a1[c + 7])));
-          }
-        }
-        tmem_ld_32x32(t_lane + col_dk, a0);
-        tmem_ld_32x32(t_lane + col_dk + 32, a1);
+        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + kv) * (3 * D) + h * AT_DH + 32 * hf;
+        tmem_ld_32x32(t_lane + col_dv + 32 * hf, a0);
+        tmem_ld_32x32(t_lane + col_dk + 32 * hf, a1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_accfree);
@@ -497,10 +489,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           const float sc = p.scale;
 #pragma unroll
           for (int c = 0; c < 32; c += 8) {
+            *reinterpret_cast<uint4*>(dst + 2 * D + c) = make_uint4(
+                pack_bf16x2(__uint_as_float(a0[c]), __uint_as_float(a0[c + 1])), pack_bf16x2(__uint_as_float(a0[c + 2]), __uint_as_float(a0[c + 3])),
+                pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7])));
             *reinterpret_cast<uint4*>(dst + D + c) = make_uint4(
-                pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
-                pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc));
-            *reinterpret_cast<uint4*>(dst + D + 32 + c) = make_uint4(
                 pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
                 pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc));
           }
@@ -509,22 +501,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     }
     // dQ_i (the last bar_acc phase covers every MMA issued)
     for (int i = 0; i < nt; ++i) {
-      uint32_t a0[32], a1[32];
-      tmem_ld_32x32(t_lane + col_dq + 64 * i, a0);
-      tmem_ld_32x32(t_lane + col_dq + 64 * i + 32, a1);
+      uint32_t a0[32];
+      tmem_ld_32x32(t_lane + col_dq + 64 * i + 32 * hf, a0);
       tmem_ld_wait();
       const int q = i * 128 + r;
       if (q < S) {
         const float sc = p.scale;
-        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + q) * (3 * D) + h * AT_DH;
+        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + q) * (3 * D) + h * AT_DH + 32 * hf;
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
           *reinterpret_cast<uint4*>(dst + c) = make_uint4(
               pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
               pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc));
-          *reinterpret_cast<uint4*>(dst + 32 + c) = make_uint4(
-              pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
-              pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc));
         }
       }
     }
@@ -586,7 +574,7 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
     p.scale_log2 = a.scale * LOG2E;
     const int nslab = (p.SP + 63) / 64;
-    int smem = (p.nqt * 128 + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 256 + 1024;
+    int smem = (p.nqt * 128 + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 2048 /*row stats*/ + 256 + 1024;
     // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
     if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
     if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;

@@ -155,108 +155,198 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
 //   dN = dY (1+scale); dscale = sum_t N dY; dshift = sum_t dY; dgamma = sum dN xhat; dbeta = sum dN
 //   dx = rstd (dhat - mean(dhat) - xhat mean(dhat xhat)),  dhat = dN gamma
 // =========================================================================================
-template <int NV, typename DyT>
-__global__ void __launch_bounds__(256) ln_mod_bwd_kernel(LnBwdArgs a) {
+// Work decomposition: grid (sample, row chunk); a row is shared by W = 1 or 2 warps (W = 2 halves the per-thread
+// column state so that two CTAs fit on an SM); the per-sample sums leave by atomicAdd (several chunks per sample),
+// so the caller zeroes dshift / dscale / g_dgate beforehand.
+template <int NV, typename DyT, bool GATE>
+__global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int rows_per_chunk) {
   constexpr int D = NV * 128;
-  __shared__ float red[8][D];
+  constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;  // warps per row
+  constexpr int NL = NV / W;                            // float4 columns per lane
+  constexpr int RP = 8 / W;                             // rows in flight per CTA
+  constexpr int CPT = (D + 255) / 256;                  // columns per thread in the final cross-warp reductions
+  __shared__ float red[RP][D];
+  __shared__ float s_gs[D];                             // gamma * (1 + scale): d xhat = dy * s_gs
+  __shared__ float2 part[2][RP][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rp = warp / W, half = warp % W;
   const int n = blockIdx.x;
   const int S = seq_of(a.rm, n);
+  const int tok_begin = blockIdx.y * rows_per_chunk;
+  if (tok_begin >= S) return;
+  const int tok_end = min(S, tok_begin + rows_per_chunk);
   const float* scp = a.scale ? a.scale + static_cast<long long>(n) * a.ldmod : nullptr;
-  float4 gam[NV], sc1[NV];
+  for (int c = threadIdx.x; c < D; c += 256) s_gs[c] = a.gamma[c] * (scp ? 1.f + scp[c] : 1.f);
+  __syncthreads();
+  const float* gatep = (GATE && a.g_gate) ? a.g_gate + static_cast<long long>(n) * a.g_ldgate : nullptr;
+  const int col0 = half * NL * 128 + lane * 4;
+  // Every per-column sum of App. E steps 4-5 is a combination of A1 = sum_t dy and A2 = sum_t dy * xhat:
+  //   dshift = A1, dscale = gamma A2 + beta A1, dbeta += (1+scale) A1, dgamma += (1+scale) A2;
+  // the gate stage adds A3 = sum_t z dx and A4 = sum_t dx.
+  float4 A1[NL], A2[NL], A3[NL], A4[NL];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = lane * 4 + 128 * i;
-    gam[i] = *reinterpret_cast<const float4*>(a.gamma + c);
-    sc1[i] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (scp) {
-      float4 t = *reinterpret_cast<const float4*>(scp + c);
-      sc1[i] = make_float4(1.f + t.x, 1.f + t.y, 1.f + t.z, 1.f + t.w);
-    }
-  }
-  float4 bet[NV];
-  float4 acc_sh[NV], acc_sc[NV], acc_g[NV], acc_b[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    bet[i] = *reinterpret_cast<const float4*>(a.beta + lane * 4 + 128 * i);
-    acc_sh[i] = acc_sc[i] = acc_g[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  for (int tok = warp; tok < S; tok += 8) {
+  for (int i = 0; i < NL; ++i) A1[i] = A2[i] = A3[i] = A4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int it = 0;
+  for (int tok = tok_begin + rp; tok < tok_end; tok += RP) {
     const int xrow = row_of(a.rm, n, tok);
     float* dxp = a.dx + static_cast<long long>(xrow) * D;
     int drow = xrow;
+    bool skip = false;
     if (a.gather_L > 0) {
       const int j = tok - a.gather_off;
-      if (j < 0 || j >= a.gather_L) {
-        if (!a.accumulate) {
-#pragma unroll
-          for (int i = 0; i < NV; ++i) store_row4(dxp + lane * 4 + 128 * i, 0.f, 0.f, 0.f, 0.f);
-        }
-        continue;
-      }
+      skip = (j < 0 || j >= a.gather_L);
       drow = n * a.gather_L + j;
+    }
+    if (skip) {
+      // rows outside the gathered window receive no gradient from this LayerNorm
+#pragma unroll
+      for (int i = 0; i < NL; ++i) {
+        const int c = col0 + 128 * i;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.accumulate) o = *reinterpret_cast<const float4*>(dxp + c);
+        else *reinterpret_cast<float4*>(dxp + c) = o;
+        if (GATE) {
+          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (gatep) g = *reinterpret_cast<const float4*>(gatep + c);
+          store_row4(a.g_dz + static_cast<long long>(xrow) * D + c, g.x * o.x, g.y * o.y, g.z * o.z, g.w * o.w);
+          A4[i].x += o.x; A4[i].y += o.y; A4[i].z += o.z; A4[i].w += o.w;
+          if (a.g_dgate) {
+            const float4 z = load_row4(a.g_z + static_cast<long long>(xrow) * D + c);
+            A3[i].x += z.x * o.x; A3[i].y += z.y * o.y; A3[i].z += z.z * o.z; A3[i].w += z.w * o.w;
+          }
+        }
+      }
+      continue;
     }
     const float mean = a.mean[drow], rstd = a.rstd[drow];
     const float* xp = a.x + static_cast<long long>(xrow) * D;
     const DyT* dyp = reinterpret_cast<const DyT*>(a.dy) + static_cast<long long>(drow) * D;
-    float4 xh[NV], dh[NV];
+    float4 xh[NL], dh[NL];
     float m1 = 0.f, m2 = 0.f;
+    // everything this row needs from HBM is requested up front (the second half of the row's work would otherwise
+    // start a second dependent round trip after the reduction)
+    float4 pv[NL];
+    uint2 zraw[NL];
+    const bool want_z = GATE && a.g_dgate;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane * 4 + 128 * i;
-      float4 xv = *reinterpret_cast<const float4*>(xp + c);
-      float4 dy = load_row4(dyp + c);
+    for (int i = 0; i < NL; ++i) {
+      const int c = col0 + 128 * i;
+      pv[i] = a.accumulate ? *reinterpret_cast<const float4*>(dxp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zraw[i] = want_z ? *reinterpret_cast<const uint2*>(a.g_z + static_cast<long long>(xrow) * D + c) : make_uint2(0u, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      const int c = col0 + 128 * i;
+      const float4 xv = *reinterpret_cast<const float4*>(xp + c);
+      const float4 dy = load_row4(dyp + c);
+      const float4 gs = *reinterpret_cast<const float4*>(&s_gs[c]);
       xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
-      // N = xhat*gamma + beta (pre-modulation LN output)
-      float n0 = xh[i].x * gam[i].x + bet[i].x, n1 = xh[i].y * gam[i].y + bet[i].y;
-      float n2 = xh[i].z * gam[i].z + bet[i].z, n3 = xh[i].w * gam[i].w + bet[i].w;
-      acc_sh[i].x += dy.x; acc_sh[i].y += dy.y; acc_sh[i].z += dy.z; acc_sh[i].w += dy.w;
-      acc_sc[i].x += n0 * dy.x; acc_sc[i].y += n1 * dy.y; acc_sc[i].z += n2 * dy.z; acc_sc[i].w += n3 * dy.w;
-      float4 dn = make_float4(dy.x * sc1[i].x, dy.y * sc1[i].y, dy.z * sc1[i].z, dy.w * sc1[i].w);
-      acc_g[i].x += dn.x * xh[i].x; acc_g[i].y += dn.y * xh[i].y; acc_g[i].z += dn.z * xh[i].z; acc_g[i].w += dn.w * xh[i].w;
-      acc_b[i].x += dn.x; acc_b[i].y += dn.y; acc_b[i].z += dn.z; acc_b[i].w += dn.w;
-      dh[i] = make_float4(dn.x * gam[i].x, dn.y * gam[i].y, dn.z * gam[i].z, dn.w * gam[i].w);
+      A1[i].x += dy.x; A1[i].y += dy.y; A1[i].z += dy.z; A1[i].w += dy.w;
+      A2[i].x += dy.x * xh[i].x; A2[i].y += dy.y * xh[i].y; A2[i].z += dy.z * xh[i].z; A2[i].w += dy.w * xh[i].w;
+      dh[i] = make_float4(dy.x * gs.x, dy.y * gs.y, dy.z * gs.z, dy.w * gs.w);
       m1 += dh[i].x + dh[i].y + dh[i].z + dh[i].w;
       m2 += dh[i].x * xh[i].x + dh[i].y * xh[i].y + dh[i].z * xh[i].z + dh[i].w * xh[i].w;
     }
-    m1 = warp_sum(m1) * (1.f / D);
-    m2 = warp_sum(m2) * (1.f / D);
+    m1 = warp_sum(m1);
+    m2 = warp_sum(m2);
+    if (W == 2) {
+      // the two warps of a row exchange their partial sums (double-buffered slot: one named barrier per row)
+      const int buf = it & 1;
+      if (lane == 0) part[buf][rp][half] = make_float2(m1, m2);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + rp) : "memory");
+      const float2 o2 = part[buf][rp][half ^ 1];
+      m1 += o2.x;
+      m2 += o2.y;
+      ++it;
+    }
+    m1 *= (1.f / D);
+    m2 *= (1.f / D);
+    const bool cond_tok = a.dcond && tok == 0;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane * 4 + 128 * i;
+    for (int i = 0; i < NL; ++i) {
+      const int c = col0 + 128 * i;
       float4 o = make_float4(rstd * (dh[i].x - m1 - xh[i].x * m2), rstd * (dh[i].y - m1 - xh[i].y * m2),
                              rstd * (dh[i].z - m1 - xh[i].z * m2), rstd * (dh[i].w - m1 - xh[i].w * m2));
-      if (a.accumulate) {
-        float4 p = *reinterpret_cast<const float4*>(dxp + c);
-        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      o.x += pv[i].x; o.y += pv[i].y; o.z += pv[i].z; o.w += pv[i].w;
+      if (cond_tok) {
+        float4* dc = reinterpret_cast<float4*>(a.dcond + static_cast<long long>(n) * D + c);
+        float4 t = *dc;
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        *dc = t;
+        o = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       *reinterpret_cast<float4*>(dxp + c) = o;
+      if (GATE) {
+        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (gatep) g = *reinterpret_cast<const float4*>(gatep + c);
+        store_row4(a.g_dz + static_cast<long long>(xrow) * D + c, g.x * o.x, g.y * o.y, g.z * o.z, g.w * o.w);
+        A4[i].x += o.x; A4[i].y += o.y; A4[i].z += o.z; A4[i].w += o.w;
+        if (want_z) {
+          A3[i].x += bf16_lo(zraw[i].x) * o.x; A3[i].y += bf16_hi(zraw[i].x) * o.y;
+          A3[i].z += bf16_lo(zraw[i].y) * o.z; A3[i].w += bf16_hi(zraw[i].y) * o.w;
+        }
+      }
     }
   }
-  // cross-warp reduction of the four column accumulators, one at a time through `red`
-  auto reduce_store = [&](float4 (&acc)[NV], float* out_direct, float* out_atomic) {
+  // cross-warp reduction of the column accumulators, one at a time through `red`
+  auto reduce = [&](float4 (&acc)[NL], float (&out)[CPT]) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(&red[warp][lane * 4 + 128 * i]) = acc[i];
+    for (int i = 0; i < NL; ++i) *reinterpret_cast<float4*>(&red[rp][col0 + 128 * i]) = acc[i];
     __syncthreads();
-    for (int c = threadIdx.x; c < D; c += 256) {
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = threadIdx.x + 256 * k;
       float t = 0.f;
+      if (c < D) {
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w][c];
-      if (out_direct) out_direct[c] = t;
-      if (out_atomic) atomicAdd(out_atomic + c, t);
+        for (int w = 0; w < RP; ++w) t += red[w][c];
+      }
+      out[k] = t;
     }
   };
-  if (a.dshift) reduce_store(acc_sh, a.dshift + static_cast<long long>(n) * a.ldd, nullptr);
-  if (a.dscale) reduce_store(acc_sc, a.dscale + static_cast<long long>(n) * a.ldd, nullptr);
-  reduce_store(acc_g, nullptr, a.dgamma);
-  reduce_store(acc_b, nullptr, a.dbeta);
+  float r1[CPT], r2[CPT];
+  reduce(A1, r1);
+  reduce(A2, r2);
+#pragma unroll
+  for (int k = 0; k < CPT; ++k) {
+    const int c = threadIdx.x + 256 * k;
+    if (c < D) {
+      const float sc1 = scp ? 1.f + scp[c] : 1.f;
+      if (a.dshift) atomicAdd(a.dshift + static_cast<long long>(n) * a.ldd + c, r1[k]);
+      if (a.dscale) atomicAdd(a.dscale + static_cast<long long>(n) * a.ldd + c, a.gamma[c] * r2[k] + a.beta[c] * r1[k]);
+      atomicAdd(a.dgamma + c, sc1 * r2[k]);
+      atomicAdd(a.dbeta + c, sc1 * r1[k]);
+    }
+  }
+  if (GATE) {
+    reduce(A4, r1);
+    if (a.g_dgate) reduce(A3, r2);
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = threadIdx.x + 256 * k;
+      if (c < D) {
+        if (a.g_dbias) atomicAdd(a.g_dbias + c, (gatep ? gatep[c] : 1.f) * r1[k]);
+        if (a.g_dgate) atomicAdd(a.g_dgate + static_cast<long long>(n) * a.g_lddgate + c, r2[k]);
+      }
+    }
+  }
 }
 
 template <typename DyT>
 static int ln_bwd_dispatch(const LnBwdArgs& a, int D, int nsamples, cudaStream_t st) {
+  const bool gate = a.g_dz != nullptr;
+  int smax = a.rm.n0 > 0 ? a.rm.s0 : 0;
+  if (nsamples > a.rm.n0 && a.rm.s1 > smax) smax = a.rm.s1;
+  const int nchunks = ceil_div(smax, 96);
+  const int rpc = ceil_div(smax, nchunks);
+  const dim3 grid(nsamples, nchunks);
   switch (D / 128) {
-#define CASE(NV) case NV: ln_mod_bwd_kernel<NV, DyT><<<nsamples, 256, 0, st>>>(a); break;
+#define CASE(NV)                                                                     \
+  case NV:                                                                           \
+    if (gate) ln_mod_bwd_kernel<NV, DyT, true><<<grid, 256, 0, st>>>(a, rpc);        \
+    else ln_mod_bwd_kernel<NV, DyT, false><<<grid, 256, 0, st>>>(a, rpc);            \
+    break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     default: set_error("ln_mod_bwd: width %d unsupported", D); return UMD_ERR_UNSUPPORTED;
@@ -265,15 +355,15 @@ static int ln_bwd_dispatch(const LnBwdArgs& a, int D, int nsamples, cudaStream_t
   return UMD_OK;
 }
 
+// NOTE: dshift / dscale / g_dgate are accumulated with atomicAdd (a sample's rows are split over several CTAs):
+// the caller zeroes them first.
 int ln_mod_bwd(const LnBwdArgs& a, int D, int nsamples, bool dy_bf16, cudaStream_t st) {
   if (nsamples <= 0) return UMD_OK;
   UMD_REQUIRE(D % 128 == 0 && D <= 1024, "ln_mod_bwd: width %d unsupported", D);
-  {
-    // algorithmic bytes: dy in, x in, dx read-modify-write (fp32)
-    const double rows = static_cast<double>(a.rm.split_row) + static_cast<double>(nsamples - a.rm.n0) * a.rm.s1;
-    ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + 4 + (a.accumulate ? 8 : 4)), st);
-    return dy_bf16 ? ln_bwd_dispatch<__nv_bfloat16>(a, D, nsamples, st) : ln_bwd_dispatch<float>(a, D, nsamples, st);
-  }
+  UMD_REQUIRE(!a.g_dgate || a.g_z, "ln_mod_bwd: the gate stage needs the saved branch output to form dgate");
+  // algorithmic bytes: dy in, x in, dx read-modify-write (fp32); gate stage: dz out (bf16), z in (bf16)
+  const double rows = static_cast<double>(a.rm.split_row) + static_cast<double>(nsamples - a.rm.n0) * a.rm.s1;
+  ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + 4 + (a.accumulate ? 8 : 4) + (a.g_dz ? 2 : 0) + (a.g_dgate ? 2 : 0)), st);
   return dy_bf16 ? ln_bwd_dispatch<__nv_bfloat16>(a, D, nsamples, st) : ln_bwd_dispatch<float>(a, D, nsamples, st);
 }
 

@@ -197,15 +197,23 @@ void set_rowmap(umd_gemm_args& g, const RowMap& rm) {
   g.split_row = rm.split_row; g.s0 = rm.s0; g.s1 = rm.s1; g.n0 = rm.n0;
 }
 int pick_split(int M, int N, int K, int batch) {
+  // Split-K factor of a weight-gradient GEMM: the persistent kernel runs ceil(items / SMs) rounds of
+  // (k-blocks per item + a fixed fill/drain cost); pick the factor that minimises that product.
   const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   const long long tiles = static_cast<long long>(ceil_div(M, 128)) * ceil_div(N, bn) * batch;
   if (g_sm == 0) g_sm = sm_count();
-  long long want = (2LL * g_sm + tiles - 1) / tiles;
   const int kb = ceil_div(K, 64);
-  long long cap = kb / 4 > 0 ? kb / 4 : 1;
-  if (want > cap) want = cap;
-  if (want < 1) want = 1;
-  return static_cast<int>(want);
+  const int cap = kb / 4 > 0 ? kb / 4 : 1;
+  const double fixed = 6.0;  // pipeline fill + accumulator drain, in k-block units
+  int best = 1;
+  double best_t = 1e30;
+  for (int sp = 1; sp <= cap && sp <= 64; ++sp) {
+    const long long items = tiles * sp;
+    const double rounds = static_cast<double>((items + g_sm - 1) / g_sm);
+    const double t = rounds * (static_cast<double>(ceil_div(kb, sp)) + fixed);
+    if (t < best_t * 0.999) { best_t = t; best = sp; }
+  }
+  return best;
 }
 
 // Y[M,N] = X[M,K] W[K,N] (+bias) : forward Dense with the Flax [in,out] kernel as an MN-major B operand.
@@ -340,7 +348,22 @@ int stack_forward(Ctx& c, Stack& s) {
   return UMD_OK;
 }
 
-// Backward of the stack; dx holds d x[depth] on entry and d x[0] on exit (App. E steps 1-10).
+// Gate backward of the MLP branch of block l (App. E step 1), run as the tail of the LayerNorm backward that
+// finalises d x[l+1]:  dzb = gate1 * dx, dgate1 = sum_t z dx, d fc2-bias += sum_t dzb.
+void gate_stage_mlp(const Ctx& c, const Stack& s, int l, LnBwdArgs& lnb) {
+  const Plan& P = c.P;
+  const int D = P.D;
+  const long long ldada = static_cast<long long>(s.depth) * 6 * D;
+  const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
+  float* dada = s.dada ? s.dada + static_cast<long long>(l) * 6 * D : nullptr;
+  lnb.g_dz = P.dzb; lnb.g_z = s.L[l].z;
+  lnb.g_gate = ada ? ada + 5 * D : nullptr; lnb.g_ldgate = ldada;
+  lnb.g_dgate = dada ? dada + 5 * D : nullptr; lnb.g_lddgate = ldada;
+  lnb.g_dbias = c.G(s.base + UMD_S_FC2_B, static_cast<long long>(l) * D);
+}
+
+// Backward of the stack (App. E steps 1-10).  On entry dx holds d x[depth] and P.dzb the gated gradient of the
+// last block's MLP branch (gate_stage_mlp fused into the caller's LayerNorm backward); on exit dx holds d x[0].
 int stack_backward(Ctx& c, Stack& s, float* dx) {
   Plan& P = c.P;
   const int D = P.D, T = s.rows, M4 = P.M4;
@@ -352,11 +375,7 @@ int stack_backward(Ctx& c, Stack& s, float* dx) {
     const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
     float* dada = s.dada ? s.dada + static_cast<long long>(l) * 6 * D : nullptr;
     const long long lD = static_cast<long long>(l) * D;
-    // ---- MLP branch
-    GateBwdArgs gb;
-    gb.dx = dx; gb.z = lb.z; gb.gate = ada ? ada + 5 * D : nullptr; gb.ldgate = ldada; gb.rm = s.rm; gb.dz = P.dzb;
-    gb.dgate = dada ? dada + 5 * D : nullptr; gb.lddgate = ldada; gb.dbias = c.G(s.base + UMD_S_FC2_B, lD);
-    UMD_TRY(gate_bwd(gb, D, s.nsamples, c.st));
+    // ---- MLP branch (P.dzb = gate1 * dx)
     UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D), M4, UMD_EPI_DGELU,
                         P.dgb, lb.u));
     UMD_TRY(dense_wgrad(c, lb.g, T, M4, P.dzb, D, D, c.G(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D)));
@@ -371,11 +390,11 @@ int stack_backward(Ctx& c, Stack& s, float* dx) {
     lnb.scale = ada ? ada + 4 * D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
     lnb.dshift = dada ? dada + 3 * D : nullptr; lnb.dscale = dada ? dada + 4 * D : nullptr; lnb.ldd = ldada;
     lnb.dgamma = c.G(s.base + UMD_S_LN1_S, lD); lnb.dbeta = c.G(s.base + UMD_S_LN1_B, lD);
+    // ... followed in the same pass by the gate backward of the attention branch (App. E step 6)
+    lnb.g_dz = P.dzb; lnb.g_z = lb.a; lnb.g_gate = ada ? ada + 2 * D : nullptr; lnb.g_ldgate = ldada;
+    lnb.g_dgate = dada ? dada + 2 * D : nullptr; lnb.g_lddgate = ldada; lnb.g_dbias = c.G(s.base + UMD_S_O_B, lD);
     UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
-    // ---- attention branch
-    gb.z = lb.a; gb.gate = ada ? ada + 2 * D : nullptr; gb.dgate = dada ? dada + 2 * D : nullptr;
-    gb.dbias = c.G(s.base + UMD_S_O_B, lD);
-    UMD_TRY(gate_bwd(gb, D, s.nsamples, c.st));
+    // ---- attention branch (P.dzb = gate0 * dx)
     UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D), D, UMD_EPI_BF16, P.dyb));
     UMD_TRY(dense_wgrad(c, lb.o, T, D, P.dzb, D, D, c.G(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D)));
     AttnBwdArgs ab;
@@ -397,13 +416,15 @@ int stack_backward(Ctx& c, Stack& s, float* dx) {
       g.epi = UMD_EPI_BF16; g.out0 = P.dyb; g.ld0 = D;
       UMD_TRY(gemm_bf16(g, c.st));
     }
+    memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dyb; lnb.x = s.x[l]; lnb.mean = lb.mean0; lnb.rstd = lb.rstd0;
     lnb.gamma = c.W(s.base + UMD_S_LN0_S, lD); lnb.beta = c.W(s.base + UMD_S_LN0_B, lD);
-    lnb.scale = ada ? ada + D : nullptr;
-    lnb.dshift = dada ? dada : nullptr; lnb.dscale = dada ? dada + D : nullptr;
+    lnb.scale = ada ? ada + D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
+    lnb.dshift = dada ? dada : nullptr; lnb.dscale = dada ? dada + D : nullptr; lnb.ldd = ldada;
     lnb.dgamma = c.G(s.base + UMD_S_LN0_S, lD); lnb.dbeta = c.G(s.base + UMD_S_LN0_B, lD);
+    if (!P.adaln) lnb.dcond = P.dcond;            // token-0 row: gradient of the conditioning token (vit.py:73-74)
+    if (l > 0) gate_stage_mlp(c, s, l - 1, lnb);  // dx is now d x[l]: start block l-1's MLP-branch backward
     UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
-    if (!P.adaln) UMD_TRY(cond_row_bwd(dx, P.dcond, s.rm, s.nsamples, D, c.st));
   }
   if (P.adaln) {
     // adaLN projection backward, all blocks of the stack at once (App. E step 10)
@@ -541,6 +562,11 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
   UMD_CHECK_CUDA(cudaMemsetAsync(P.dcond, 0, static_cast<size_t>(B) * D * sizeof(float), st));
   UMD_CHECK_CUDA(cudaMemsetAsync(P.dWf_mat, 0, static_cast<size_t>(D) * P.NC * sizeof(float), st));
   UMD_CHECK_CUDA(cudaMemsetAsync(P.dbiasm, 0, static_cast<size_t>(P.NC) * sizeof(float), st));
+  if (P.adaln) {  // per-sample modulation gradients are accumulated atomically by the LayerNorm backward kernels
+    UMD_CHECK_CUDA(cudaMemsetAsync(P.enc.dada, 0, static_cast<size_t>(B) * P.enc.depth * 6 * D * sizeof(float), st));
+    UMD_CHECK_CUDA(cudaMemsetAsync(P.dec.dada, 0, static_cast<size_t>(B) * P.dec.depth * 6 * D * sizeof(float), st));
+    UMD_CHECK_CUDA(cudaMemsetAsync(P.dfmod, 0, static_cast<size_t>(B) * 2 * D * sizeof(float), st));
+  }
   // ---- un-patchify (final_conv) backward
   UMD_TRY(dense_wgrad(c, P.xm, BL, D, P.dpredp, P.NC, P.NC, P.dWf_mat));
   UMD_TRY(colsum_bf16(P.dpredp, P.NC, BL, P.NC, P.dbiasm, st));
@@ -556,6 +582,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     lnb.dshift = P.dfmod; lnb.dscale = P.dfmod ? P.dfmod + D : nullptr; lnb.ldd = 2 * D;
     lnb.dgamma = c.G(UMD_P_DEC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_DEC_BASE + UMD_S_NORM_B);
     lnb.gather_L = P.L; lnb.gather_off = P.tok0 + 1;
+    gate_stage_mlp(c, P.dec, P.dec.depth - 1, lnb);
     UMD_TRY(ln_mod_bwd(lnb, D, B, true, st));
   }
   if (P.adaln) {  // final_modulation Dense backward
@@ -576,6 +603,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     lnb.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
     lnb.rm = P.enc.rm; lnb.dx = P.dx_enc; lnb.accumulate = 0;
     lnb.dgamma = c.G(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_ENC_BASE + UMD_S_NORM_B);
+    gate_stage_mlp(c, P.enc, P.enc.depth - 1, lnb);
     UMD_TRY(ln_mod_bwd(lnb, D, B, false, st));
   }
   UMD_TRY(stack_backward(c, P.enc, P.dx_enc));

@@ -52,6 +52,18 @@ struct LnBwdArgs {
   float* dbeta;
   int gather_L;
   int gather_off;
+  // adaln=False (vit.py:73-74,111-112): the gradient of every sample's token-0 row goes to dcond[n] and the
+  // row itself is cleared (the block's output row 0 was discarded)
+  float* dcond;
+  // Optional fused gate backward (App. E steps 1 and 6) of the branch whose residual add produced x:
+  //   dz = gate * dx_new (bf16 GEMM operand), dgate[n] = sum_t z dx_new, dbias += gate * sum_t dx_new
+  __nv_bfloat16* g_dz;        // [rows, D] out; null = no gate stage
+  const __nv_bfloat16* g_z;   // [rows, D] saved branch output (needed only with g_dgate)
+  const float* g_gate;        // per-sample rows (stride g_ldgate) or null (= 1)
+  long long g_ldgate;
+  float* g_dgate;             // per-sample out (stride g_lddgate) or null
+  long long g_lddgate;
+  float* g_dbias;             // [D] atomically accumulated or null
 };
 int ln_mod_bwd(const LnBwdArgs& a, int D, int nsamples, bool dy_bf16, cudaStream_t st);
 
