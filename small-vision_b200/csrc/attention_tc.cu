@@ -22,9 +22,13 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace umd {
 
 extern long long g_launch_count;
+
+long long* g_attn_timeline = nullptr;
 
 namespace {
 
@@ -43,6 +47,8 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+#define TL(slot, idx) do { if (tl_on) p.tl[(slot) * 64 + (idx)] = clock64(); } while (0)
+
 __device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // 16-byte chunk `chunk` (0..7) of row r of a [rows][64] bf16 slab in the 128B-swizzled layout TMA / UMMA use.
@@ -119,9 +125,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     load_rows(sK, &tm128, &tm16, bar_kv, D + h * AT_DH, row0, SP);
     load_rows(sQ, &tm128, &tm16, bar_kv, h * AT_DH, row0, SP);
     load_rows(sV, &tm128, &tm16, bar_kv, 2 * D + h * AT_DH, row0, SP);
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-converged; the tcgen05
+    // instructions themselves run under elect.sync so that descriptors stay in uniform registers)
+    // Descriptors are built once; every MMA below only adds a constant to the 14-bit start-address field
+    // (units of 16 bytes; shared memory is < 256 KB so the add never carries out of the field).
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
+    const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
+    const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
+    const int ksteps = SP >> 4;
     mbar_wait(bar_kv, 0);
     tc_fence_after();
     for (int i = 0; i < nqt; ++i) {
@@ -129,24 +141,39 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         mbar_wait(bar_free, (i - 1) & 1);
         tc_fence_after();
       }
+      // (descriptors of the two score chunks are rebuilt per tile: the hoisted form of this short sequence
+      //  produced wrong columns >= 256 on hardware, see profiles/r01_notes.md)
       const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + i * 128 * AT_ROW), 0, 1024);
-      for (int n0 = 0; n0 < SP; n0 += 256) {
-        const int n = min(256, SP - n0);
-        const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + n0 * AT_ROW), 0, 1024);
-        const uint32_t idesc = make_idesc_bf16(128, n, false, false);
+      if (elect_one()) {
+        for (int n0 = 0; n0 < SP; n0 += 256) {
+          const int n = min(256, SP - n0);
+          const uint64_t bdesc = make_smem_desc_sw128(smem_u32(sK + n0 * AT_ROW), 0, 1024);
+          const uint32_t idesc = make_idesc_bf16(128, n, false, false);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + n0, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + n0, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_s);
       }
-      umma_commit(bar_s);
+      __syncwarp();
       mbar_wait(bar_p, i & 1);
       tc_fence_after();
-      const int ksteps = SP >> 4;
-      for (int kk = 0; kk < ksteps; ++kk) {
-        const uint64_t pa = make_smem_desc_sw128(smem_u32(sP + (kk >> 2) * AT_SLAB + (kk & 3) * 32), 0, 1024);
-        const uint64_t vb = make_smem_desc_sw128(smem_u32(sV + kk * 16 * AT_ROW), 8192, 1024);
-        umma_f16_ss(tmem_base + p.o_col, pa, vb, idesc_pv, kk > 0 ? 1u : 0u);
+      if (elect_one()) {
+        uint64_t pa = p_desc, vb = v_desc;
+        int kk = 0;
+#pragma unroll 1
+        for (; kk + 4 <= ksteps; kk += 4) {  // one 64-key slab of P per iteration
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16_ss(tmem_base + p.o_col, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv,
+                        (kk + k) > 0 ? 1u : 0u);
+          pa += AT_SLAB / 16;
+          vb += 4 * (16 * AT_ROW / 16);
+        }
+        for (int k = 0; kk < ksteps; ++kk, ++k)
+          umma_f16_ss(tmem_base + p.o_col, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv, kk > 0 ? 1u : 0u);
+        umma_commit(bar_o);
       }
-      umma_commit(bar_o);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
@@ -269,6 +296,8 @@ struct BwdParams {
   int row_base;
   int S, SP, nt, H;
   int nbuf;  // TMEM score buffers (2 when nt <= 2)
+  int prefetch;  // issue the next block's scores ahead of this block's accumulation (needs nbuf == 2)
+  long long* tl;  // optional timeline buffer (tools/attn_timeline.py): CTA 0 records clock64() at its sync points
   float scale, scale_log2;
 };
 
@@ -337,68 +366,103 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, row0, SP);
     load_rows(sV, &tq128, &tq16, bar_ld, 2 * D + h * AT_DH, row0, SP);
     load_rows(sdO, &td128, &td16, bar_ld, h * AT_DH, row0, SP);
-  } else if (warp == 1 && lane == 0) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-converged, see forward)
     constexpr uint32_t idesc_kt = make_idesc_bf16(128, 64, false, true);   // A K-major (P^T / dS^T), B MN-major (dO / Q)
     constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, true, true);    // A MN-major (dS), B MN-major (K)
+    constexpr uint32_t ROW16 = AT_ROW / 16;                                // descriptor units per 128-byte row
+    // descriptors built once; per MMA only a constant is added to the start-address field
+    const uint64_t q_k = make_smem_desc_sw128(smem_u32(sQ), 0, 1024);      // Q  as K-major B   (scores)
+    const uint64_t o_k = make_smem_desc_sw128(smem_u32(sdO), 0, 1024);     // dO as K-major B   (scores)
+    const uint64_t k_k = make_smem_desc_sw128(smem_u32(sK), 0, 1024);      // K  as K-major A
+    const uint64_t v_k = make_smem_desc_sw128(smem_u32(sV), 0, 1024);      // V  as K-major A
+    const uint64_t q_mn = make_smem_desc_sw128(smem_u32(sQ), 8192, 1024);  // Q  as MN-major B  (dK)
+    const uint64_t o_mn = make_smem_desc_sw128(smem_u32(sdO), 8192, 1024); // dO as MN-major B  (dV)
+    const uint64_t k_mn = make_smem_desc_sw128(smem_u32(sK), 8192, 1024);  // K  as MN-major B  (dQ)
+    const uint64_t pt_k = make_smem_desc_sw128(smem_u32(sPt), 0, 1024);    // P^T  as K-major A
+    const uint64_t st_k = make_smem_desc_sw128(smem_u32(sdSt), 0, 1024);   // dS^T as K-major A
+    const uint64_t st_mn = make_smem_desc_sw128(smem_u32(sdSt), AT_SLAB, 1024);  // dS^T tile as MN-major A (= dS)
+    const bool tl_on = p.tl != nullptr && blockIdx.x == 0 && lane == 0;
     mbar_wait(bar_ld, 0);
     tc_fence_after();
-    int step = 0, blk = 0;
-    uint32_t cnt_p[2] = {0, 0};
-    for (int j = 0; j < nt; ++j) {
-      const int nkv = min(128, SP - 128 * j);
-      const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sK + j * 128 * AT_ROW), 0, 1024);
-      const uint64_t vdesc = make_smem_desc_sw128(smem_u32(sV + j * 128 * AT_ROW), 0, 1024);
-      for (int i = 0; i < nt; ++i) {
-        const int nq = min(128, SP - 128 * i);
-        const int nh = (nq + 63) >> 6;
-        for (int hh = 0; hh < nh; ++hh, ++step) {
-          const int b = step % nbuf, u = step / nbuf;
-          if (u > 0) {
-            mbar_wait(&bar_sfree[b], (u - 1) & 1);
-            tc_fence_after();
-          }
-          const int nqh = min(64, nq - 64 * hh);
-          const uint32_t idesc = make_idesc_bf16(128, nqh, false, false);
-          const uint64_t qdesc = make_smem_desc_sw128(smem_u32(sQ + (i * 128 + hh * 64) * AT_ROW), 0, 1024);
-          const uint64_t odesc = make_smem_desc_sw128(smem_u32(sdO + (i * 128 + hh * 64) * AT_ROW), 0, 1024);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128, kdesc + 2 * k, qdesc + 2 * k, idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_base + b * 128 + 64, vdesc + 2 * k, odesc + 2 * k, idesc, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[b]);
-        }
-        for (int hh = 0; hh < nh; ++hh) {
-          mbar_wait(&bar_p[hh], cnt_p[hh] & 1);
-          ++cnt_p[hh];
-        }
-        tc_fence_after();
-        if (i == 0 && j > 0) {
-          mbar_wait(bar_accfree, (j - 1) & 1);
+    TL(0, 0);
+    int step = 0;
+    // S^T = K_j Q_i^T and dP^T = V_j dO_i^T of block n = (j, i), one 64-query half at a time
+    auto issue_scores = [&](int n) {
+      const int j = n / nt, i = n - j * nt;
+      const int nq = min(128, SP - 128 * i);
+      const int nh = (nq + 63) >> 6;
+      const uint64_t kd = k_k + static_cast<uint64_t>(j * 128 * ROW16), vd = v_k + static_cast<uint64_t>(j * 128 * ROW16);
+      for (int hh = 0; hh < nh; ++hh, ++step) {
+        const int b = step % nbuf, u = step / nbuf;
+        if (u > 0) {
+          mbar_wait(&bar_sfree[b], (u - 1) & 1);
           tc_fence_after();
         }
-        const int kq = nq >> 4;
-        for (int kk = 0; kk < kq; ++kk) {   // dV_j += P^T dO_i
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sPt + (kk >> 2) * AT_SLAB + (kk & 3) * 32), 0, 1024);
-          const uint64_t bb = make_smem_desc_sw128(smem_u32(sdO + (i * 128 + kk * 16) * AT_ROW), 8192, 1024);
-          umma_f16_ss(tmem_base + col_dv, a, bb, idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+        const int nqh = min(64, nq - 64 * hh);
+        const uint32_t idesc = make_idesc_bf16(128, nqh, false, false);
+        const uint64_t qd = q_k + static_cast<uint64_t>((i * 128 + hh * 64) * ROW16);
+        const uint64_t od = o_k + static_cast<uint64_t>((i * 128 + hh * 64) * ROW16);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128, kd + 2 * k, qd + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128 + 64, vd + 2 * k, od + 2 * k, idesc, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[b]);
         }
-        for (int kk = 0; kk < kq; ++kk) {   // dK_j += dS^T Q_i
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sdSt + (kk >> 2) * AT_SLAB + (kk & 3) * 32), 0, 1024);
-          const uint64_t bb = make_smem_desc_sw128(smem_u32(sQ + (i * 128 + kk * 16) * AT_ROW), 8192, 1024);
-          umma_f16_ss(tmem_base + col_dk, a, bb, idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
-        }
-        const int kkv = nkv >> 4;
-        for (int kk = 0; kk < kkv; ++kk) {  // dQ_i += dS K_j   (dS^T tile read as an MN-major A operand)
-          const uint64_t a = make_smem_desc_sw128(smem_u32(sdSt + kk * 16 * AT_ROW), AT_SLAB, 1024);
-          const uint64_t bb = make_smem_desc_sw128(smem_u32(sK + (j * 128 + kk * 16) * AT_ROW), 8192, 1024);
-          umma_f16_ss(tmem_base + col_dq + 64 * i, a, bb, idesc_mn, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_tfree);
-        ++blk;
+        __syncwarp();
+        TL(1, step);
       }
-      umma_commit(bar_acc);
+    };
+    const int nblk = nt * nt;
+    uint32_t cnt_p[2] = {0, 0};
+    issue_scores(0);
+    for (int n = 0; n < nblk; ++n) {
+      const int j = n / nt, i = n - j * nt;
+      const int nq = min(128, SP - 128 * i), nkv = min(128, SP - 128 * j);
+      const int nh = (nq + 63) >> 6;
+      // with two score buffers the next block's scores are issued ahead of this block's accumulation, so the
+      // softmax warps never wait for them
+      if (p.prefetch && n + 1 < nblk) issue_scores(n + 1);
+      for (int hh = 0; hh < nh; ++hh) {
+        mbar_wait(&bar_p[hh], cnt_p[hh] & 1);
+        ++cnt_p[hh];
+      }
+      tc_fence_after();
+      TL(2, n);
+      if (i == 0 && j > 0) {
+        mbar_wait(bar_accfree, (j - 1) & 1);
+        tc_fence_after();
+      }
+      const int kq = nq >> 4, kkv = nkv >> 4;
+      if (elect_one()) {
+      {  // dV_j += P^T dO_i
+        const uint64_t bb = o_mn + static_cast<uint64_t>(i * 128 * ROW16);
+#pragma unroll 1
+        for (int kk = 0; kk < kq; ++kk)
+          umma_f16_ss(tmem_base + col_dv, pt_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
+                      bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+      }
+      {  // dK_j += dS^T Q_i
+        const uint64_t bb = q_mn + static_cast<uint64_t>(i * 128 * ROW16);
+#pragma unroll 1
+        for (int kk = 0; kk < kq; ++kk)
+          umma_f16_ss(tmem_base + col_dk, st_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
+                      bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+      }
+      {  // dQ_i += dS K_j   (dS^T tile read as an MN-major A operand)
+        const uint64_t bb = k_mn + static_cast<uint64_t>(j * 128 * ROW16);
+#pragma unroll 1
+        for (int kk = 0; kk < kkv; ++kk)
+          umma_f16_ss(tmem_base + col_dq + 64 * i, st_mn + static_cast<uint64_t>(kk * 16 * ROW16),
+                      bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_mn, (j > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(bar_tfree);
+      if (i == nt - 1) umma_commit(bar_acc);
+      }
+      __syncwarp();
+      TL(3, n);
+      if (!p.prefetch && n + 1 < nblk) issue_scores(n + 1);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax backward + epilogues
@@ -406,26 +470,49 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const int hf = (warp - 4) >> 2;  // which 32 of the 64 columns of a score half / of an output tile
     const int r = quad * 32 + lane;  // key row inside the key tile (TMEM lane); query row in the dQ epilogue
     const int tid = threadIdx.x - 128;
+    const bool tl_on = p.tl != nullptr && blockIdx.x == 0 && tid == 0;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    // delta = rowsum(dO * O), lse in log2 units
-    for (int q = tid; q < SP; q += AT_SM_THREADS) {
-      float dl = 0.f, l2 = 0.f;
-      if (q < S) {
-        const uint4* po = reinterpret_cast<const uint4*>(p.out + static_cast<long long>(row0 + q) * D + h * AT_DH);
-        const uint4* pg = reinterpret_cast<const uint4*>(p.dout + static_cast<long long>(row0 + q) * D + h * AT_DH);
+    TL(4, 0);
+    // delta = rowsum(dO * O) and lse in log2 units.  Eight lanes share a row (one 16-byte chunk each): O comes
+    // from global memory with fully coalesced 128-byte row reads, all requested at once before anything else;
+    // dO is taken from the shared-memory copy the TMA producer is fetching anyway.
+    {
+      const int sub = tid & 7, rloc = tid >> 3;  // 32 rows per pass of the 256 threads
+      uint4 av[9];
+      float l2v[9];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 a = po[c], g = pg[c];
-          dl += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-                bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
-                bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+      for (int u = 0; u < 9; ++u) {
+        const int q = 32 * u + rloc;
+        av[u] = make_uint4(0u, 0u, 0u, 0u);
+        l2v[u] = 0.f;
+        if (q < S) {
+          av[u] = *reinterpret_cast<const uint4*>(p.out + static_cast<long long>(row0 + q) * D + h * AT_DH + sub * 8);
+          if (sub == 0) l2v[u] = p.lse[static_cast<long long>(row0 + q) * p.H + h] * LOG2E;
         }
-        l2 = p.lse[static_cast<long long>(row0 + q) * p.H + h] * LOG2E;
       }
-      sDelta[q] = dl;
-      sLse[q] = l2;
+      mbar_wait(bar_ld, 0);
+#pragma unroll
+      for (int u = 0; u < 9; ++u) {
+        const int q = 32 * u + rloc;
+        float dl = 0.f;
+        if (q < SP) {
+          const uint4 a = av[u];
+          const uint4 g = *reinterpret_cast<const uint4*>(sdO + q * AT_ROW + ((sub ^ (q & 7)) << 4));
+          dl = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+               bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+               bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+        }
+        dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+        dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+        dl += __shfl_xor_sync(0xffffffffu, dl, 4);
+        if (sub == 0) {
+          sDelta[q] = dl;
+          sLse[q] = l2v[u];
+        }
+      }
     }
     bar_softmax();
+    TL(4, 1);
     const float sl2 = p.scale_log2;
     int step = 0, blk = 0;
     for (int j = 0; j < nt; ++j) {
@@ -438,13 +525,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           const int b = step % nbuf, u = step / nbuf;
           mbar_wait(&bar_s[b], u & 1);
           tc_fence_after();
+          TL(5, step);
           uint32_t sv[32], dv[32];
           tmem_ld_32x32(t_lane + b * 128 + 32 * hf, sv);
           tmem_ld_32x32(t_lane + b * 128 + 64 + 32 * hf, dv);
           tmem_ld_wait();
           tc_fence_before();
           mbar_arrive(&bar_sfree[b]);
+          TL(6, step);
           if (hh == 0 && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
+          TL(7, step);
           const int q0 = i * 128 + hh * 64 + 32 * hf;
           uint8_t* slabP = sPt + hh * AT_SLAB;
           uint8_t* slabS = sdSt + hh * AT_SLAB;
@@ -471,12 +561,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           }
           fence_proxy_async();
           mbar_arrive(&bar_p[hh]);
+          TL(8, step);
         }
         ++blk;
       }
       // dK_j, dV_j: each half owns 32 of the 64 head-dim columns
       mbar_wait(bar_acc, j & 1);
       tc_fence_after();
+      TL(9, j);
       {
         uint32_t a0[32], a1[32];
         __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + kv) * (3 * D) + h * AT_DH + 32 * hf;
@@ -499,6 +591,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
         }
       }
     }
+    TL(10, 0);
     // dQ_i (the last bar_acc phase covers every MMA issued)
     for (int i = 0; i < nt; ++i) {
       uint32_t a0[32];
@@ -518,6 +611,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     }
   }
 
+  if (p.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 128) p.tl[10 * 64 + 1] = clock64();
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -605,7 +699,9 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     p.out = a.out; p.dout = a.dout; p.lse = a.lse; p.dqkv = a.dqkv; p.row_base = seg[k].row_base;
     p.S = seg[k].S; p.SP = (p.S + 15) & ~15; p.nt = (p.S + 127) / 128; p.H = a.H;
     p.nbuf = p.nt <= 2 ? 2 : 1;
+    { const char* e = getenv("UMD_ATTN_PREFETCH"); p.prefetch = (p.nbuf == 2) && (e ? atoi(e) != 0 : true); }
     p.scale = a.scale; p.scale_log2 = a.scale * LOG2E;
+    p.tl = g_attn_timeline;
     int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 2 * AT_STAT_N * 4 + 256 + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
     attn_bwd_tc_kernel<<<seg[k].n * a.H, AT_THREADS, smem, st>>>(tq128, tq16, td128, td16, p);
@@ -616,3 +712,6 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
 }
 
 }  // namespace umd
+
+// debug aid (tools/attn_timeline.py): device buffer of 11 x 64 clock64() stamps written by CTA 0 of the backward kernel
+extern "C" void umd_debug_attn_timeline(long long* device_buf) { umd::g_attn_timeline = device_buf; }

@@ -141,7 +141,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tiles_mn = m_tiles * n_tiles;
   const long long total_items = static_cast<long long>(tiles_mn) * p.split_k * p.batch;
 
-  if (warp == 0 && lane == 0) {
+  // Producer and MMA issuer run warp-converged with the asynchronous instructions themselves under elect.sync:
+  // addresses, descriptors and loop state then stay in uniform registers (a lane-0-only branch makes the
+  // compiler wrap every UTMALDG / UTCHMMA in a R2UR.BROADCAST loop that costs ~100 cycles per instruction).
+  if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -152,6 +155,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int bb = p.b_bcast ? 0 : b;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
@@ -173,13 +177,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + 64 * i, k0, bb);
         }
+        }
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
     // per UMMA_K (=16 elements) advance of the descriptor start address, in 16-byte units
@@ -204,12 +210,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             make_smem_desc_sw128(smem_u32(smem_a + stage * Cfg::A_BYTES), A_MN ? lbo : 0, 1024);
         const uint64_t bdesc =
             make_smem_desc_sw128(smem_u32(smem_b + stage * Cfg::B_BYTES), B_MN ? lbo : 0, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_f16_ss(d_tmem, adesc + k * a_adv, bdesc + k * b_adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            umma_f16_ss(d_tmem, adesc + k * a_adv, bdesc + k * b_adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+        __syncwarp();
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
