@@ -56,13 +56,14 @@ __device__ __forceinline__ void st_swz(uint8_t* slab, int r, int chunk, uint4 v)
   *reinterpret_cast<uint4*>(slab + r * AT_ROW + ((chunk ^ (r & 7)) << 4)) = v;
 }
 
+// rows [0, rows) of one sample (tensor map dims: column, row in sample, sample; rows >= S are zero-filled).
+// tm16 is the tensor map whose box holds the rows % 128 tail rows (a multiple of 16).
 __device__ __forceinline__ void load_rows(uint8_t* dst, const CUtensorMap* tm128, const CUtensorMap* tm16, uint64_t* bar,
-                                          int col, int row0, int rows) {
+                                          int col, int sample, int rows) {
   int r = 0;
 #pragma unroll 1
-  for (; r + 128 <= rows; r += 128) tma_load_3d(dst + r * AT_ROW, tm128, bar, col, row0 + r, 0);
-#pragma unroll 1
-  for (; r < rows; r += 16) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, row0 + r, 0);
+  for (; r + 128 <= rows; r += 128) tma_load_3d(dst + r * AT_ROW, tm128, bar, col, r, sample);
+  if (r < rows) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, r, sample);  // one box of rows % 128 rows
 }
 
 struct FwdParams {
@@ -72,16 +73,20 @@ struct FwdParams {
   int S, SP, nqt, H;
   int o_col, tmem_cols;
   float scale_log2;
+  int stagger_ctas, stagger_ns;  // first-wave CTAs start (blockIdx % 8) * stagger_ns apart (see attention_fwd_tc)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16, const FwdParams p) {
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
+                   const __grid_constant__ CUtensorMap tmo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(blockIdx.x) < p.stagger_ctas) __nanosleep((blockIdx.x & 7) * p.stagger_ns);
   const int S = p.S, SP = p.SP, nqt = p.nqt;
   const int D = p.H * AT_DH;
   const int h = blockIdx.x % p.H;
-  const int row0 = p.row_base + (blockIdx.x / p.H) * S;
+  const int sample = blockIdx.x / p.H;   // within the segment
+  const int row0 = p.row_base + sample * S;
   const int nslab = (SP + 63) >> 6;
   uint8_t* sQ = smem;                      // nqt * 128 rows (rows >= SP stay unwritten: they only feed unused lanes)
   uint8_t* sK = sQ + nqt * 128 * AT_ROW;   // SP rows
@@ -101,6 +106,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm128);
     tma_prefetch_desc(&tm16);
+    tma_prefetch_desc(&tmo);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_kv, 1);
@@ -122,9 +128,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
     mbar_expect_tx(bar_kv, 3u * SP * AT_ROW);
-    load_rows(sK, &tm128, &tm16, bar_kv, D + h * AT_DH, row0, SP);
-    load_rows(sQ, &tm128, &tm16, bar_kv, h * AT_DH, row0, SP);
-    load_rows(sV, &tm128, &tm16, bar_kv, 2 * D + h * AT_DH, row0, SP);
+    load_rows(sK, &tm128, &tm16, bar_kv, D + h * AT_DH, sample, SP);
+    load_rows(sQ, &tm128, &tm16, bar_kv, h * AT_DH, sample, SP);
+    load_rows(sV, &tm128, &tm16, bar_kv, 2 * D + h * AT_DH, sample, SP);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged; the tcgen05
     // instructions themselves run under elect.sync so that descriptors stay in uniform registers)
@@ -184,7 +190,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const float sl2 = p.scale_log2;
     const int csplit = ((SP >> 4) + 1) / 2 * 16;          // columns [0, csplit) -> half 0, [csplit, SP) -> half 1
     const int cb = hf ? csplit : 0, ce = hf ? SP : csplit;
+    const int tid = threadIdx.x - 128;
     for (int i = 0; i < nqt; ++i) {
+      // the previous tile's output store must have finished reading its staging slab (slab 0 of P) before pass 2
+      // of this tile rewrites it; the max-exchange barrier below orders the other threads behind this wait
+      if (i > 0 && tid == 0) bulk_wait_read<0>();
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
       // pass 1: maximum of the raw logits over this thread's columns
@@ -259,21 +269,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       bar_softmax();                     // partial sums of both halves are visible
       sum += sSum[(hf ^ 1) * 128 + r];
       mbar_arrive(bar_free);
+      // O / rowsum leaves as one [128 x 64] bf16 tile: staged in slab 0 of the P buffer (dead once PV has
+      // completed) and written by a TMA store whose tensor map clips the rows of the tile that lie beyond S
       const int row = i * 128 + r;
-      if (row < S) {
-        const float inv = 1.f / sum;
-        __nv_bfloat16* op = p.out + static_cast<long long>(row0 + row) * D + h * AT_DH + 32 * hf;
+      const float inv = 1.f / sum;
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          *reinterpret_cast<uint4*>(op + j) = make_uint4(
-              pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
-              pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
-              pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
-              pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
-        }
-        if (p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
+      for (int j = 0; j < 32; j += 8) {
+        st_swz(sP, r, 4 * hf + (j >> 3),
+               make_uint4(pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
+                          pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
+                          pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
+                          pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv)));
       }
+      fence_proxy_async();
+      bar_softmax();
+      if (tid == 0) {
+        tma_store_3d(&tmo, sP, h * AT_DH, i * 128, sample);
+        bulk_commit();
+      }
+      if (row < S && p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
     }
+    if (tid == 0) bulk_wait_read<0>();
   }
 
   __syncwarp();
@@ -297,19 +313,26 @@ struct BwdParams {
   int S, SP, nt, H;
   int nbuf;  // TMEM score buffers (2 when nt <= 2)
   int prefetch;  // issue the next block's scores ahead of this block's accumulation (needs nbuf == 2)
+  int stagger_ctas, stagger_ns;
+  int lse_bulk;  // the sample's [S][H] lse block is 16-byte aligned: fetch it with one bulk copy
+  int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py): CTA 0 records clock64() at its sync points
   float scale, scale_log2;
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_constant__ CUtensorMap tq16,
-                   const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16, const BwdParams p) {
+                   const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16,
+                   const __grid_constant__ CUtensorMap tmdq, const __grid_constant__ CUtensorMap to128,
+                   const __grid_constant__ CUtensorMap to16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(blockIdx.x) < p.stagger_ctas) __nanosleep((blockIdx.x & 7) * p.stagger_ns);
   const int S = p.S, SP = p.SP, nt = p.nt, nbuf = p.nbuf;
   const int D = p.H * AT_DH;
   const int h = blockIdx.x % p.H;
-  const int row0 = p.row_base + (blockIdx.x / p.H) * S;
+  const int sample = blockIdx.x / p.H;   // within the segment
+  const int row0 = p.row_base + sample * S;
   // K and V are also read as 128-row A operands: the reads past row SP of K land in V, those of V in the
   // P^T tile — allocated memory whose content only reaches TMEM lanes that are masked below.
   uint8_t* sQ = smem;
@@ -318,9 +341,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   uint8_t* sV = sK + SP * AT_ROW;
   uint8_t* sPt = sV + SP * AT_ROW;   // [128 kv][128 q] as two slabs of 64 q
   uint8_t* sdSt = sPt + 2 * AT_SLAB;
-  float* sLse = reinterpret_cast<float*>(sdSt + 2 * AT_SLAB);  // [SP] lse * log2e
-  float* sDelta = sLse + AT_STAT_N;                           // [SP] rowsum(dO * O)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + AT_STAT_N);
+  // per-query statistics live in their own (static) arrays so that the compiler knows the score-tile stores
+  // never alias them and can hoist their loads
+  __shared__ __align__(16) float sLse[AT_STAT_N];     // lse * log2e
+  __shared__ __align__(16) float sDelta[AT_STAT_N];   // rowsum(dO * O)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + 2 * AT_SLAB);
   uint64_t* bar_ld = bars + 0;
   uint64_t* bar_s = bars + 1;       // [2]
   uint64_t* bar_sfree = bars + 3;   // [2]
@@ -336,6 +361,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     tma_prefetch_desc(&tq16);
     tma_prefetch_desc(&td128);
     tma_prefetch_desc(&td16);
+    tma_prefetch_desc(&tmdq);
+    tma_prefetch_desc(&to128);
+    tma_prefetch_desc(&to16);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_ld, 1);
@@ -361,11 +389,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
-    mbar_expect_tx(bar_ld, 4u * SP * AT_ROW);
-    load_rows(sK, &tq128, &tq16, bar_ld, D + h * AT_DH, row0, SP);
-    load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, row0, SP);
-    load_rows(sV, &tq128, &tq16, bar_ld, 2 * D + h * AT_DH, row0, SP);
-    load_rows(sdO, &td128, &td16, bar_ld, h * AT_DH, row0, SP);
+    // O (for delta) and this sample's [S][H] block of log-sum-exps are parked in the P^T / dS^T tile region,
+    // which has no other use until the first score tile has been processed
+    const uint32_t lse_bytes = p.lse_bulk ? static_cast<uint32_t>(S) * p.H * 4u : 0u;
+    mbar_expect_tx(bar_ld, 5u * SP * AT_ROW + lse_bytes);
+    load_rows(sK, &tq128, &tq16, bar_ld, D + h * AT_DH, sample, SP);
+    load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, sample, SP);
+    load_rows(sV, &tq128, &tq16, bar_ld, 2 * D + h * AT_DH, sample, SP);
+    load_rows(sdO, &td128, &td16, bar_ld, h * AT_DH, sample, SP);
+    load_rows(sPt, &to128, &to16, bar_ld, h * AT_DH, sample, SP);
+    if (p.lse_bulk) bulk_load_1d(sPt + SP * AT_ROW, p.lse + static_cast<long long>(row0) * p.H, lse_bytes, bar_ld);
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged, see forward)
     constexpr uint32_t idesc_kt = make_idesc_bf16(128, 64, false, true);   // A K-major (P^T / dS^T), B MN-major (dO / Q)
@@ -382,48 +415,53 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const uint64_t pt_k = make_smem_desc_sw128(smem_u32(sPt), 0, 1024);    // P^T  as K-major A
     const uint64_t st_k = make_smem_desc_sw128(smem_u32(sdSt), 0, 1024);   // dS^T as K-major A
     const uint64_t st_mn = make_smem_desc_sw128(smem_u32(sdSt), AT_SLAB, 1024);  // dS^T tile as MN-major A (= dS)
-    const bool tl_on = p.tl != nullptr && blockIdx.x == 0 && lane == 0;
+    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && lane == 0;
     mbar_wait(bar_ld, 0);
     tc_fence_after();
     TL(0, 0);
     int step = 0;
-    // S^T = K_j Q_i^T and dP^T = V_j dO_i^T of block n = (j, i), one 64-query half at a time
-    auto issue_scores = [&](int n) {
+    // S^T = K_j Q_i^T and dP^T = V_j dO_i^T for 64-query half hh of block n = (j, i).  Steps are issued in order.
+    auto halves_of = [&](int n) { return (min(128, SP - 128 * (n % nt)) + 63) >> 6; };
+    auto issue_step = [&](int n, int hh) {
       const int j = n / nt, i = n - j * nt;
       const int nq = min(128, SP - 128 * i);
-      const int nh = (nq + 63) >> 6;
-      const uint64_t kd = k_k + static_cast<uint64_t>(j * 128 * ROW16), vd = v_k + static_cast<uint64_t>(j * 128 * ROW16);
-      for (int hh = 0; hh < nh; ++hh, ++step) {
-        const int b = step % nbuf, u = step / nbuf;
-        if (u > 0) {
-          mbar_wait(&bar_sfree[b], (u - 1) & 1);
-          tc_fence_after();
-        }
-        const int nqh = min(64, nq - 64 * hh);
-        const uint32_t idesc = make_idesc_bf16(128, nqh, false, false);
-        const uint64_t qd = q_k + static_cast<uint64_t>((i * 128 + hh * 64) * ROW16);
-        const uint64_t od = o_k + static_cast<uint64_t>((i * 128 + hh * 64) * ROW16);
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128, kd + 2 * k, qd + 2 * k, idesc, k > 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128 + 64, vd + 2 * k, od + 2 * k, idesc, k > 0 ? 1u : 0u);
-          umma_commit(&bar_s[b]);
-        }
-        __syncwarp();
-        TL(1, step);
+      const int b = step % nbuf, u = step / nbuf;
+      if (u > 0) {
+        mbar_wait(&bar_sfree[b], (u - 1) & 1);
+        tc_fence_after();
       }
+      const int nqh = min(64, nq - 64 * hh);
+      const uint32_t idesc = make_idesc_bf16(128, nqh, false, false);
+      const uint64_t kd = k_k + static_cast<uint64_t>(j * 128 * ROW16), vd = v_k + static_cast<uint64_t>(j * 128 * ROW16);
+      const uint64_t qd = q_k + static_cast<uint64_t>((i * 128 + hh * 64) * ROW16);
+      const uint64_t od = o_k + static_cast<uint64_t>((i * 128 + hh * 64) * ROW16);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128, kd + 2 * k, qd + 2 * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + b * 128 + 64, vd + 2 * k, od + 2 * k, idesc, k > 0 ? 1u : 0u);
+        umma_commit(&bar_s[b]);
+      }
+      __syncwarp();
+      ++step;
+      TL(1, step);
     };
     const int nblk = nt * nt;
     uint32_t cnt_p[2] = {0, 0};
-    issue_scores(0);
+    for (int hh = 0; hh < halves_of(0); ++hh) issue_step(0, hh);
     for (int n = 0; n < nblk; ++n) {
       const int j = n / nt, i = n - j * nt;
       const int nq = min(128, SP - 128 * i), nkv = min(128, SP - 128 * j);
       const int nh = (nq + 63) >> 6;
-      // with two score buffers the next block's scores are issued ahead of this block's accumulation, so the
-      // softmax warps never wait for them
-      if (p.prefetch && n + 1 < nblk) issue_scores(n + 1);
+      // Score steps of the next block that can run ahead of this block's accumulation: all of them with two
+      // TMEM score buffers, the first half with one (its buffer is free as soon as the softmax warps have read
+      // the current scores; the second half needs them to have read the first, which at a key-tile boundary
+      // only happens after the dK/dV epilogue that waits for this block's accumulation).
+      int ahead = 0;
+      if (p.prefetch && n + 1 < nblk) {
+        ahead = (nbuf == 2) ? halves_of(n + 1) : 1;
+        for (int hh = 0; hh < ahead; ++hh) issue_step(n + 1, hh);
+      }
       for (int hh = 0; hh < nh; ++hh) {
         mbar_wait(&bar_p[hh], cnt_p[hh] & 1);
         ++cnt_p[hh];
@@ -462,7 +500,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       }
       __syncwarp();
       TL(3, n);
-      if (!p.prefetch && n + 1 < nblk) issue_scores(n + 1);
+      if (n + 1 < nblk)
+        for (int hh = ahead; hh < halves_of(n + 1); ++hh) issue_step(n + 1, hh);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax backward + epilogues
@@ -470,51 +509,51 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const int hf = (warp - 4) >> 2;  // which 32 of the 64 columns of a score half / of an output tile
     const int r = quad * 32 + lane;  // key row inside the key tile (TMEM lane); query row in the dQ epilogue
     const int tid = threadIdx.x - 128;
-    const bool tl_on = p.tl != nullptr && blockIdx.x == 0 && tid == 0;
+    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     TL(4, 0);
-    // delta = rowsum(dO * O) and lse in log2 units.  Eight lanes share a row (one 16-byte chunk each): O comes
-    // from global memory with fully coalesced 128-byte row reads, all requested at once before anything else;
-    // dO is taken from the shared-memory copy the TMA producer is fetching anyway.
+    // delta = rowsum(dO * O) and lse in log2 units, both from shared memory, one query row per thread (the
+    // 128B swizzle makes the row-per-lane reads conflict-free); the region O and the lse block are read from
+    // becomes the P^T / dS^T tiles after the barrier below
     {
-      const int sub = tid & 7, rloc = tid >> 3;  // 32 rows per pass of the 256 threads
-      uint4 av[9];
-      float l2v[9];
+      const float* lse_blk = reinterpret_cast<const float*>(sPt + SP * AT_ROW);   // [S][H]
+      float lse_direct[2] = {0.f, 0.f};
+      if (!p.lse_bulk) {
 #pragma unroll
-      for (int u = 0; u < 9; ++u) {
-        const int q = 32 * u + rloc;
-        av[u] = make_uint4(0u, 0u, 0u, 0u);
-        l2v[u] = 0.f;
-        if (q < S) {
-          av[u] = *reinterpret_cast<const uint4*>(p.out + static_cast<long long>(row0 + q) * D + h * AT_DH + sub * 8);
-          if (sub == 0) l2v[u] = p.lse[static_cast<long long>(row0 + q) * p.H + h] * LOG2E;
+        for (int u = 0; u < 2; ++u) {
+          const int q = tid + 256 * u;
+          if (q < S) lse_direct[u] = p.lse[static_cast<long long>(row0 + q) * p.H + h];
         }
       }
+      TL(4, 2);
       mbar_wait(bar_ld, 0);
+      TL(4, 3);
 #pragma unroll
-      for (int u = 0; u < 9; ++u) {
-        const int q = 32 * u + rloc;
-        float dl = 0.f;
+      for (int u = 0; u < 2; ++u) {
+        const int q = tid + 256 * u;
         if (q < SP) {
-          const uint4 a = av[u];
-          const uint4 g = *reinterpret_cast<const uint4*>(sdO + q * AT_ROW + ((sub ^ (q & 7)) << 4));
-          dl = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-               bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
-               bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
-        }
-        dl += __shfl_xor_sync(0xffffffffu, dl, 1);
-        dl += __shfl_xor_sync(0xffffffffu, dl, 2);
-        dl += __shfl_xor_sync(0xffffffffu, dl, 4);
-        if (sub == 0) {
-          sDelta[q] = dl;
-          sLse[q] = l2v[u];
+          float dl = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int off = q * AT_ROW + ((c ^ (q & 7)) << 4);
+            const uint4 a = *reinterpret_cast<const uint4*>(sPt + off);
+            const uint4 g = *reinterpret_cast<const uint4*>(sdO + off);
+            dl += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+                  bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+                  bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+          }
+          const float ls = (q < S) ? (p.lse_bulk ? lse_blk[q * p.H + h] : lse_direct[u]) * LOG2E : 0.f;
+          sDelta[q] = (q < S) ? dl : 0.f;
+          sLse[q] = ls;
         }
       }
     }
+    TL(4, 4);
     bar_softmax();
     TL(4, 1);
     const float sl2 = p.scale_log2;
     int step = 0, blk = 0;
+    bool store_pending = false;
     for (int j = 0; j < nt; ++j) {
       const int kv = j * 128 + r;
       const bool kv_ok = kv < S;
@@ -534,6 +573,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           mbar_arrive(&bar_sfree[b]);
           TL(6, step);
           if (hh == 0 && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
+          if (store_pending) {   // dK_j / dV_j of the previous key tile were staged in the P^T tile
+            if (tid == 0) bulk_wait_read<0>();
+            bar_softmax();
+            store_pending = false;
+          }
           TL(7, step);
           const int q0 = i * 128 + hh * 64 + 32 * hf;
           uint8_t* slabP = sPt + hh * AT_SLAB;
@@ -565,53 +609,66 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
         }
         ++blk;
       }
-      // dK_j, dV_j: each half owns 32 of the 64 head-dim columns
+      // dK_j, dV_j: each half owns 32 of the 64 head-dim columns.  The two [128 x 64] bf16 tiles are staged in the
+      // P^T tile (dead: bar_acc covers every MMA issued so far) and leave by TMA stores that clip rows >= S.
       mbar_wait(bar_acc, j & 1);
       tc_fence_after();
       TL(9, j);
       {
         uint32_t a0[32], a1[32];
-        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + kv) * (3 * D) + h * AT_DH + 32 * hf;
         tmem_ld_32x32(t_lane + col_dv + 32 * hf, a0);
         tmem_ld_32x32(t_lane + col_dk + 32 * hf, a1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(bar_accfree);
-        if (kv_ok) {
-          const float sc = p.scale;
+        const float sc = p.scale;
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            *reinterpret_cast<uint4*>(dst + 2 * D + c) = make_uint4(
-                pack_bf16x2(__uint_as_float(a0[c]), __uint_as_float(a0[c + 1])), pack_bf16x2(__uint_as_float(a0[c + 2]), __uint_as_float(a0[c + 3])),
-                pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7])));
-            *reinterpret_cast<uint4*>(dst + D + c) = make_uint4(
-                pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
-                pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc));
-          }
+        for (int c = 0; c < 32; c += 8) {
+          st_swz(sPt, r, 4 * hf + (c >> 3), make_uint4(
+              pack_bf16x2(__uint_as_float(a0[c]), __uint_as_float(a0[c + 1])), pack_bf16x2(__uint_as_float(a0[c + 2]), __uint_as_float(a0[c + 3])),
+              pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7]))));
+          st_swz(sPt + AT_SLAB, r, 4 * hf + (c >> 3), make_uint4(
+              pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
+              pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc)));
         }
+        fence_proxy_async();
+        bar_softmax();
+        if (tid == 0) {
+          tma_store_3d(&tmdq, sPt, 2 * D + h * AT_DH, j * 128, sample);
+          tma_store_3d(&tmdq, sPt + AT_SLAB, D + h * AT_DH, j * 128, sample);
+          bulk_commit();
+        }
+        store_pending = true;
       }
     }
     TL(10, 0);
-    // dQ_i (the last bar_acc phase covers every MMA issued)
+    // dQ_i (the last bar_acc phase covers every MMA issued): staged in the P^T / dS^T tiles once the dK / dV store
+    // has drained, then one TMA store per query tile
+    if (tid == 0) bulk_wait_read<0>();
+    bar_softmax();
     for (int i = 0; i < nt; ++i) {
       uint32_t a0[32];
       tmem_ld_32x32(t_lane + col_dq + 64 * i + 32 * hf, a0);
       tmem_ld_wait();
-      const int q = i * 128 + r;
-      if (q < S) {
-        const float sc = p.scale;
-        __nv_bfloat16* dst = p.dqkv + static_cast<long long>(row0 + q) * (3 * D) + h * AT_DH + 32 * hf;
+      const float sc = p.scale;
+      uint8_t* stage = sPt + i * AT_SLAB;   // slabs 0,1 of P^T, then slab 0 of dS^T (contiguous)
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          *reinterpret_cast<uint4*>(dst + c) = make_uint4(
-              pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
-              pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc));
-        }
+      for (int c = 0; c < 32; c += 8) {
+        st_swz(stage, r, 4 * hf + (c >> 3), make_uint4(
+            pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
+            pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc)));
       }
+    }
+    fence_proxy_async();
+    bar_softmax();
+    if (tid == 0) {
+      for (int i = 0; i < nt; ++i) tma_store_3d(&tmdq, sPt + i * AT_SLAB, h * AT_DH, i * 128, sample);
+      bulk_commit();
+      bulk_wait_read<0>();
     }
   }
 
-  if (p.tl != nullptr && blockIdx.x == 0 && threadIdx.x == 128) p.tl[10 * 64 + 1] = clock64();
+  if (p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && threadIdx.x == 128) p.tl[10 * 64 + 1] = clock64();
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -624,16 +681,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
 struct Segment {
   int n, S, row_base;
 };
+// rows of the last, partial 128-row box of a sample padded to 16 (16 when there is none: the map is then unused)
+int tail_rows(int S) {
+  const int t = ((S + 15) & ~15) % 128;
+  return t ? t : 16;
+}
+// Every CTA of these kernels runs the same load -> compute -> store sequence for the same time, so a grid that
+// starts in lockstep stays in lockstep and hammers HBM in bursts.  Offsetting the start of the first wave spreads
+// the phases for the rest of the launch.  Only worth it when the grid runs for several waves.
+void stagger_params(int ctas, int* n_ctas, int* ns) {
+  static int env_ns = -1;
+  if (env_ns < 0) {
+    const char* e = getenv("UMD_ATTN_STAGGER_NS");
+    env_ns = e ? atoi(e) : 0;
+  }
+  const int sms = sm_count();
+  *n_ctas = (ctas >= 4 * sms) ? sms : 0;
+  *ns = env_ns;
+}
 int segments(const RowMap& rm, int nsamples, Segment (&seg)[2]) {
   int k = 0;
   const int n0 = rm.n0 < nsamples ? rm.n0 : nsamples;
   if (n0 > 0) seg[k++] = Segment{n0, rm.s0, 0};
   if (nsamples > n0) seg[k++] = Segment{nsamples - n0, rm.s1, rm.split_row};
   return k;
-}
-int total_rows(const RowMap& rm, int nsamples) {
-  const int n0 = rm.n0 < nsamples ? rm.n0 : nsamples;
-  return n0 * rm.s0 + (nsamples - n0) * rm.s1;
 }
 
 }  // namespace
@@ -650,29 +721,34 @@ bool attention_tc_supported(const RowMap& rm, int nsamples, int H, int Dh) {
 int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
   Segment seg[2];
   const int ns = segments(a.rm, a.nsamples, seg);
-  const int rows = total_rows(a.rm, a.nsamples);
   const int D = a.H * AT_DH;
-  CUtensorMap tm128, tm16;
-  UMD_TRY(make_tmap_bf16(&tm128, a.qkv, 3 * D, rows, 1, 3 * D, 0, 128));
-  UMD_TRY(make_tmap_bf16(&tm16, a.qkv, 3 * D, rows, 1, 3 * D, 0, 16));
   static bool cfg = false;
   if (!cfg) {
     UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cfg = true;
   }
   for (int k = 0; k < ns; ++k) {
+    const int n = seg[k].n, S = seg[k].S;
+    // per-segment views [sample][row in sample][column]: loads zero-fill and stores clip rows >= S
+    const __nv_bfloat16* qkv = a.qkv + static_cast<long long>(seg[k].row_base) * 3 * D;
+    __nv_bfloat16* out = a.out + static_cast<long long>(seg[k].row_base) * D;
+    CUtensorMap tm128, tm16, tmo;
+    UMD_TRY(make_tmap_bf16(&tm128, qkv, 3 * D, S, n, 3 * D, static_cast<uint64_t>(S) * 3 * D, 128));
+    UMD_TRY(make_tmap_bf16(&tm16, qkv, 3 * D, S, n, 3 * D, static_cast<uint64_t>(S) * 3 * D, tail_rows(S)));
+    UMD_TRY(make_tmap_bf16(&tmo, out, D, S, n, D, static_cast<uint64_t>(S) * D, 128));
     FwdParams p;
     p.out = a.out; p.lse = a.lse; p.row_base = seg[k].row_base;
-    p.S = seg[k].S; p.SP = (p.S + 15) & ~15; p.nqt = (p.S + 127) / 128; p.H = a.H;
+    p.S = S; p.SP = (p.S + 15) & ~15; p.nqt = (p.S + 127) / 128; p.H = a.H;
     p.o_col = (p.SP + 31) & ~31;
     p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
     p.scale_log2 = a.scale * LOG2E;
+    stagger_params(n * a.H, &p.stagger_ctas, &p.stagger_ns);
     const int nslab = (p.SP + 63) / 64;
     int smem = (p.nqt * 128 + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 2048 /*row stats*/ + 256 + 1024;
     // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
     if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
     if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;
-    attn_fwd_tc_kernel<<<seg[k].n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, p);
+    attn_fwd_tc_kernel<<<n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, tmo, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }
@@ -682,29 +758,41 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
 int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
   Segment seg[2];
   const int ns = segments(a.rm, a.nsamples, seg);
-  const int rows = total_rows(a.rm, a.nsamples);
   const int D = a.H * AT_DH;
-  CUtensorMap tq128, tq16, td128, td16;
-  UMD_TRY(make_tmap_bf16(&tq128, a.qkv, 3 * D, rows, 1, 3 * D, 0, 128));
-  UMD_TRY(make_tmap_bf16(&tq16, a.qkv, 3 * D, rows, 1, 3 * D, 0, 16));
-  UMD_TRY(make_tmap_bf16(&td128, a.dout, D, rows, 1, D, 0, 128));
-  UMD_TRY(make_tmap_bf16(&td16, a.dout, D, rows, 1, D, 0, 16));
   static bool cfg = false;
   if (!cfg) {
-    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 223 * 1024));
     cfg = true;
   }
   for (int k = 0; k < ns; ++k) {
+    const int n = seg[k].n, S = seg[k].S;
+    const __nv_bfloat16* qkv = a.qkv + static_cast<long long>(seg[k].row_base) * 3 * D;
+    const __nv_bfloat16* dout = a.dout + static_cast<long long>(seg[k].row_base) * D;
+    __nv_bfloat16* dqkv = a.dqkv + static_cast<long long>(seg[k].row_base) * 3 * D;
+    CUtensorMap tq128, tq16, td128, td16, tmdq;
+    UMD_TRY(make_tmap_bf16(&tq128, qkv, 3 * D, S, n, 3 * D, static_cast<uint64_t>(S) * 3 * D, 128));
+    UMD_TRY(make_tmap_bf16(&tq16, qkv, 3 * D, S, n, 3 * D, static_cast<uint64_t>(S) * 3 * D, tail_rows(S)));
+    UMD_TRY(make_tmap_bf16(&td128, dout, D, S, n, D, static_cast<uint64_t>(S) * D, 128));
+    UMD_TRY(make_tmap_bf16(&td16, dout, D, S, n, D, static_cast<uint64_t>(S) * D, tail_rows(S)));
+    UMD_TRY(make_tmap_bf16(&tmdq, dqkv, 3 * D, S, n, 3 * D, static_cast<uint64_t>(S) * 3 * D, 128));
+    const __nv_bfloat16* outp = a.out + static_cast<long long>(seg[k].row_base) * D;
+    CUtensorMap to128, to16;
+    UMD_TRY(make_tmap_bf16(&to128, outp, D, S, n, D, static_cast<uint64_t>(S) * D, 128));
+    UMD_TRY(make_tmap_bf16(&to16, outp, D, S, n, D, static_cast<uint64_t>(S) * D, tail_rows(S)));
     BwdParams p;
+    p.lse_bulk = ((S * a.H * 4) % 16 == 0) && ((static_cast<long long>(seg[k].row_base) * a.H * 4) % 16 == 0) &&
+                 ((reinterpret_cast<uintptr_t>(a.lse) & 15) == 0) && (((S + 15) & ~15) * AT_ROW + S * a.H * 4 <= 4 * AT_SLAB);
     p.out = a.out; p.dout = a.dout; p.lse = a.lse; p.dqkv = a.dqkv; p.row_base = seg[k].row_base;
-    p.S = seg[k].S; p.SP = (p.S + 15) & ~15; p.nt = (p.S + 127) / 128; p.H = a.H;
+    p.S = S; p.SP = (p.S + 15) & ~15; p.nt = (p.S + 127) / 128; p.H = a.H;
     p.nbuf = p.nt <= 2 ? 2 : 1;
-    { const char* e = getenv("UMD_ATTN_PREFETCH"); p.prefetch = (p.nbuf == 2) && (e ? atoi(e) != 0 : true); }
+    { const char* e = getenv("UMD_ATTN_PREFETCH"); p.prefetch = e ? atoi(e) != 0 : 1; }
     p.scale = a.scale; p.scale_log2 = a.scale * LOG2E;
     p.tl = g_attn_timeline;
-    int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 2 * AT_STAT_N * 4 + 256 + 1024;
+    { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
+    stagger_params(n * a.H, &p.stagger_ctas, &p.stagger_ns);
+    int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 256 + 1024;   // + 3 KB of static shared memory
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
-    attn_bwd_tc_kernel<<<seg[k].n * a.H, AT_THREADS, smem, st>>>(tq128, tq16, td128, td16, p);
+    attn_bwd_tc_kernel<<<n * a.H, AT_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }

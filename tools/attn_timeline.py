@@ -28,5 +28,5 @@ def run(n, S, H=12):
     vals = [int(v) - t0 for v in t[k] if int(v) != 0]
     print(f"{nm:28s}", vals)
 
-for n, S in ((1480, 257), (1480, 164), (1480, 68)):
-  run(n // 12 * 12 // 12, S)
+for n, S in ((512, 257),):
+  run(n, S)
