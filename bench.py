@@ -335,9 +335,16 @@ def main():
                   "launches_per_step": prof_n[i] / args.steps}
     gm = cats["gemm"]
     gemm_tf = gm["work_per_step"] / (gm["ms_per_step"] * 1e-3) / 1e12 if gm["ms_per_step"] > 0 else 0.0
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_summary.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture
+      with open(tpath) as f:
+        traffic = json.load(f).get("traffic_bytes_per_launch_mean")
+      traffic_src = "profiles/r01_ncu_gemm_summary.json (6 captured launches, mean)"
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 forward/dgrad GEMMs)", "achieved": gemm_tf,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": gm["work_per_step"] / max(gm["launches_per_step"], 1), "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": gm["launches_per_step"], "share_of_step": gm["ms_per_step"] / ms_step}
     breakdown = {}
     for nm, c in cats.items():
@@ -358,7 +365,8 @@ def main():
                    "global_batch": B_global, "per_gpu_batch": per_gpu, "parallelism": f"dp{world}",
                    "params": model.layout.num_params, "l2": "inputs rotate over 4 batches; each step writes > 10 GB of activations (>> 126 MB L2)",
                    "precision": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / loss / AdamW (bf16 mu)"},
-        "step_tflops": fl_img * value / 1e12, "step_frac_of_bf16_peak": fl_img * value / 1e12 / peaks["tf_sustained"],
+        "step_tflops_per_gpu": fl_img * value / world / 1e12,
+        "step_frac_of_bf16_peak": fl_img * value / world / 1e12 / peaks["tf_sustained"],
         "flops_per_image": fl_img, "final_loss": final_loss,
         "roofline": roofline, "breakdown": breakdown, "profile_scopes_dropped": dropped,
         "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
