@@ -74,6 +74,8 @@ struct FwdParams {
   int o_col, tmem_cols;
   float scale_log2;
   int stagger_ctas, stagger_ns;  // first-wave CTAs start (blockIdx % 8) * stagger_ns apart (see attention_fwd_tc)
+  int tl_cta;
+  long long* tl;  // optional timeline buffer (tools/attn_timeline.py)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -140,15 +142,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
     const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
     const int ksteps = SP >> 4;
+    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && lane == 0;
     mbar_wait(bar_kv, 0);
     tc_fence_after();
-    for (int i = 0; i < nqt; ++i) {
-      if (i > 0) {
-        mbar_wait(bar_free, (i - 1) & 1);
-        tc_fence_after();
-      }
-      // (descriptors of the two score chunks are rebuilt per tile: the hoisted form of this short sequence
-      //  produced wrong columns >= 256 on hardware, see profiles/r01_notes.md)
+    TL(0, 0);
+    // S = Q_i K^T for query tile i (two column chunks when SP > 256).  (Descriptors of the two score chunks are
+    // rebuilt per tile: a hoisted form of this short sequence produced wrong columns >= 256 on hardware.)
+    auto issue_qk = [&](int i) {
       const uint64_t adesc = make_smem_desc_sw128(smem_u32(sQ + i * 128 * AT_ROW), 0, 1024);
       if (elect_one()) {
         for (int n0 = 0; n0 < SP; n0 += 256) {
@@ -161,8 +161,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         umma_commit(bar_s);
       }
       __syncwarp();
+    };
+    TL(1, 0);
+    issue_qk(0);
+    TL(2, 0);
+    for (int i = 0; i < nqt; ++i) {
+      // bar_p(i): every softmax thread has finished reading S(i) and writing P(i), and (program order) has long
+      // finished the epilogue of tile i-1 -> both the O accumulator and the S columns may be overwritten
       mbar_wait(bar_p, i & 1);
       tc_fence_after();
+      TL(3, i);
       if (elect_one()) {
         uint64_t pa = p_desc, vb = v_desc;
         int kk = 0;
@@ -180,6 +188,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         umma_commit(bar_o);
       }
       __syncwarp();
+      // the next tile's scores run right behind P V of this one, while the softmax warps do the epilogue
+      if (i + 1 < nqt) {
+        TL(1, i + 1);
+        issue_qk(i + 1);
+        TL(2, i + 1);
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
@@ -191,12 +205,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const int csplit = ((SP >> 4) + 1) / 2 * 16;          // columns [0, csplit) -> half 0, [csplit, SP) -> half 1
     const int cb = hf ? csplit : 0, ce = hf ? SP : csplit;
     const int tid = threadIdx.x - 128;
+    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
+    TL(4, 0);
     for (int i = 0; i < nqt; ++i) {
       // the previous tile's output store must have finished reading its staging slab (slab 0 of P) before pass 2
       // of this tile rewrites it; the max-exchange barrier below orders the other threads behind this wait
       if (i > 0 && tid == 0) bulk_wait_read<0>();
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
+      TL(5, i);
       // pass 1: maximum of the raw logits over this thread's columns
       float m = -INFINITY;
       for (int c = cb; c < ce; c += 32) {
@@ -220,6 +237,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         }
       }
       sMax[hf * 128 + r] = m;
+      TL(6, i);
       bar_softmax();
       m = fmaxf(m, sMax[(hf ^ 1) * 128 + r]);
       const float ms = m * sl2;
@@ -259,16 +277,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       sSum[hf * 128 + r] = sum;
       fence_proxy_async();
       mbar_arrive(bar_p);
+      TL(7, i);
       // epilogue: O / rowsum; each half owns 32 of the 64 output columns
       mbar_wait(bar_o, i & 1);
       tc_fence_after();
+      TL(8, i);
       uint32_t o0[32];
       tmem_ld_32x32(t_lane + p.o_col + 32 * hf, o0);
       tmem_ld_wait();
       tc_fence_before();
       bar_softmax();                     // partial sums of both halves are visible
       sum += sSum[(hf ^ 1) * 128 + r];
-      mbar_arrive(bar_free);
       // O / rowsum leaves as one [128 x 64] bf16 tile: staged in slab 0 of the P buffer (dead once PV has
       // completed) and written by a TMA store whose tensor map clips the rows of the tile that lie beyond S
       const int row = i * 128 + r;
@@ -288,6 +307,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         bulk_commit();
       }
       if (row < S && p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
+      TL(9, i);
     }
     if (tid == 0) bulk_wait_read<0>();
   }
@@ -743,6 +763,8 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
     p.scale_log2 = a.scale * LOG2E;
     stagger_params(n * a.H, &p.stagger_ctas, &p.stagger_ns);
+    p.tl = g_attn_timeline;
+    { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
     const int nslab = (p.SP + 63) / 64;
     int smem = (p.nqt * 128 + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 2048 /*row stats*/ + 256 + 1024;
     // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
