@@ -68,21 +68,27 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_kernel(LnFwdArgs a) {
     const bool is_cond = a.cond_row && token_of(a.rm, in_row) == 0;
     const __nv_bfloat16* bp = a.res_branch ? a.res_branch + static_cast<long long>(in_row) * D : nullptr;
     const float* gp = a.res_gate ? a.res_gate + static_cast<long long>(sample) * a.ldgate : nullptr;
+    const float* src = is_cond ? a.cond_row + static_cast<long long>(sample) * D : xp;
+    // every load of the row is issued before the first store: x_out may alias x, so a store in between would
+    // pin all later loads behind it
+    uint2 braw[NV];
+    float4 g[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane * 4 + 128 * i;
-      if (is_cond) {
-        v[i] = *reinterpret_cast<const float4*>(a.cond_row + static_cast<long long>(sample) * D + c);
-      } else {
-        v[i] = *reinterpret_cast<const float4*>(xp + c);
-        if (bp) {
-          const float4 bv = load_row4(bp + c);
-          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (gp) g = *reinterpret_cast<const float4*>(gp + c);
-          v[i].x += g.x * bv.x; v[i].y += g.y * bv.y; v[i].z += g.z * bv.z; v[i].w += g.w * bv.w;
-        }
-      }
-      if (a.x_out) *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(in_row) * D + c) = v[i];
+      v[i] = *reinterpret_cast<const float4*>(src + c);
+      braw[i] = (bp && !is_cond) ? *reinterpret_cast<const uint2*>(bp + c) : make_uint2(0u, 0u);
+      g[i] = gp ? *reinterpret_cast<const float4*>(gp + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[i].x += g[i].x * bf16_lo(braw[i].x); v[i].y += g[i].y * bf16_hi(braw[i].x);
+      v[i].z += g[i].z * bf16_lo(braw[i].y); v[i].w += g[i].w * bf16_hi(braw[i].y);
+    }
+    if (a.x_out) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(in_row) * D + lane * 4 + 128 * i) = v[i];
     }
   } else {
 #pragma unroll
@@ -102,14 +108,17 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_kernel(LnFwdArgs a) {
     if (a.mean) a.mean[r] = mean;
     if (a.rstd) a.rstd[r] = rstd;
   }
-  const float* shp = a.shift ? a.shift + static_cast<long long>(sample) * a.ldmod : nullptr;
-  const float* scp = a.scale ? a.scale + static_cast<long long>(sample) * a.ldmod : nullptr;
-  OutT* op = reinterpret_cast<OutT*>(a.out) + static_cast<long long>(r) * D;
+  // the parameter vectors never alias the output: restrict lets their loads move ahead of the row's stores
+  const float* __restrict__ shp = a.shift ? a.shift + static_cast<long long>(sample) * a.ldmod : nullptr;
+  const float* __restrict__ scp = a.scale ? a.scale + static_cast<long long>(sample) * a.ldmod : nullptr;
+  const float* __restrict__ gammap = a.gamma;
+  const float* __restrict__ betap = a.beta;
+  OutT* __restrict__ op = reinterpret_cast<OutT*>(a.out) + static_cast<long long>(r) * D;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = lane * 4 + 128 * i;
-    float4 g = *reinterpret_cast<const float4*>(a.gamma + c);
-    float4 b = *reinterpret_cast<const float4*>(a.beta + c);
+    float4 g = *reinterpret_cast<const float4*>(gammap + c);
+    float4 b = *reinterpret_cast<const float4*>(betap + c);
     float y0 = (v[i].x - mean) * rstd * g.x + b.x;
     float y1 = (v[i].y - mean) * rstd * g.y + b.y;
     float y2 = (v[i].z - mean) * rstd * g.z + b.z;
