@@ -7,6 +7,8 @@
 #include "ptx.cuh"
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 namespace umd {
 
 extern long long g_launch_count;
@@ -347,7 +349,13 @@ static int ln_bwd_dispatch(const LnBwdArgs& a, int D, int nsamples, cudaStream_t
   const bool gate = a.g_dz != nullptr;
   int smax = a.rm.n0 > 0 ? a.rm.s0 : 0;
   if (nsamples > a.rm.n0 && a.rm.s1 > smax) smax = a.rm.s1;
-  const int nchunks = ceil_div(smax, 96);
+  static int target_rows = 0;
+  if (target_rows == 0) {
+    const char* e = getenv("UMD_LN_BWD_ROWS");
+    target_rows = e ? atoi(e) : 96;
+    if (target_rows < 8) target_rows = 8;
+  }
+  const int nchunks = ceil_div(smax, target_rows);
   const int rpc = ceil_div(smax, nchunks);
   const dim3 grid(nsamples, nchunks);
   switch (D / 128) {
@@ -426,7 +434,8 @@ int gate_bwd(const GateBwdArgs& a, int D, int nsamples, cudaStream_t st) {
 // Column sums of a bf16 [rows, N] matrix accumulated into fp32 out[N] (bias gradients).
 // =========================================================================================
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows,
-                                                          int N, float* __restrict__ out, int rows_per_cta) {
+                                                          int N, float* __restrict__ out, int rows_per_cta, int seg_cols,
+                                                          long long seg_stride) {
   __shared__ float sm[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
@@ -434,7 +443,19 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   const int r1 = min(rows, r0 + rows_per_cta);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (col < N) {
-    for (int r = r0 + rl; r < r1; r += 8) {
+    int r = r0 + rl;
+    // four independent 16-byte loads in flight per thread
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * u) * ld + col);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+        acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
+      }
+    }
+    for (; r < r1; r += 8) {
       uint4 v = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld + col);
       acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
       acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
@@ -448,17 +469,21 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += sm[w][c];
-    atomicAdd(out + blockIdx.x * 256 + c, t);
+    const int col_out = blockIdx.x * 256 + c;
+    // column c of segment j = c / seg_cols goes to out[j * seg_stride + c % seg_cols] (q | k | v bias leaves)
+    const long long o = seg_cols > 0 ? (col_out / seg_cols) * seg_stride + (col_out % seg_cols) : col_out;
+    atomicAdd(out + o, t);
   }
 }
 
-int colsum_bf16(const void* x, long long ld, int rows, int N, float* out, cudaStream_t st) {
+int colsum_bf16(const void* x, long long ld, int rows, int N, float* out, cudaStream_t st, int seg_cols,
+                long long seg_stride) {
   if (rows <= 0) return UMD_OK;
   UMD_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8");
   ProfScope prof(PC_COLSUM, static_cast<double>(rows) * N * 2, st);
-  const int rpc = 512;
+  const int rpc = 256;
   dim3 grid(ceil_div(N, 256), ceil_div(rows, rpc));
-  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, N, out, rpc);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, N, out, rpc, seg_cols, seg_stride);
   UMD_LAUNCH_CHECK();
   return UMD_OK;
 }

@@ -408,8 +408,7 @@ int stack_backward(Ctx& c, Stack& s, float* dx) {
       g.split_k = pick_split(D, D, T, 3);
       UMD_TRY(gemm_bf16(g, c.st));
     }
-    for (int j = 0; j < 3; ++j)
-      UMD_TRY(colsum_bf16(P.dqkv + j * D, 3 * D, T, D, c.G(s.base + UMD_S_Q_B, lD + j * qkvb_sp), c.st));
+    UMD_TRY(colsum_bf16(P.dqkv, 3 * D, T, 3 * D, c.G(s.base + UMD_S_Q_B, lD), c.st, D, qkvb_sp));  // dbq | dbk | dbv
     {  // dY0 = [dQ|dK|dV] [Wq|Wk|Wv]^T, contraction chunked over the three kernels
       umd_gemm_args g = gemm_base(P.dqkv, c.WB(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D), T, D, 3 * D);
       g.a_mn = 0; g.b_mn = 0; g.lda = 3 * D; g.ldb = D; g.b_bs = qkv_sp; g.b_kchunk = D;

@@ -80,7 +80,9 @@ struct GateBwdArgs {
 };
 int gate_bwd(const GateBwdArgs& a, int D, int nsamples, cudaStream_t st);
 
-int colsum_bf16(const void* x, long long ld, int rows, int N, float* out, cudaStream_t st);
+// seg_cols > 0: column c is accumulated into out[(c / seg_cols) * seg_stride + c % seg_cols]
+int colsum_bf16(const void* x, long long ld, int rows, int N, float* out, cudaStream_t st, int seg_cols = 0,
+                long long seg_stride = 0);
 int colsum_f32(const float* x, long long ld, int rows, int N, float* out, cudaStream_t st);
 
 // ---- conditioning path ----------------------------------------------------------------
