@@ -13,6 +13,9 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 namespace umd {
 
 constexpr int BM = 128;
@@ -22,6 +25,7 @@ constexpr int GEMM_THREADS = 384;
 struct GemmParams {
   int M, N, K, batch, split_k;
   int a_bcast, b_bcast, b_kchunk;
+  int cta2;   // run on CTA pairs (256-row tiles)
   void* out0;
   long long ld0, bs0;
   void* out1;
@@ -35,11 +39,14 @@ struct GemmParams {
   RowMap rmap;
 };
 
-template <int BN>
+// CTA2: the tile is 256 x BN over a pair of CTAs (tcgen05 cta_group::2).  Each CTA stages its 128 rows of A and
+// half of B's BN rows, so a stage is 32 KB instead of 48 KB and the ring is 6 deep: ~3000 cycles of look-ahead
+// instead of ~2000, which is what the K = 768 GEMMs of the block need to stop waiting for TMA.
+template <int BN, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
+  static constexpr int STAGES = CTA2 ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   // epilogue staging: one [32 rows][64 bf16] swizzled chunk per epilogue warp, drained by TMA stores
   static constexpr int STAGE_OUT_BYTES = (BN >= 128) ? 8 * 4096 : 0;
@@ -63,7 +70,7 @@ struct WorkItem {
   int m0, n0, b, kb0, kb1;
 };
 // item order: n fastest, then batch, then k-split, then m — CTAs running concurrently share the A row-panel.
-template <int BN>
+template <int BN, int TM = BM>
 __device__ __forceinline__ WorkItem decode_item(long long item, int n_tiles, int batch, int split_k, int kb_total) {
   WorkItem w;
   const int n = static_cast<int>(item % n_tiles);
@@ -72,20 +79,21 @@ __device__ __forceinline__ WorkItem decode_item(long long item, int n_tiles, int
   r /= batch;
   const int ks = static_cast<int>(r % split_k);
   const int m = static_cast<int>(r / split_k);
-  w.m0 = m * BM;
+  w.m0 = m * TM;
   w.n0 = n * BN;
   w.kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / split_k);
   w.kb1 = static_cast<int>(static_cast<long long>(ks + 1) * kb_total / split_k);
   return w;
 }
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
             const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTA2>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TM = CTA2 ? 2 * BM : BM;   // rows of one work item
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -104,6 +112,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs of the pair)
+  const int worker = CTA2 ? blockIdx.x >> 1 : blockIdx.x;             // work items are dealt to CTA pairs
+  const int nworkers = CTA2 ? gridDim.x >> 1 : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -121,21 +132,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], CTA2 ? 16 : 8);   // the leader's copy collects the epilogue warps of both CTAs
     }
     for (int i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();   // the pair's barriers exist before either CTA signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const int m_tiles = (p.M + TM - 1) / TM;
   const int n_tiles = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
   const int tiles_mn = m_tiles * n_tiles;
@@ -148,34 +164,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
-      const int m0 = w.m0, n0 = w.n0, b = w.b, kb0 = w.kb0, kb1 = w.kb1;
+    // CTA2: both CTAs load their own 128 rows of A and their half of B; every byte is credited to the leader's
+    // full barrier, which therefore expects the stage of both CTAs
+    constexpr int BNL = CTA2 ? BN / 2 : BN;     // B rows staged by this CTA
+    auto load = [&](void* dst, const void* tm, uint64_t* bar, int c0, int c1, int c2) {
+      if (CTA2) tma_load_3d_2sm(dst, tm, bar, c0, c1, c2); else tma_load_3d(dst, tm, bar, c0, c1, c2);
+    };
+    for (long long item = worker; item < total_items; item += nworkers) {
+      const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const int m0 = w.m0 + rank * BM, n0 = w.n0 + rank * BNL, b = w.b, kb0 = w.kb0, kb1 = w.kb1;
       const int ba = p.a_bcast ? 0 : b;
       const int bb = p.b_bcast ? 0 : b;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-        mbar_expect_tx(&full_bar[stage], Cfg::A_BYTES + Cfg::B_BYTES);
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], (CTA2 ? 2 : 1) * (Cfg::A_BYTES + Cfg::B_BYTES));
         uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
         uint8_t* sb = smem_b + stage * Cfg::B_BYTES;
         const int k0 = kb * BK;
         if (!A_MN) {
-          tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0, ba);
+          load(sa, &tmA, &full_bar[stage], k0, m0, ba);
         } else {
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i) tma_load_3d(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], m0 + 64 * i, k0, ba);
+          for (int i = 0; i < BM / 64; ++i) load(sa + i * (64 * BK * 2), &tmA, &full_bar[stage], m0 + 64 * i, k0, ba);
         }
         if (!B_MN) {
           if (p.b_kchunk) {
             const int chunk = k0 / p.b_kchunk;
-            tma_load_3d(sb, &tmB, &full_bar[stage], k0 - chunk * p.b_kchunk, n0, chunk);
+            load(sb, &tmB, &full_bar[stage], k0 - chunk * p.b_kchunk, n0, chunk);
           } else {
-            tma_load_3d(sb, &tmB, &full_bar[stage], k0, n0, bb);
+            load(sb, &tmB, &full_bar[stage], k0, n0, bb);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_3d(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + 64 * i, k0, bb);
+          for (int i = 0; i < BNL / 64; ++i) load(sb + i * (64 * BK * 2), &tmB, &full_bar[stage], n0 + 64 * i, k0, bb);
         }
         }
         __syncwarp();
@@ -185,9 +207,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (the leader CTA of a pair)
+    constexpr uint32_t idesc = make_idesc_bf16(TM, BN, A_MN, B_MN);
     // per UMMA_K (=16 elements) advance of the descriptor start address, in 16-byte units
     constexpr uint32_t a_adv = A_MN ? (16 * 128) >> 4 : 32 >> 4;
     constexpr uint32_t b_adv = B_MN ? (16 * 128) >> 4 : 32 >> 4;
@@ -195,8 +217,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
+    for (long long item = worker; item < total_items; item += nworkers, ++it) {
+      const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
       const int kb0 = w.kb0, kb1 = w.kb1;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -213,10 +235,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            umma_f16_ss(d_tmem, adesc + k * a_adv, bdesc + k * b_adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2) umma_f16_ss_2sm(d_tmem, adesc + k * a_adv, bdesc + k * b_adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_f16_ss(d_tmem, adesc + k * a_adv, bdesc + k * b_adv, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          if (CTA2) {   // frees the stage / publishes the accumulator in both CTAs
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_2sm(&tfull_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -233,9 +261,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int HALF_COLS = BN / 2;
     uint32_t aux_uses = 0;
     int it = 0;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      const WorkItem w = decode_item<BN>(item, n_tiles, p.batch, p.split_k, kb_total);
-      const int m0 = w.m0, n0 = w.n0, b = w.b;
+    for (long long item = worker; item < total_items; item += nworkers, ++it) {
+      const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const int m0 = w.m0 + rank * BM, n0 = w.n0, b = w.b;   // this CTA's 128 rows of the accumulator, all BN columns
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
@@ -448,7 +476,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }  // !STAGED
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_leader(&tempty_bar[as]); else mbar_arrive(&tempty_bar[as]);
+      }
     }
     if (STAGED && lane == 0) bulk_wait<0>();  // the staging buffer must outlive the last TMA store's read
     (void)aux_uses;
@@ -456,10 +486,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();   // neither CTA of a pair leaves while its peer may still read it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS); else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -468,23 +498,42 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // ---------------------------------------------------------------------------------------
 extern long long g_launch_count;
 
-template <int BN, bool A_MN, bool B_MN, int EPI>
-static int launch_gemm_t(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
-  const CUtensorMap &tmA = tm[0], &tmB = tm[1];
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI>;
+template <int BN, bool A_MN, bool B_MN, int EPI, bool CTA2>
+static int launch_gemm_cfg(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, CTA2>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, EPI, CTA2>;
   static bool configured = false;
   if (!configured) {
     UMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
-  const int m_tiles = ceil_div(p.M, BM), n_tiles = ceil_div(p.N, BN);
-  long long items = static_cast<long long>(m_tiles) * n_tiles * p.split_k * p.batch;
-  int grid = static_cast<int>(items < sm_count() ? items : sm_count());
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tm[2], tm[3], tm[4], p);
+  const int tile_m = CTA2 ? 2 * BM : BM;
+  const int m_tiles = ceil_div(p.M, tile_m), n_tiles = ceil_div(p.N, BN);
+  const long long items = static_cast<long long>(m_tiles) * n_tiles * p.split_k * p.batch;
+  const int workers_max = CTA2 ? sm_count() / 2 : sm_count();
+  const int workers = static_cast<int>(items < workers_max ? items : workers_max);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(CTA2 ? 2 * workers : workers);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTA2 ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  UMD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tm[0], tm[1], tm[2], tm[3], tm[4], p));
   ++g_launch_count;
-  UMD_CHECK_CUDA(cudaGetLastError());
   return UMD_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int EPI>
+static int launch_gemm_t(const CUtensorMap* tm, const GemmParams& p, cudaStream_t stream) {
+  if (BN == 256 && p.cta2) return launch_gemm_cfg<256, A_MN, B_MN, EPI, true>(tm, p, stream);
+  return launch_gemm_cfg<BN, A_MN, B_MN, EPI, false>(tm, p, stream);
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -549,13 +598,22 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   else if (a.N <= 128) bn = 128;
   else if (a.N % 256 != 0 && a.N % 128 == 0 && a.N < 1024) bn = 128;
 
+  {
+    static int use2 = -1;
+    if (use2 < 0) {
+      const char* e = getenv("UMD_GEMM_CTA2");
+      use2 = e ? atoi(e) : 1;
+    }
+    p.cta2 = (use2 && bn == 256 && a.M >= 256) ? 1 : 0;
+  }
+  const int b_box = p.cta2 ? bn / 2 : bn;   // rows of B staged per CTA
   CUtensorMap tm[5];
   CUtensorMap &tmA = tm[0], &tmB = tm[1];
   const uint64_t a_batch = p.a_bcast ? 1 : a.batch, b_batch = p.b_bcast ? 1 : a.batch;
   if (!a.a_mn) UMD_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a_batch, a.lda, a.a_bs, BM));
   else         UMD_TRY(make_tmap_bf16(&tmA, a.A, a.M, a.K, a_batch, a.lda, a.a_bs, BK));
-  if (a.b_kchunk) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.b_kchunk, a.N, a.K / a.b_kchunk, a.ldb, a.b_bs, bn));
-  else if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, bn));
+  if (a.b_kchunk) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.b_kchunk, a.N, a.K / a.b_kchunk, a.ldb, a.b_bs, b_box));
+  else if (!a.b_mn) UMD_TRY(make_tmap_bf16(&tmB, a.B, a.K, a.N, b_batch, a.ldb, a.b_bs, b_box));
   else         UMD_TRY(make_tmap_bf16(&tmB, a.B, a.N, a.K, b_batch, a.ldb, a.b_bs, BK));
 
   tm[2] = tm[3] = tm[4] = tmA;  // placeholders for the epilogues that do not use them
