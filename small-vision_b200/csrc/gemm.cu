@@ -40,16 +40,17 @@ struct GemmParams {
 };
 
 // CTA2: the tile is 256 x BN over a pair of CTAs (tcgen05 cta_group::2).  Each CTA stages its 128 rows of A and
-// half of B's BN rows, so a stage is 32 KB instead of 48 KB and the ring is 6 deep: ~3000 cycles of look-ahead
-// instead of ~2000, which is what the K = 768 GEMMs of the block need to stop waiting for TMA.
+// half of B's BN rows, so a stage is 32 KB instead of 48 KB and the ring is 5 deep (~2500 cycles of look-ahead
+// instead of ~2000, plus room for double-buffered epilogue staging), which is what the K = 768 GEMMs of the block need to stop waiting for TMA.
 template <int BN, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
-  static constexpr int STAGES = CTA2 ? 6 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGES = CTA2 ? 5 : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int OUT_BUFS = CTA2 ? 2 : 1;   // staging chunks per epilogue warp (2: a store drains while the next is staged)
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   // epilogue staging: one [32 rows][64 bf16] swizzled chunk per epilogue warp, drained by TMA stores
-  static constexpr int STAGE_OUT_BYTES = (BN >= 128) ? 8 * 4096 : 0;
+  static constexpr int STAGE_OUT_BYTES = (BN >= 128) ? 8 * OUT_BUFS * 4096 : 0;
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGE_OUT_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
@@ -260,6 +261,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = ew >> 2;           // which half of the BN columns
     constexpr int HALF_COLS = BN / 2;
     uint32_t aux_uses = 0;
+    uint32_t nstaged = 0;   // chunks staged by this warp so far (selects the staging buffer)
     int it = 0;
     for (long long item = worker; item < total_items; item += nworkers, ++it) {
       const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
@@ -276,17 +278,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (EPI == UMD_EPI_GATE_RES && p.gate && row_ok) sample = sample_of(p.rmap, row);
 
       if constexpr (STAGED) {
-        uint8_t* sbuf = smem_out + ew * 4096;
+        constexpr int NB = Cfg::OUT_BUFS;
+        uint8_t* sbuf0 = smem_out + ew * (NB * 4096);
         const int srow = quad * 32 + lane;
-        uint8_t* my_row = sbuf + lane * 128;
         const int sw = lane & 7;
         const int trow = m0 + quad * 32;   // first row of this warp's 32-row slab
 #pragma unroll 1
         for (int c = 0; c < HALF_COLS; c += 64) {
           const int col0 = n0 + half * HALF_COLS + c;
           const bool active = col0 < p.N;  // warp-uniform
+          // staging buffer of this chunk; bulk_wait_read<NB-1>: the store that last used it has drained
+          uint8_t* sbuf = sbuf0 + (nstaged % NB) * 4096;
+          uint8_t* my_row = sbuf + lane * 128;
           if (EPI == UMD_EPI_DGELU && active && lane == 0) {
-            bulk_wait_read<0>();
+            bulk_wait_read<NB - 1>();
             mbar_expect_tx(&aux_bar[ew], 4096);
             tma_load_3d(sbuf, &tmAux, &aux_bar[ew], col0, trow, 0);
           }
@@ -323,7 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
             } else {
-              if (lane == 0) bulk_wait_read<0>();
+              if (lane == 0) bulk_wait_read<NB - 1>();
               __syncwarp();
             }
 #pragma unroll
@@ -338,8 +343,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_store_3d(&tmO0, sbuf, col0, trow, b);
               bulk_commit();
             }
+            ++nstaged;
             if (EPI == UMD_EPI_GELU) {
-              if (lane == 0) bulk_wait_read<0>();
+              sbuf = sbuf0 + (nstaged % NB) * 4096;
+              my_row = sbuf + lane * 128;
+              if (lane == 0) bulk_wait_read<NB - 1>();
               __syncwarp();
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -355,6 +363,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 tma_store_3d(&tmO1, sbuf, col0, trow, b);
                 bulk_commit();
               }
+              ++nstaged;
             }
           }
           (void)srow;
@@ -482,6 +491,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     if (STAGED && lane == 0) bulk_wait<0>();  // the staging buffer must outlive the last TMA store's read
     (void)aux_uses;
+    (void)nstaged;
   }
 
   __syncwarp();
