@@ -66,42 +66,91 @@ __device__ __forceinline__ void load_rows(uint8_t* dst, const CUtensorMap* tm128
   if (r < rows) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, r, sample);  // one box of rows % 128 rows
 }
 
+// rows [r0, r1) of one sample (r0 a multiple of 128), see load_rows
+__device__ __forceinline__ void load_rows_from(uint8_t* dst, const CUtensorMap* tm128, const CUtensorMap* tm16, uint64_t* bar,
+                                               int col, int sample, int r0, int r1) {
+  int r = r0;
+#pragma unroll 1
+  for (; r + 128 <= r1; r += 128) tma_load_3d(dst + r * AT_ROW, tm128, bar, col, r, sample);
+  if (r < r1) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, r, sample);
+}
+
 struct FwdParams {
   __nv_bfloat16* out;
   float* lse;
   int row_base;  // first row of the segment
-  int S, SP, nqt, H;
+  int S, SP, H;
+  int nqt;       // 128-query tiles that run on the tensor cores
+  int ntail;     // trailing query rows (S = 128 nqt + ntail, ntail <= AT_TAIL) computed on the idle control warps
+  int csplit;    // score columns [0, csplit) belong to softmax half 0, [csplit, SP) to half 1 (multiple of 16)
   int o_col, tmem_cols;
   float scale_log2;
-  int stagger_ctas, stagger_ns;  // first-wave CTAs start (blockIdx % 8) * stagger_ns apart (see attention_fwd_tc)
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py)
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+constexpr int AT_TAIL = 4;        // largest query / key tail handled outside the 128-row tiles
+constexpr int AT_TAIL_THREADS = 96;
+
+// W score columns [c, c + W) of one query row: running maximum
+template <int W, bool MASK>
+__device__ __forceinline__ void fwd_max(const uint32_t* v, int c, int S, float (&m)[4]) {
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    float x = __uint_as_float(v[j]);
+    if (MASK) x = (c + j < S) ? x : -INFINITY;
+    m[j & 3] = fmaxf(m[j & 3], x);
+  }
+}
+// ... p = exp2(s * scale*log2e - max) -> partial row sums and the bf16 P tile (K-major, 128B swizzle)
+template <int W, bool MASK>
+__device__ __forceinline__ void fwd_exp(const uint32_t* v, int c, int S, float sl2, float ms, float (&sum)[4], uint32_t sp_row,
+                                        int r7) {
+#pragma unroll
+  for (int j = 0; j < W; j += 8) {
+    float e[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float x = ex2(fmaf(__uint_as_float(v[j + q]), sl2, -ms));
+      if (MASK) x = (c + j + q < S) ? x : 0.f;
+      e[q] = x;
+      sum[q & 3] += x;
+    }
+    const int cc = c + j;
+    st_shared_v4(sp_row + ((cc >> 6) << 14) + ((((cc >> 3) & 7) ^ r7) << 4), pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]),
+                 pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+  }
+}
+
+// TWO: the CTA needs at most 256 TMEM columns and half of the shared memory, so two of them share an SM (the register
+// budget is then 85 per thread)
+template <bool TWO>
+__global__ void __launch_bounds__(AT_THREADS, TWO ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                    const __grid_constant__ CUtensorMap tmo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if (static_cast<int>(blockIdx.x) < p.stagger_ctas) __nanosleep((blockIdx.x & 7) * p.stagger_ns);
   const int S = p.S, SP = p.SP, nqt = p.nqt;
   const int D = p.H * AT_DH;
   const int h = blockIdx.x % p.H;
   const int sample = blockIdx.x / p.H;   // within the segment
   const int row0 = p.row_base + sample * S;
   const int nslab = (SP + 63) >> 6;
-  uint8_t* sQ = smem;                      // nqt * 128 rows (rows >= SP stay unwritten: they only feed unused lanes)
-  uint8_t* sK = sQ + nqt * 128 * AT_ROW;   // SP rows
+  const int qrows = max(nqt * 128, SP);
+  uint8_t* sQ = smem;                      // qrows rows (rows >= SP stay unwritten: they only feed unused lanes)
+  uint8_t* sK = sQ + qrows * AT_ROW;       // SP rows
   uint8_t* sV = sK + SP * AT_ROW;          // SP rows
   uint8_t* sP = sV + SP * AT_ROW;          // nslab slabs [128 q][64 kv]
   float* sMax = reinterpret_cast<float*>(sP + nslab * AT_SLAB);    // [2 halves][128 rows]
   float* sSum = sMax + 256;                                        // [2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 256);
-  uint64_t* bar_kv = bars + 0;
-  uint64_t* bar_s = bars + 1;
-  uint64_t* bar_p = bars + 2;
-  uint64_t* bar_o = bars + 3;
-  uint64_t* bar_free = bars + 4;
+  float* sTs = sSum + 256;                                         // [AT_MAX_S] tail-row scores / probabilities
+  float* sTr = sTs + AT_MAX_S;                                     // [3][64] tail-row partial outputs, [8] reductions
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTr + 3 * 64 + 16);
+  uint64_t* bar_k = bars + 0;    // K and the first query tile have landed
+  uint64_t* bar_v = bars + 1;    // V and the remaining query rows have landed
+  uint64_t* bar_s = bars + 2;    // scores of the current tile are in TMEM
+  uint64_t* bar_o = bars + 3;    // P V of the current tile is in TMEM
+  uint64_t* bar_p = bars + 4;    // P of the current tile is in shared memory (and S, O_{i-1} have been read)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,11 +160,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     tma_prefetch_desc(&tmo);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(bar_kv, 1);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_p, AT_SM_THREADS);
     mbar_init(bar_o, 1);
-    mbar_init(bar_free, AT_SM_THREADS);
+    mbar_init(bar_p, AT_SM_THREADS);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -129,21 +178,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------------------------------ TMA producer
-    mbar_expect_tx(bar_kv, 3u * SP * AT_ROW);
-    load_rows(sK, &tm128, &tm16, bar_kv, D + h * AT_DH, sample, SP);
-    load_rows(sQ, &tm128, &tm16, bar_kv, h * AT_DH, sample, SP);
-    load_rows(sV, &tm128, &tm16, bar_kv, 2 * D + h * AT_DH, sample, SP);
-  } else if (warp == 1) {
+    // two completion groups so that Q_0 K^T can start once half of the bytes are in
+    const int q0rows = min(128, SP);
+    mbar_expect_tx(bar_k, static_cast<uint32_t>(SP + q0rows) * AT_ROW);
+    load_rows_from(sK, &tm128, &tm16, bar_k, D + h * AT_DH, sample, 0, SP);
+    load_rows_from(sQ, &tm128, &tm16, bar_k, h * AT_DH, sample, 0, q0rows);
+    mbar_expect_tx(bar_v, static_cast<uint32_t>(2 * SP - q0rows) * AT_ROW);
+    load_rows_from(sV, &tm128, &tm16, bar_v, 2 * D + h * AT_DH, sample, 0, SP);
+    if (SP > q0rows) load_rows_from(sQ, &tm128, &tm16, bar_v, h * AT_DH, sample, 128, SP);
+  }
+  if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged; the tcgen05
     // instructions themselves run under elect.sync so that descriptors stay in uniform registers)
-    // Descriptors are built once; every MMA below only adds a constant to the 14-bit start-address field
-    // (units of 16 bytes; shared memory is < 256 KB so the add never carries out of the field).
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);
     const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
     const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
     const int ksteps = SP >> 4;
     const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && lane == 0;
-    mbar_wait(bar_kv, 0);
+    mbar_wait(bar_k, 0);
     tc_fence_after();
     TL(0, 0);
     // S = Q_i K^T for query tile i (two column chunks when SP > 256).  (Descriptors of the two score chunks are
@@ -165,6 +217,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     TL(1, 0);
     issue_qk(0);
     TL(2, 0);
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
     for (int i = 0; i < nqt; ++i) {
       // bar_p(i): every softmax thread has finished reading S(i) and writing P(i), and (program order) has long
       // finished the epilogue of tile i-1 -> both the O accumulator and the S columns may be overwritten
@@ -200,10 +254,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const int quad = warp & 3;
     const int hf = (warp - 4) >> 2;  // which half of the score columns (and of the 64 output columns)
     const int r = quad * 32 + lane;  // row inside the query tile = TMEM lane
+    const int r7 = r & 7;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const uint32_t sp_row = smem_u32(sP) + r * AT_ROW;
     const float sl2 = p.scale_log2;
-    const int csplit = ((SP >> 4) + 1) / 2 * 16;          // columns [0, csplit) -> half 0, [csplit, SP) -> half 1
-    const int cb = hf ? csplit : 0, ce = hf ? SP : csplit;
+    const int cb = hf ? p.csplit : 0, ce = hf ? SP : p.csplit;
     const int tid = threadIdx.x - 128;
     const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
     TL(4, 0);
@@ -214,69 +269,47 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
       TL(5, i);
-      // pass 1: maximum of the raw logits over this thread's columns
-      float m = -INFINITY;
+      // pass 1: maximum of the raw logits over this thread's columns (32 at a time; a 16-column remainder last)
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
       for (int c = cb; c < ce; c += 32) {
+        uint32_t v[32];
         if (c + 32 <= ce) {
-          uint32_t v[32];
           tmem_ld_32x32(t_lane + c, v);
-          tmem_ld_wait();
-          if (c + 32 <= S) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, (c + j < S) ? __uint_as_float(v[j]) : -INFINITY);
-          }
+          tmem_ld_wait_dep32(v);
+          if (c + 32 <= S) fwd_max<32, false>(v, c, S, m4); else fwd_max<32, true>(v, c, S, m4);
         } else {
-          uint32_t v[16];
-          tmem_ld_32x16(t_lane + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) m = fmaxf(m, (c + j < S) ? __uint_as_float(v[j]) : -INFINITY);
+          tmem_ld_32x16(t_lane + c, reinterpret_cast<uint32_t(&)[16]>(v));
+          tmem_ld_wait_dep16(reinterpret_cast<uint32_t(&)[16]>(v));
+          if (c + 16 <= S) fwd_max<16, false>(v, c, S, m4); else fwd_max<16, true>(v, c, S, m4);
         }
       }
+      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       sMax[hf * 128 + r] = m;
       TL(6, i);
       bar_softmax();
       m = fmaxf(m, sMax[(hf ^ 1) * 128 + r]);
       const float ms = m * sl2;
       // pass 2: p = exp2(s * scale*log2e - max), partial row sum, bf16 P -> shared memory
-      float sum = 0.f;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
       for (int c = cb; c < ce; c += 32) {
         uint32_t v[32];
-        const bool full = (c + 32 <= ce);
-        if (full) {
+        if (c + 32 <= ce) {
           tmem_ld_32x32(t_lane + c, v);
+          tmem_ld_wait_dep32(v);
+          if (c + 32 <= S) fwd_exp<32, false>(v, c, S, sl2, ms, s4, sp_row, r7); else fwd_exp<32, true>(v, c, S, sl2, ms, s4, sp_row, r7);
         } else {
-          uint32_t w[16];
-          tmem_ld_32x16(t_lane + c, w);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = w[j];
-#pragma unroll
-          for (int j = 16; j < 32; ++j) v[j] = 0;
-        }
-        tmem_ld_wait();
-        const bool nomask = (c + 32 <= S);
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (full || j < 16) {
-            float e[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float x = ex2(__uint_as_float(v[j + q]) * sl2 - ms);
-              e[q] = (nomask || c + j + q < S) ? x : 0.f;
-              sum += e[q];
-            }
-            const int cc = c + j;
-            st_swz(sP + (cc >> 6) * AT_SLAB, r, (cc & 63) >> 3,
-                   make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7])));
-          }
+          tmem_ld_32x16(t_lane + c, reinterpret_cast<uint32_t(&)[16]>(v));
+          tmem_ld_wait_dep16(reinterpret_cast<uint32_t(&)[16]>(v));
+          if (c + 16 <= S) fwd_exp<16, false>(v, c, S, sl2, ms, s4, sp_row, r7); else fwd_exp<16, true>(v, c, S, sl2, ms, s4, sp_row, r7);
         }
       }
-      sSum[hf * 128 + r] = sum;
+      tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_p);
+      float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      sSum[hf * 128 + r] = sum;
       TL(7, i);
       // epilogue: O / rowsum; each half owns 32 of the 64 output columns
       mbar_wait(bar_o, i & 1);
@@ -284,7 +317,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       TL(8, i);
       uint32_t o0[32];
       tmem_ld_32x32(t_lane + p.o_col + 32 * hf, o0);
-      tmem_ld_wait();
+      tmem_ld_wait_dep32(o0);
       tc_fence_before();
       bar_softmax();                     // partial sums of both halves are visible
       sum += sSum[(hf ^ 1) * 128 + r];
@@ -294,15 +327,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       const float inv = 1.f / sum;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        st_swz(sP, r, 4 * hf + (j >> 3),
-               make_uint4(pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
-                          pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
-                          pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
-                          pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv)));
+        st_shared_v4(sp_row + (((4 * hf + (j >> 3)) ^ r7) << 4),
+                     pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
       }
       fence_proxy_async();
       bar_softmax();
       if (tid == 0) {
+        // rows of the last tile that belong to the SIMT tail (and rows >= S) must not be written: the tensor map's
+        // row extent is 128 nqt when there is a tail
         tma_store_3d(&tmo, sP, h * AT_DH, i * 128, sample);
         bulk_commit();
       }
@@ -310,6 +345,75 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       TL(9, i);
     }
     if (tid == 0) bulk_wait_read<0>();
+  } else if (!TWO && p.ntail > 0) {
+    // ------------------------------------------------------------------ query tail on CUDA cores (warps 0, 2, 3;
+    // compiled only into the one-CTA-per-SM variant: the launcher sends every shape with a tail there)
+    // S = 128 nqt + ntail with ntail <= AT_TAIL (every decoder of the reference has 257 tokens, the label-conditioned
+    // encoder 260): a third query tile would run the whole softmax for one to four live rows.  The idle control
+    // warps compute those rows from the K / V / Q tiles already in shared memory instead.
+    __syncwarp();
+    const int tt = (warp == 0 ? 0 : warp - 1) * 32 + lane;   // 0..95
+    const int tw = tt >> 5;
+    const float sl2 = p.scale_log2;
+    const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV);
+    mbar_wait(bar_k, 0);
+    mbar_wait(bar_v, 0);
+    for (int t = 0; t < p.ntail; ++t) {
+      const int qrow = nqt * 128 + t;
+      // scores of query qrow against every key: one key per thread, 64-long dot product on packed bf16 pairs
+      uint4 qv[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) qv[c] = ld_shared_v4(q_u + qrow * AT_ROW + ((c ^ (qrow & 7)) << 4));
+      float mx = -INFINITY;
+      for (int k = tt; k < SP; k += AT_TAIL_THREADS) {
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 kv = ld_shared_v4(k_u + k * AT_ROW + ((c ^ (k & 7)) << 4));
+          acc += bf16_lo(qv[c].x) * bf16_lo(kv.x) + bf16_hi(qv[c].x) * bf16_hi(kv.x) + bf16_lo(qv[c].y) * bf16_lo(kv.y) +
+                 bf16_hi(qv[c].y) * bf16_hi(kv.y) + bf16_lo(qv[c].z) * bf16_lo(kv.z) + bf16_hi(qv[c].z) * bf16_hi(kv.z) +
+                 bf16_lo(qv[c].w) * bf16_lo(kv.w) + bf16_hi(qv[c].w) * bf16_hi(kv.w);
+        }
+        const float sc = (k < S) ? acc * sl2 : -INFINITY;
+        sTs[k] = sc;
+        mx = fmaxf(mx, sc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) sTr[192 + tw] = mx;
+      bar_sync_named(2, AT_TAIL_THREADS);
+      mx = fmaxf(fmaxf(sTr[192], sTr[193]), sTr[194]);
+      float sum = 0.f;
+      for (int k = tt; k < SP; k += AT_TAIL_THREADS) {
+        const float e = ex2(sTs[k] - mx);   // exp2(-inf) = 0 for the padded keys
+        sTs[k] = e;
+        sum += e;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) sTr[196 + tw] = sum;
+      bar_sync_named(2, AT_TAIL_THREADS);
+      sum = sTr[196] + sTr[197] + sTr[198];
+      // O[qrow] = P V: lane owns output columns 2 lane, 2 lane + 1; warp tw takes keys tw, tw + 3, ...
+      float o0 = 0.f, o1 = 0.f;
+      for (int k = tw; k < S; k += 3) {
+        const float pk = sTs[k];
+        const uint32_t vv = ld_shared_b32(v_u + k * AT_ROW + (((lane >> 2) ^ (k & 7)) << 4) + ((lane & 3) << 2));
+        o0 = fmaf(pk, bf16_lo(vv), o0);
+        o1 = fmaf(pk, bf16_hi(vv), o1);
+      }
+      sTr[tw * 64 + 2 * lane] = o0;
+      sTr[tw * 64 + 2 * lane + 1] = o1;
+      bar_sync_named(2, AT_TAIL_THREADS);
+      if (tw == 0) {
+        const float inv = 1.f / sum;
+        o0 = (sTr[2 * lane] + sTr[64 + 2 * lane] + sTr[128 + 2 * lane]) * inv;
+        o1 = (sTr[2 * lane + 1] + sTr[64 + 2 * lane + 1] + sTr[128 + 2 * lane + 1]) * inv;
+        *reinterpret_cast<uint32_t*>(p.out + static_cast<long long>(row0 + qrow) * D + h * AT_DH + 2 * lane) = pack_bf16x2(o0, o1);
+        if (lane == 0 && p.lse) p.lse[static_cast<long long>(row0 + qrow) * p.H + h] = (mx + log2f(sum)) * LN2;
+      }
+      bar_sync_named(2, AT_TAIL_THREADS);   // scratch is reused by the next tail row
+    }
   }
 
   __syncwarp();
@@ -706,6 +810,17 @@ int tail_rows(int S) {
   const int t = ((S + 15) & ~15) % 128;
   return t ? t : 16;
 }
+// S = 128 * tiles + tail: a tail of 1..AT_TAIL rows behind at least one full tile is computed on CUDA cores
+void split_tail(int S, int* tiles, int* tail) {
+  const int t = S % 128;
+  if (S > 128 && t >= 1 && t <= AT_TAIL) {
+    *tiles = S / 128;
+    *tail = t;
+  } else {
+    *tiles = (S + 127) / 128;
+    *tail = 0;
+  }
+}
 // Every CTA of these kernels runs the same load -> compute -> store sequence for the same time, so a grid that
 // starts in lockstep stays in lockstep and hammers HBM in bursts.  Offsetting the start of the first wave spreads
 // the phases for the rest of the launch.  Only worth it when the grid runs for several waves.
@@ -744,7 +859,8 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
   const int D = a.H * AT_DH;
   static bool cfg = false;
   if (!cfg) {
-    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     cfg = true;
   }
   for (int k = 0; k < ns; ++k) {
@@ -758,19 +874,24 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     UMD_TRY(make_tmap_bf16(&tmo, out, D, S, n, D, static_cast<uint64_t>(S) * D, 128));
     FwdParams p;
     p.out = a.out; p.lse = a.lse; p.row_base = seg[k].row_base;
-    p.S = S; p.SP = (p.S + 15) & ~15; p.nqt = (p.S + 127) / 128; p.H = a.H;
+    p.S = S; p.SP = (p.S + 15) & ~15; p.H = a.H;
+    split_tail(S, &p.nqt, &p.ntail);
+    p.csplit = ((p.SP >> 4) + 1) / 2 * 16;
     p.o_col = (p.SP + 31) & ~31;
     p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
     p.scale_log2 = a.scale * LOG2E;
-    stagger_params(n * a.H, &p.stagger_ctas, &p.stagger_ns);
     p.tl = g_attn_timeline;
     { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
     const int nslab = (p.SP + 63) / 64;
-    int smem = (p.nqt * 128 + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 2048 /*row stats*/ + 256 + 1024;
+    const int qrows = p.nqt * 128 > p.SP ? p.nqt * 128 : p.SP;
+    int smem = (qrows + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 2048 /*row stats*/ + (AT_MAX_S + 208) * 4 /*tail scratch*/ + 256 + 1024;
     // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
     if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
     if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;
-    attn_fwd_tc_kernel<<<n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, tmo, p);
+    if (p.tmem_cols == 256 && smem <= 113 * 1024 && p.ntail == 0)
+      attn_fwd_tc_kernel<true><<<n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, tmo, p);
+    else
+      attn_fwd_tc_kernel<false><<<n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, tmo, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }
