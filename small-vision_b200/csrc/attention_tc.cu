@@ -36,8 +36,8 @@ constexpr int AT_DH = 64;
 constexpr int AT_MAX_S = 272;
 constexpr int AT_ROW = 128;            // bytes per 64-element bf16 row
 constexpr int AT_SLAB = 128 * AT_ROW;  // [128 rows][64 cols] bf16 = 16 KB
-constexpr int AT_THREADS = 384;         // 4 control warps + 8 softmax warps (two per TMEM lane quadrant)
-constexpr int AT_SM_THREADS = 256;      // softmax / epilogue threads
+constexpr int AT_BWD_THREADS = 640;     // backward: 4 control warps + 16 softmax warps (four per TMEM lane quadrant)
+constexpr int AT_BWD_SM = 512;          // backward: softmax / epilogue threads
 constexpr int AT_STAT_N = 384;         // per-query statistics padded to three 128-query tiles
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -50,6 +50,8 @@ __device__ __forceinline__ float ex2(float x) {
 #define TL(slot, idx) do { if (tl_on) p.tl[(slot) * 64 + (idx)] = clock64(); } while (0)
 
 __device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NT>
+__device__ __forceinline__ void bar_softmax_n() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // 16-byte chunk `chunk` (0..7) of row r of a [rows][64] bf16 slab in the 128B-swizzled layout TMA / UMMA use.
 __device__ __forceinline__ void st_swz(uint8_t* slab, int r, int chunk, uint4 v) {
@@ -75,6 +77,15 @@ __device__ __forceinline__ void load_rows_from(uint8_t* dst, const CUtensorMap* 
   if (r < r1) tma_load_3d(dst + r * AT_ROW, tm16, bar, col, r, sample);
 }
 
+// L2 prefetch of rows [0, rows) of one sample: issued for the (sample, head) that the CTA one resident wave ahead
+// will load, so that its TMA loads hit L2 instead of paying the HBM round trip at the head of a serial chain
+__device__ __forceinline__ void prefetch_rows(const CUtensorMap* tm128, const CUtensorMap* tm16, int col, int sample, int rows) {
+  int r = 0;
+#pragma unroll 1
+  for (; r + 128 <= rows; r += 128) tma_prefetch_l2_3d(tm128, col, r, sample);
+  if (r < rows) tma_prefetch_l2_3d(tm16, col, r, sample);
+}
+
 struct FwdParams {
   __nv_bfloat16* out;
   float* lse;
@@ -82,8 +93,8 @@ struct FwdParams {
   int S, SP, H;
   int nqt;       // 128-query tiles that run on the tensor cores
   int ntail;     // trailing query rows (S = 128 nqt + ntail, ntail <= AT_TAIL) computed on the idle control warps
-  int csplit;    // score columns [0, csplit) belong to softmax half 0, [csplit, SP) to half 1 (multiple of 16)
   int o_col, tmem_cols;
+  int ahead;     // CTAs resident on the device at once: the L2 prefetch distance
   float scale_log2;
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py)
@@ -122,10 +133,14 @@ __device__ __forceinline__ void fwd_exp(const uint32_t* v, int c, int S, float s
   }
 }
 
-// TWO: the CTA needs at most 256 TMEM columns and half of the shared memory, so two of them share an SM (the register
-// budget is then 85 per thread)
+// Softmax needs MUFU.EX2 (16 lanes / clk / SM) behind a dependent chain TMEM load -> FFMA -> EX2 -> pack -> store; it
+// only reaches the MUFU rate with four warps per SM sub-partition (tools/ubench/pipes.cu: 64 cycles per 8 EX2 at four
+// warps, 93 at two).  NQ = softmax warps per TMEM lane quadrant; each owns 1/NQ of the score columns of its 32 rows.
+//   TWO  (NQ = 2, 384 threads): the CTA needs at most 256 TMEM columns and half of the shared memory, two CTAs share
+//        an SM (register budget 85 per thread) and supply the four warps per sub-partition between them;
+//   !TWO (NQ = 4, 640 threads): one CTA per SM.
 template <bool TWO>
-__global__ void __launch_bounds__(AT_THREADS, TWO ? 2 : 1)
+__global__ void __launch_bounds__(TWO ? 384 : 640, TWO ? 2 : 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_constant__ CUtensorMap tm16,
                    const __grid_constant__ CUtensorMap tmo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -141,9 +156,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint8_t* sK = sQ + qrows * AT_ROW;       // SP rows
   uint8_t* sV = sK + SP * AT_ROW;          // SP rows
   uint8_t* sP = sV + SP * AT_ROW;          // nslab slabs [128 q][64 kv]
-  float* sMax = reinterpret_cast<float*>(sP + nslab * AT_SLAB);    // [2 halves][128 rows]
-  float* sSum = sMax + 256;                                        // [2 halves][128 rows]
-  float* sTs = sSum + 256;                                         // [AT_MAX_S] tail-row scores / probabilities
+  constexpr int NQ = TWO ? 2 : 4;
+  constexpr int SMT = 128 * NQ;                                    // softmax / epilogue threads
+  float* sMax = reinterpret_cast<float*>(sP + nslab * AT_SLAB);    // [NQ parts][128 rows]
+  float* sSum = sMax + 512;                                        // [NQ parts][128 rows]
+  float* sTs = sSum + 512;                                         // [AT_MAX_S] tail-row scores / probabilities
   float* sTr = sTs + AT_MAX_S;                                     // [3][64] tail-row partial outputs, [8] reductions
   uint64_t* bars = reinterpret_cast<uint64_t*>(sTr + 3 * 64 + 16);
   uint64_t* bar_k = bars + 0;    // K and the first query tile have landed
@@ -164,7 +181,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
-    mbar_init(bar_p, AT_SM_THREADS);
+    mbar_init(bar_p, SMT);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -186,6 +203,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     mbar_expect_tx(bar_v, static_cast<uint32_t>(2 * SP - q0rows) * AT_ROW);
     load_rows_from(sV, &tm128, &tm16, bar_v, 2 * D + h * AT_DH, sample, 0, SP);
     if (SP > q0rows) load_rows_from(sQ, &tm128, &tm16, bar_v, h * AT_DH, sample, 128, SP);
+    const int nxt = blockIdx.x + p.ahead;
+    if (p.ahead > 0 && nxt < static_cast<int>(gridDim.x)) {
+      const int h2 = nxt % p.H, s2 = nxt / p.H;
+      prefetch_rows(&tm128, &tm16, D + h2 * AT_DH, s2, SP);
+      prefetch_rows(&tm128, &tm16, h2 * AT_DH, s2, SP);
+      prefetch_rows(&tm128, &tm16, 2 * D + h2 * AT_DH, s2, SP);
+    }
   }
   if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged; the tcgen05
@@ -252,13 +276,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
     const int quad = warp & 3;
-    const int hf = (warp - 4) >> 2;  // which half of the score columns (and of the 64 output columns)
+    const int hf = (warp - 4) >> 2;  // which part of the score columns (and of the 64 output columns)
     const int r = quad * 32 + lane;  // row inside the query tile = TMEM lane
     const int r7 = r & 7;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const uint32_t sp_row = smem_u32(sP) + r * AT_ROW;
     const float sl2 = p.scale_log2;
-    const int cb = hf ? p.csplit : 0, ce = hf ? SP : p.csplit;
+    // the SP / 16 column groups are dealt out as evenly as possible
+    const int units = SP >> 4, ubase = units / NQ, urem = units % NQ;
+    const int cb = 16 * (hf * ubase + min(hf, urem)), ce = cb + 16 * (ubase + (hf < urem ? 1 : 0));
     const int tid = threadIdx.x - 128;
     const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
     TL(4, 0);
@@ -287,8 +313,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       sMax[hf * 128 + r] = m;
       TL(6, i);
-      bar_softmax();
-      m = fmaxf(m, sMax[(hf ^ 1) * 128 + r]);
+      bar_softmax_n<SMT>();
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) m = fmaxf(m, sMax[((hf + q) % NQ) * 128 + r]);
       const float ms = m * sl2;
       // pass 2: p = exp2(s * scale*log2e - max), partial row sum, bf16 P -> shared memory
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -315,29 +342,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       mbar_wait(bar_o, i & 1);
       tc_fence_after();
       TL(8, i);
-      uint32_t o0[32];
-      tmem_ld_32x32(t_lane + p.o_col + 32 * hf, o0);
-      tmem_ld_wait_dep32(o0);
+      constexpr int OC = 64 / NQ;          // output columns per part
+      uint32_t o0[OC];
+      if constexpr (OC == 32) {
+        tmem_ld_32x32(t_lane + p.o_col + OC * hf, o0);
+        tmem_ld_wait_dep32(o0);
+      } else {
+        tmem_ld_32x16(t_lane + p.o_col + OC * hf, o0);
+        tmem_ld_wait_dep16(o0);
+      }
       tc_fence_before();
-      bar_softmax();                     // partial sums of both halves are visible
-      sum += sSum[(hf ^ 1) * 128 + r];
+      bar_softmax_n<SMT>();                // partial sums of all parts are visible
+#pragma unroll
+      for (int q = 1; q < NQ; ++q) sum += sSum[((hf + q) % NQ) * 128 + r];
       // O / rowsum leaves as one [128 x 64] bf16 tile: staged in slab 0 of the P buffer (dead once PV has
       // completed) and written by a TMA store whose tensor map clips the rows of the tile that lie beyond S
       const int row = i * 128 + r;
       const float inv = 1.f / sum;
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        st_shared_v4(sp_row + (((4 * hf + (j >> 3)) ^ r7) << 4),
+      for (int j = 0; j < OC; j += 8) {
+        st_shared_v4(sp_row + ((((OC / 8) * hf + (j >> 3)) ^ r7) << 4),
                      pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
                      pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
                      pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
                      pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
       }
       fence_proxy_async();
-      bar_softmax();
+      bar_softmax_n<SMT>();
       if (tid == 0) {
-        // rows of the last tile that belong to the SIMT tail (and rows >= S) must not be written: the tensor map's
-        // row extent is 128 nqt when there is a tail
         tma_store_3d(&tmo, sP, h * AT_DH, i * 128, sample);
         bulk_commit();
       }
@@ -439,12 +471,13 @@ struct BwdParams {
   int prefetch;  // issue the next block's scores ahead of this block's accumulation (needs nbuf == 2)
   int stagger_ctas, stagger_ns;
   int lse_bulk;  // the sample's [S][H] lse block is 16-byte aligned: fetch it with one bulk copy
+  int ahead;     // L2 prefetch distance in CTAs (0 = off)
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py): CTA 0 records clock64() at its sync points
   float scale, scale_log2;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_constant__ CUtensorMap tq16,
                    const __grid_constant__ CUtensorMap td128, const __grid_constant__ CUtensorMap td16,
                    const __grid_constant__ CUtensorMap tmdq, const __grid_constant__ CUtensorMap to128,
@@ -493,12 +526,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     mbar_init(bar_ld, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_sfree[i], AT_SM_THREADS);
-      mbar_init(&bar_p[i], AT_SM_THREADS);
+      mbar_init(&bar_sfree[i], AT_BWD_SM);
+      mbar_init(&bar_p[i], AT_BWD_SM);
     }
     mbar_init(bar_tfree, 1);
     mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, AT_SM_THREADS);
+    mbar_init(bar_accfree, AT_BWD_SM);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -523,6 +556,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     load_rows(sdO, &td128, &td16, bar_ld, h * AT_DH, sample, SP);
     load_rows(sPt, &to128, &to16, bar_ld, h * AT_DH, sample, SP);
     if (p.lse_bulk) bulk_load_1d(sPt + SP * AT_ROW, p.lse + static_cast<long long>(row0) * p.H, lse_bytes, bar_ld);
+    const int nxt = blockIdx.x + p.ahead;
+    if (p.ahead > 0 && nxt < static_cast<int>(gridDim.x)) {
+      const int h2 = nxt % p.H, s2 = nxt / p.H;
+      prefetch_rows(&tq128, &tq16, D + h2 * AT_DH, s2, SP);
+      prefetch_rows(&tq128, &tq16, h2 * AT_DH, s2, SP);
+      prefetch_rows(&tq128, &tq16, 2 * D + h2 * AT_DH, s2, SP);
+      prefetch_rows(&td128, &td16, h2 * AT_DH, s2, SP);
+      prefetch_rows(&to128, &to16, h2 * AT_DH, s2, SP);
+    }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged, see forward)
     constexpr uint32_t idesc_kt = make_idesc_bf16(128, 64, false, true);   // A K-major (P^T / dS^T), B MN-major (dO / Q)
@@ -630,7 +672,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax backward + epilogues
     const int quad = warp & 3;
-    const int hf = (warp - 4) >> 2;  // which 32 of the 64 columns of a score half / of an output tile
+    const int hf = (warp - 4) >> 2;  // which 16 of the 64 columns of a score half / of an output tile (0..3)
     const int r = quad * 32 + lane;  // key row inside the key tile (TMEM lane); query row in the dQ epilogue
     const int tid = threadIdx.x - 128;
     const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
@@ -641,46 +683,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     // becomes the P^T / dS^T tiles after the barrier below
     {
       const float* lse_blk = reinterpret_cast<const float*>(sPt + SP * AT_ROW);   // [S][H]
-      float lse_direct[2] = {0.f, 0.f};
-      if (!p.lse_bulk) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int q = tid + 256 * u;
-          if (q < S) lse_direct[u] = p.lse[static_cast<long long>(row0 + q) * p.H + h];
-        }
-      }
+      float lse_direct = 0.f;
+      if (!p.lse_bulk && tid < S) lse_direct = p.lse[static_cast<long long>(row0 + tid) * p.H + h];
       TL(4, 2);
       mbar_wait(bar_ld, 0);
       TL(4, 3);
+      const int q = tid;   // AT_BWD_SM >= AT_MAX_S: one query row per thread
+      if (q < SP) {
+        float dl = 0.f;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int q = tid + 256 * u;
-        if (q < SP) {
-          float dl = 0.f;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const int off = q * AT_ROW + ((c ^ (q & 7)) << 4);
-            const uint4 a = *reinterpret_cast<const uint4*>(sPt + off);
-            const uint4 g = *reinterpret_cast<const uint4*>(sdO + off);
-            dl += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-                  bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
-                  bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
-          }
-          const float ls = (q < S) ? (p.lse_bulk ? lse_blk[q * p.H + h] : lse_direct[u]) * LOG2E : 0.f;
-          sDelta[q] = (q < S) ? dl : 0.f;
-          sLse[q] = ls;
+        for (int c = 0; c < 8; ++c) {
+          const int off = q * AT_ROW + ((c ^ (q & 7)) << 4);
+          const uint4 a = *reinterpret_cast<const uint4*>(sPt + off);
+          const uint4 g = *reinterpret_cast<const uint4*>(sdO + off);
+          dl += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+                bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+                bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
         }
+        const float ls = (q < S) ? (p.lse_bulk ? lse_blk[q * p.H + h] : lse_direct) * LOG2E : 0.f;
+        sDelta[q] = (q < S) ? dl : 0.f;
+        sLse[q] = ls;
       }
     }
     TL(4, 4);
-    bar_softmax();
+    bar_softmax_n<AT_BWD_SM>();
     TL(4, 1);
     const float sl2 = p.scale_log2;
+    const int r7 = r & 7;
+    const uint32_t pt_row = smem_u32(sPt) + r * AT_ROW, st_row = smem_u32(sdSt) + r * AT_ROW;
     int step = 0, blk = 0;
     bool store_pending = false;
     for (int j = 0; j < nt; ++j) {
-      const int kv = j * 128 + r;
-      const bool kv_ok = kv < S;
       for (int i = 0; i < nt; ++i) {
         const int nq = min(128, SP - 128 * i);
         const int nh = (nq + 63) >> 6;
@@ -689,25 +722,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           mbar_wait(&bar_s[b], u & 1);
           tc_fence_after();
           TL(5, step);
-          uint32_t sv[32], dv[32];
-          tmem_ld_32x32(t_lane + b * 128 + 32 * hf, sv);
-          tmem_ld_32x32(t_lane + b * 128 + 64 + 32 * hf, dv);
-          tmem_ld_wait();
+          uint32_t sv[16], dv[16];
+          tmem_ld_32x16(t_lane + b * 128 + 16 * hf, sv);
+          tmem_ld_32x16(t_lane + b * 128 + 64 + 16 * hf, dv);
+          tmem_ld_wait_dep16(sv);
+          tmem_ld_wait_dep16(dv);
           tc_fence_before();
           mbar_arrive(&bar_sfree[b]);
           TL(6, step);
           if (hh == 0 && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
           if (store_pending) {   // dK_j / dV_j of the previous key tile were staged in the P^T tile
             if (tid == 0) bulk_wait_read<0>();
-            bar_softmax();
+            bar_softmax_n<AT_BWD_SM>();
             store_pending = false;
           }
           TL(7, step);
-          const int q0 = i * 128 + hh * 64 + 32 * hf;
-          uint8_t* slabP = sPt + hh * AT_SLAB;
-          uint8_t* slabS = sdSt + hh * AT_SLAB;
+          // No masking: query columns >= S have Q = dO = 0 (TMA zero fill), lse = delta = 0, hence P = 1 against a zero
+          // dO row and dS = 0; key rows >= S only reach dK / dV rows that the TMA stores clip, and enter dQ against
+          // zero-filled K rows (rows >= SP are never read by the dQ MMA).
+          const int q0 = i * 128 + hh * 64 + 16 * hf;
+          const uint32_t rowP = pt_row + hh * AT_SLAB, rowS = st_row + hh * AT_SLAB;
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
+          for (int c = 0; c < 16; c += 8) {
             float pe[8], de[8];
             const float4 la = *reinterpret_cast<const float4*>(&sLse[q0 + c]);
             const float4 lb = *reinterpret_cast<const float4*>(&sLse[q0 + c + 4]);
@@ -717,16 +753,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
             const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const bool ok = kv_ok && (q0 + c + e < S);
-              const float pv = ex2(__uint_as_float(sv[c + e]) * sl2 - l2[e]);
-              pe[e] = ok ? pv : 0.f;
-              de[e] = ok ? pv * (__uint_as_float(dv[c + e]) - dl[e]) : 0.f;
+              pe[e] = ex2(fmaf(__uint_as_float(sv[c + e]), sl2, -l2[e]));
+              de[e] = pe[e] * (__uint_as_float(dv[c + e]) - dl[e]);
             }
-            st_swz(slabP, r, 4 * hf + (c >> 3),
-                   make_uint4(pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7])));
-            st_swz(slabS, r, 4 * hf + (c >> 3),
-                   make_uint4(pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7])));
+            const uint32_t off = ((2 * hf + (c >> 3)) ^ r7) << 4;
+            st_shared_v4(rowP + off, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
+            st_shared_v4(rowS + off, pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7]));
           }
+          TL(10, 2 + step);
           fence_proxy_async();
           mbar_arrive(&bar_p[hh]);
           TL(8, step);
@@ -739,24 +773,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       tc_fence_after();
       TL(9, j);
       {
-        uint32_t a0[32], a1[32];
-        tmem_ld_32x32(t_lane + col_dv + 32 * hf, a0);
-        tmem_ld_32x32(t_lane + col_dk + 32 * hf, a1);
-        tmem_ld_wait();
+        uint32_t a0[16], a1[16];
+        tmem_ld_32x16(t_lane + col_dv + 16 * hf, a0);
+        tmem_ld_32x16(t_lane + col_dk + 16 * hf, a1);
+        tmem_ld_wait_dep16(a0);
+        tmem_ld_wait_dep16(a1);
         tc_fence_before();
         mbar_arrive(bar_accfree);
         const float sc = p.scale;
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          st_swz(sPt, r, 4 * hf + (c >> 3), make_uint4(
+        for (int c = 0; c < 16; c += 8) {
+          const uint32_t off = ((2 * hf + (c >> 3)) ^ r7) << 4;
+          st_shared_v4(pt_row + off,
               pack_bf16x2(__uint_as_float(a0[c]), __uint_as_float(a0[c + 1])), pack_bf16x2(__uint_as_float(a0[c + 2]), __uint_as_float(a0[c + 3])),
-              pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7]))));
-          st_swz(sPt + AT_SLAB, r, 4 * hf + (c >> 3), make_uint4(
+              pack_bf16x2(__uint_as_float(a0[c + 4]), __uint_as_float(a0[c + 5])), pack_bf16x2(__uint_as_float(a0[c + 6]), __uint_as_float(a0[c + 7])));
+          st_shared_v4(pt_row + AT_SLAB + off,
               pack_bf16x2(__uint_as_float(a1[c]) * sc, __uint_as_float(a1[c + 1]) * sc), pack_bf16x2(__uint_as_float(a1[c + 2]) * sc, __uint_as_float(a1[c + 3]) * sc),
-              pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc)));
+              pack_bf16x2(__uint_as_float(a1[c + 4]) * sc, __uint_as_float(a1[c + 5]) * sc), pack_bf16x2(__uint_as_float(a1[c + 6]) * sc, __uint_as_float(a1[c + 7]) * sc));
         }
         fence_proxy_async();
-        bar_softmax();
+        bar_softmax_n<AT_BWD_SM>();
         if (tid == 0) {
           tma_store_3d(&tmdq, sPt, 2 * D + h * AT_DH, j * 128, sample);
           tma_store_3d(&tmdq, sPt + AT_SLAB, D + h * AT_DH, j * 128, sample);
@@ -769,22 +805,22 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     // dQ_i (the last bar_acc phase covers every MMA issued): staged in the P^T / dS^T tiles once the dK / dV store
     // has drained, then one TMA store per query tile
     if (tid == 0) bulk_wait_read<0>();
-    bar_softmax();
+    bar_softmax_n<AT_BWD_SM>();
     for (int i = 0; i < nt; ++i) {
-      uint32_t a0[32];
-      tmem_ld_32x32(t_lane + col_dq + 64 * i + 32 * hf, a0);
-      tmem_ld_wait();
+      uint32_t a0[16];
+      tmem_ld_32x16(t_lane + col_dq + 64 * i + 16 * hf, a0);
+      tmem_ld_wait_dep16(a0);
       const float sc = p.scale;
-      uint8_t* stage = sPt + i * AT_SLAB;   // slabs 0,1 of P^T, then slab 0 of dS^T (contiguous)
+      const uint32_t stage = pt_row + i * AT_SLAB;   // slabs 0,1 of P^T, then slab 0 of dS^T (contiguous)
 #pragma unroll
-      for (int c = 0; c < 32; c += 8) {
-        st_swz(stage, r, 4 * hf + (c >> 3), make_uint4(
+      for (int c = 0; c < 16; c += 8) {
+        st_shared_v4(stage + (((2 * hf + (c >> 3)) ^ r7) << 4),
             pack_bf16x2(__uint_as_float(a0[c]) * sc, __uint_as_float(a0[c + 1]) * sc), pack_bf16x2(__uint_as_float(a0[c + 2]) * sc, __uint_as_float(a0[c + 3]) * sc),
-            pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc)));
+            pack_bf16x2(__uint_as_float(a0[c + 4]) * sc, __uint_as_float(a0[c + 5]) * sc), pack_bf16x2(__uint_as_float(a0[c + 6]) * sc, __uint_as_float(a0[c + 7]) * sc));
       }
     }
     fence_proxy_async();
-    bar_softmax();
+    bar_softmax_n<AT_BWD_SM>();
     if (tid == 0) {
       for (int i = 0; i < nt; ++i) tma_store_3d(&tmdq, sPt + i * AT_SLAB, h * AT_DH, i * 128, sample);
       bulk_commit();
@@ -876,22 +912,25 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.out = a.out; p.lse = a.lse; p.row_base = seg[k].row_base;
     p.S = S; p.SP = (p.S + 15) & ~15; p.H = a.H;
     split_tail(S, &p.nqt, &p.ntail);
-    p.csplit = ((p.SP >> 4) + 1) / 2 * 16;
     p.o_col = (p.SP + 31) & ~31;
     p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
     p.scale_log2 = a.scale * LOG2E;
     p.tl = g_attn_timeline;
     { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
     const int nslab = (p.SP + 63) / 64;
     const int qrows = p.nqt * 128 > p.SP ? p.nqt * 128 : p.SP;
-    int smem = (qrows + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 2048 /*row stats*/ + (AT_MAX_S + 208) * 4 /*tail scratch*/ + 256 + 1024;
+    int smem = (qrows + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 4096 /*row stats*/ + (AT_MAX_S + 208) * 4 /*tail scratch*/ + 256 + 1024;
     // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
     if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
     if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;
-    if (p.tmem_cols == 256 && smem <= 113 * 1024 && p.ntail == 0)
-      attn_fwd_tc_kernel<true><<<n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, tmo, p);
+    const bool two = p.tmem_cols == 256 && smem <= 113 * 1024 && p.ntail == 0;
+    p.ahead = pf ? sm_count() * (two ? 2 : 1) : 0;
+    if (two)
+      attn_fwd_tc_kernel<true><<<n * a.H, 384, smem, st>>>(tm128, tm16, tmo, p);
     else
-      attn_fwd_tc_kernel<false><<<n * a.H, AT_THREADS, smem, st>>>(tm128, tm16, tmo, p);
+      attn_fwd_tc_kernel<false><<<n * a.H, 640, smem, st>>>(tm128, tm16, tmo, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }
@@ -933,9 +972,12 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     p.tl = g_attn_timeline;
     { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
     stagger_params(n * a.H, &p.stagger_ctas, &p.stagger_ns);
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
+    p.ahead = pf ? sm_count() : 0;
     int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 256 + 1024;   // + 3 KB of static shared memory
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
-    attn_bwd_tc_kernel<<<n * a.H, AT_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
+    attn_bwd_tc_kernel<<<n * a.H, AT_BWD_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }

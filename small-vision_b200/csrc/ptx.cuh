@@ -88,6 +88,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
 }
 
 
+// L2 prefetch of one box of a 3-D tiled tensor map (no shared-memory destination, no completion)
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 // 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion on an mbarrier
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

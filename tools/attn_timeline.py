@@ -22,7 +22,7 @@ def run(n, S, H=12):
   t = tl.cpu().reshape(11, 64)
   t0 = int(t[4, 0])
   names = ["mma:loaded", "mma:scores_issued[step]", "mma:p_ready[blk]", "mma:acc_issued[blk]", "sm:start/prologue_done", "sm:s_ready[step]",
-           "sm:ld_done[step]", "sm:tile_free[step]", "sm:stored[step]", "sm:acc_ready[j]", "sm:dq_start/end"]
+           "sm:ld_done[step]", "sm:tile_free[step]", "sm:stored[step]", "sm:acc_ready[j]", "sm:dq_start/end, then before_fence[step]"]
   print(f"--- n={n} S={S}")
   for k, nm in enumerate(names):
     vals = [int(v) - t0 for v in t[k] if int(v) != 0]
