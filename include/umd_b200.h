@@ -99,6 +99,17 @@ int umd_gemm_bf16(const umd_gemm_args* args, umd_stream_t stream);
 int umd_qsample(const float* x0, const float* noise, const int* t, const float* sqrt_alphas_cumprod,
                 const float* sqrt_one_minus_alphas_cumprod, int n, int elems_per_sample, float* out,
                 umd_stream_t stream);
+/* gaussian_diffusion.py:134-211  one DDIM update (ddim_sample over p_mean_variance), fused with the classifier-free
+ * guidance combine of a doubled batch (models/ae.py:192-195) and the eps / x0 head selection of
+ * trainers/train_ae.py:472-483.  x, noise, sample, pred_xstart: [n, hw, channels] fp32; pred: [n, hw, pred_channels]
+ * with pred_channels = 2*channels (x0 head | eps head) or = channels (eps head only; needs eps_pred), [2n, ...] with
+ * use_cfg (conditional rows first).  t_next may be null (alphas_cumprod_prev[t] is used, :187-190);
+ * pred_xstart may be null.  sample = sqrt(abar_prev) x0_hat + sqrt(1 - abar_prev - sigma^2) eps + [t > 0] sigma noise. */
+int umd_ddim_step(const float* x, const float* pred, const float* noise, const int* t, const int* t_next,
+                  const float* alphas_cumprod, const float* alphas_cumprod_prev, const float* sqrt_recip_alphas_cumprod,
+                  const float* sqrt_recipm1_alphas_cumprod, int n, int hw, int channels, int pred_channels, float eta, int use_cfg,
+                  float cfg_scale, int eps_pred, int clip_denoised, float* sample, float* pred_xstart,
+                  umd_stream_t stream);
 /* models/ae.py:14-16,25-27  stable argsort of the mask noise, its inverse and the 0/1 sequence mask. */
 int umd_mask_argsort(const float* noise, int n, int L, int len_keep, int* ids_shuffle, int* ids_restore,
                      float* mask_or_null, umd_stream_t stream);

@@ -77,6 +77,78 @@ def q_sample(gd: dict, x_start: torch.Tensor, t: torch.Tensor, noise: torch.Tens
   return ca.reshape(shp) * x_start + cb.reshape(shp) * noise
 
 
+def _extract(gd, key, t, x):
+  """gaussian_diffusion.py:286-289 _extract_into_tensor (tables float32 on device, train_ae.py:183-185)."""
+  arr = torch.as_tensor(np.asarray(gd[key])).to(x.dtype)
+  return arr[t.reshape(-1).long()].reshape((-1,) + (1,) * (x.dim() - 1))
+
+
+def predict_xstart_from_eps(gd, x_t, t, eps):
+  """gaussian_diffusion.py:122-127."""
+  return _extract(gd, "sqrt_recip_alphas_cumprod", t, x_t) * x_t - _extract(gd, "sqrt_recipm1_alphas_cumprod", t, x_t) * eps
+
+
+def predict_eps_from_xstart(gd, x_t, t, pred_xstart):
+  """gaussian_diffusion.py:129-132."""
+  return (_extract(gd, "sqrt_recip_alphas_cumprod", t, x_t) * x_t - pred_xstart) / _extract(gd, "sqrt_recipm1_alphas_cumprod", t, x_t)
+
+
+def q_posterior_mean(gd, x_start, x_t, t):
+  """gaussian_diffusion.py:100-120 (mean only)."""
+  return _extract(gd, "posterior_mean_coef1", t, x_t) * x_start + _extract(gd, "posterior_mean_coef2", t, x_t) * x_t
+
+
+def ddim_sample(gd, p_apply, x, t, t_next, noise, clip_denoised=False, model_kwargs=None, eta=1.0):
+  """gaussian_diffusion.py:166-211 on top of p_mean_variance (:134-164).  `noise` replaces the N(0,1) draw of
+  :196-197; p_apply(x_t=, t=, **model_kwargs) returns the model's eps."""
+  model_output = p_apply(x_t=x, t=t, **(model_kwargs or {}))
+  pred_xstart = predict_xstart_from_eps(gd, x, t, model_output)
+  if clip_denoised:
+    pred_xstart = pred_xstart.clip(-1, 1)
+  eps = predict_eps_from_xstart(gd, x, t, pred_xstart)
+  alpha_bar = _extract(gd, "alphas_cumprod", t, x)
+  alpha_bar_prev = _extract(gd, "alphas_cumprod", t_next, x) if t_next is not None else _extract(gd, "alphas_cumprod_prev", t, x)
+  sigma = eta * torch.sqrt((1 - alpha_bar_prev) / (1 - alpha_bar)) * torch.sqrt(1 - alpha_bar / alpha_bar_prev)
+  mean_pred = pred_xstart * torch.sqrt(alpha_bar_prev) + torch.sqrt(1 - alpha_bar_prev - sigma ** 2) * eps
+  nonzero = (t.reshape((-1,) + (1,) * (x.dim() - 1)) > 0).to(x.dtype)
+  return {"sample": mean_pred + nonzero * sigma * noise, "pred_xstart": pred_xstart}
+
+
+def ddim_timesteps(num_train_steps, sampling_steps):
+  """gaussian_diffusion.py:236-237."""
+  ts = list(range(num_train_steps - 1, 0, -num_train_steps // sampling_steps))
+  return ts + [0]
+
+
+def ddim_sample_loop(gd, apply_fn, noises, ys=None, clip_denoised=False, sampling_steps=250, cfg_scale=None, eta=1.0):
+  """gaussian_diffusion.py:213-280.  noises: the draws in reference order (initial image, one per scan step, one for
+  the final t = 0 call).  Returns the final call's pred_xstart (:271-275)."""
+  model_kwargs = dict(y=ys, cfg_scale=cfg_scale)
+  img = noises[0]
+  n = img.shape[0]
+  ts = ddim_timesteps(len(np.asarray(gd["betas"])), sampling_steps)
+  for k in range(sampling_steps):
+    t_curr = torch.full((n, 1), ts[k], dtype=torch.int64)
+    t_next = torch.full((n, 1), ts[k + 1], dtype=torch.int64)
+    img = ddim_sample(gd, apply_fn, img, t_curr, t_next, noises[1 + k], clip_denoised, model_kwargs, eta)["sample"]
+  final = ddim_sample(gd, apply_fn, img, torch.zeros((n, 1), dtype=torch.int64), None, noises[1 + sampling_steps],
+                      clip_denoised, model_kwargs, eta)
+  return final["pred_xstart"]
+
+
+def make_apply_fn(params, cfg, gd=None, *, eps_pred=True, dtype=torch.float32):
+  """train_ae.py:472-483 create_apply_fn over model_apply: the model sees t + 1; the eps head is the last C channels
+  (eps_pred=False converts the x0 head instead and needs the tables)."""
+  C = cfg["channels"]
+
+  def apply_fn(*, x_t, t, y=None, cfg_scale=None):
+    pred, _ = model_apply(params, cfg, x_t, t=t.reshape(-1) + 1, y=y, cfg_scale=cfg_scale, dtype=dtype)
+    if eps_pred:
+      return pred[..., C:]
+    return predict_eps_from_xstart(gd, x_t, t, pred[..., :C])
+  return apply_fn
+
+
 # ------------------------------------------------------------------------------------------
 # models/ae.py helpers
 # ------------------------------------------------------------------------------------------

@@ -656,6 +656,59 @@ int qsample(const float* x0, const float* noise, const int* t, const float* sqrt
 }
 
 // =========================================================================================
+// DDIM update (gaussian_diffusion.py:166-284 ddim_sample on top of p_mean_variance :134-164), one fused pass:
+// classifier-free-guidance combine of the doubled batch (ae.py:192-195), eps / x0 head selection
+// (train_ae.py:472-483), pred_xstart (:122-127), optional clip, eps from x0 (:129-132), sigma and the Eq. 12 mean.
+// x, noise, sample, pred_xstart: [n, hw, C] fp32;  pred: [n (or 2n with guidance), hw, pred_ld] fp32.
+// =========================================================================================
+__global__ void ddim_step_kernel(DdimArgs a, long long total) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int C = a.C;
+  const long long pix = i / C;                 // n * hw + pixel
+  const int c = static_cast<int>(i - pix * C);
+  const int n = static_cast<int>(pix / a.hw);
+  const int t = a.t[n];
+  const float sra = a.sqrt_recip_ac[t], srm1 = a.sqrt_recipm1_ac[t];
+  const float ab = a.ac[t];
+  const float abp = a.t_next ? a.ac[a.t_next[n]] : a.ac_prev[t];
+  const float x = a.x[i];
+  // pred rows hold pred_ld values per pixel: [x0 head (C) | eps head (C)] (pred_ld = 2C) or the eps head alone (= C)
+  const int eps_off = a.pred_ld - C;
+  const long long pbase = pix * a.pred_ld + c;
+  float m_eps = a.pred[pbase + eps_off];
+  float m_x0 = a.eps_pred ? 0.f : a.pred[pbase];
+  if (a.use_cfg) {
+    const long long ubase = pbase + static_cast<long long>(a.n) * a.hw * a.pred_ld;   // unconditional half of the batch
+    const float u_eps = a.pred[ubase + eps_off];
+    m_eps = u_eps + a.cfg_scale * (m_eps - u_eps);
+    if (!a.eps_pred) {
+      const float u_x0 = a.pred[ubase];
+      m_x0 = u_x0 + a.cfg_scale * (m_x0 - u_x0);
+    }
+  }
+  const float model_eps = a.eps_pred ? m_eps : (sra * x - m_x0) / srm1;
+  float px0 = sra * x - srm1 * model_eps;
+  if (a.clip_denoised) px0 = fminf(fmaxf(px0, -1.f), 1.f);
+  const float eps = (sra * x - px0) / srm1;
+  const float sigma = a.eta * sqrtf((1.f - abp) / (1.f - ab)) * sqrtf(1.f - ab / abp);
+  const float mean_pred = px0 * sqrtf(abp) + sqrtf(1.f - abp - sigma * sigma) * eps;
+  const float nz = (t > 0) ? sigma * a.noise[i] : 0.f;
+  a.sample[i] = mean_pred + nz;
+  if (a.pred_xstart) a.pred_xstart[i] = px0;
+}
+int ddim_step(const DdimArgs& a, cudaStream_t st) {
+  if (a.n <= 0) return UMD_OK;
+  UMD_REQUIRE(a.hw > 0 && a.C > 0, "ddim_step: bad shape");
+  UMD_REQUIRE(a.pred_ld == 2 * a.C || (a.pred_ld == a.C && a.eps_pred), "ddim_step: pred must hold 2C values per pixel, or C (eps head only)");
+  UMD_REQUIRE(a.x && a.pred && a.noise && a.t && a.sample, "ddim_step: null argument");
+  const long long total = static_cast<long long>(a.n) * a.hw * a.C;
+  ddim_step_kernel<<<static_cast<int>(ceil_div_ll(total, 256)), 256, 0, st>>>(a, total);
+  UMD_LAUNCH_CHECK();
+  return UMD_OK;
+}
+
+// =========================================================================================
 // random_masking index work (ae.py:14-16,25-27): stable ascending argsort of L noise values per
 // row by exact rank counting (ties broken by index => identical to a stable sort), the inverse
 // permutation, and the 0/1 sequence mask.  Bit-exact by construction.

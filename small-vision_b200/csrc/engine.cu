@@ -660,6 +660,20 @@ extern "C" int umd_qsample(const float* x0, const float* noise, const int* t, co
                            int per_sample, float* out, umd_stream_t stream) {
   return qsample(x0, noise, t, sa, sb, n, per_sample, out, static_cast<cudaStream_t>(stream));
 }
+extern "C" int umd_ddim_step(const float* x, const float* pred, const float* noise, const int* t, const int* t_next,
+                             const float* alphas_cumprod, const float* alphas_cumprod_prev,
+                             const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod, int n, int hw,
+                             int channels, int pred_channels, float eta, int use_cfg, float cfg_scale, int eps_pred, int clip_denoised,
+                             float* sample, float* pred_xstart, umd_stream_t stream) {
+  DdimArgs a;
+  a.x = x; a.pred = pred; a.noise = noise; a.t = t; a.t_next = t_next;
+  a.ac = alphas_cumprod; a.ac_prev = alphas_cumprod_prev;
+  a.sqrt_recip_ac = sqrt_recip_alphas_cumprod; a.sqrt_recipm1_ac = sqrt_recipm1_alphas_cumprod;
+  a.n = n; a.hw = hw; a.C = channels; a.pred_ld = pred_channels; a.eta = eta; a.cfg_scale = cfg_scale;
+  a.use_cfg = use_cfg; a.eps_pred = eps_pred; a.clip_denoised = clip_denoised;
+  a.sample = sample; a.pred_xstart = pred_xstart;
+  return ddim_step(a, static_cast<cudaStream_t>(stream));
+}
 extern "C" int umd_mask_argsort(const float* noise, int n, int L, int len_keep, int* ids_shuffle, int* ids_restore,
                                 float* mask, umd_stream_t stream) {
   return mask_argsort(noise, n, L, len_keep, ids_shuffle, ids_restore, mask, static_cast<cudaStream_t>(stream));

@@ -101,6 +101,24 @@ int qsample(const float* x0, const float* noise, const int* t, const float* sqrt
             int per_sample, float* out, cudaStream_t st);
 int mask_argsort(const float* noise, int n, int L, int keep, int* ids_shuffle, int* ids_restore, float* mask,
                  cudaStream_t st);
+struct DdimArgs {
+  const float* x;        // [n, hw, C] current sample x_t
+  const float* pred;     // [n or 2n, hw, 2C] model output (x0 head, eps head)
+  const float* noise;    // [n, hw, C] N(0,1) draws
+  const int* t;          // [n] current timestep
+  const int* t_next;     // [n] next timestep, or null (alphas_cumprod_prev[t] is used)
+  const float* ac;       // alphas_cumprod
+  const float* ac_prev;  // alphas_cumprod_prev
+  const float* sqrt_recip_ac;
+  const float* sqrt_recipm1_ac;
+  int n, hw, C;
+  int pred_ld;           // values per pixel in pred: 2C (x0 head, eps head) or C (eps head only)
+  float eta, cfg_scale;
+  int use_cfg, eps_pred, clip_denoised;
+  float* sample;         // [n, hw, C]
+  float* pred_xstart;    // [n, hw, C] or null
+};
+int ddim_step(const DdimArgs& a, cudaStream_t st);
 
 struct EmbedArgs {
   const float* image;      // [n, img, img, C] fp32 NHWC

@@ -73,3 +73,116 @@ def q_sample(*, gd, x_start, t, noise, out=None):
                           lib.ptr(gd["sqrt_one_minus_alphas_cumprod"]), C.c_int(n), C.c_int(per), lib.ptr(out),
                           lib.current_stream()), "umd_qsample")
   return out
+
+
+# ------------------------------------------------------------------------------------------------
+# DDIM sampler (gaussian_diffusion.py:134-284) — SURVEY.md §8(f) rank 1: the forward kernels in a loop.
+# ------------------------------------------------------------------------------------------------
+class RawPred:
+  """What a fused apply_fn hands to ddim_sample: the model's full output [n or 2n, H, W, 2C] plus how to read it
+  (classifier-free guidance combine of ae.py:192-195 and the eps / x0 head choice of train_ae.py:472-483 are then
+  done inside the DDIM kernel instead of by separate passes)."""
+  __slots__ = ("pred", "cfg_scale", "eps_pred")
+
+  def __init__(self, pred, cfg_scale=None, eps_pred=True):
+    self.pred, self.cfg_scale, self.eps_pred = pred, cfg_scale, eps_pred
+
+
+def create_apply_fn(model, params, *, eps_pred=True):
+  """train_ae.py:472-483 create_apply_fn: apply_fn(x_t=, t=, rng=, y=, cfg_scale=) evaluates the model at t + 1.
+  Returns a RawPred (see above); ddim_sample also accepts a plain eps tensor from any other callable."""
+  def apply_fn(*, x_t, t, rng=None, y=None, cfg_scale=None):
+    pred = model.apply_raw({"params": params}, x_t, t=t.reshape(-1) + 1, y=y, cfg_scale=cfg_scale)
+    return RawPred(pred, cfg_scale, eps_pred)
+  return apply_fn
+
+
+def _normal(rng, shape, device):
+  import torch
+  return torch.randn(shape, device=device, generator=rng if isinstance(rng, torch.Generator) else None)
+
+
+def _as_generator(rng, device):
+  import torch
+  if rng is None or isinstance(rng, torch.Generator):
+    return rng
+  g = torch.Generator(device=device)
+  g.manual_seed(int(rng))
+  return g
+
+
+def ddim_sample(gd, p_apply, x, t, t_next, rng, clip_denoised=False, denoised_fn=None, model_kwargs=None, eta=1.0, *,
+                noise=None):
+  """gaussian_diffusion.py:166-211.  x: f32[n,H,W,C] on the GPU; t, t_next: int[n,1] (t_next None = the previous
+  cumulative product, :187-190); rng: torch.Generator / seed (the N(0,1) draw of :196-197 may be supplied as `noise`
+  to reproduce a reference run).  Returns {"sample", "pred_xstart", "rng"}."""
+  import torch
+  if denoised_fn is not None:
+    raise NotImplementedError("denoised_fn is not used by the reference recipes and is not fused here")
+  model_kwargs = model_kwargs or {}
+  assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+  n, H, W, Cc = x.shape
+  assert tuple(t.shape) == (n, 1), t.shape   # gaussian_diffusion.py:139
+  out = p_apply(x_t=x, t=t, rng=rng, **model_kwargs)
+  if isinstance(out, tuple):
+    out = out[0]
+  if isinstance(out, RawPred):
+    pred, cfg_scale, eps_pred = out.pred, out.cfg_scale, out.eps_pred
+  else:
+    pred, cfg_scale, eps_pred = out, None, True
+  pred = pred.contiguous()
+  use_cfg = cfg_scale is not None and pred.shape[0] == 2 * n
+  assert pred.shape[0] == (2 * n if use_cfg else n) and pred.shape[-1] in (Cc, 2 * Cc), pred.shape
+  rng = _as_generator(rng, x.device)
+  if noise is None:
+    noise = _normal(rng, x.shape, x.device)
+  tt = t.reshape(-1).to(torch.int32).contiguous()
+  tn = None if t_next is None else t_next.reshape(-1).to(torch.int32).contiguous()
+  sample, px0 = torch.empty_like(x), torch.empty_like(x)
+  L = lib.load()
+  lib.check(L.umd_ddim_step(lib.ptr(x), lib.ptr(pred), lib.ptr(noise.contiguous()), lib.ptr(tt), lib.ptr(tn),
+                            lib.ptr(gd["alphas_cumprod"]), lib.ptr(gd["alphas_cumprod_prev"]),
+                            lib.ptr(gd["sqrt_recip_alphas_cumprod"]), lib.ptr(gd["sqrt_recipm1_alphas_cumprod"]),
+                            C.c_int(n), C.c_int(H * W), C.c_int(Cc), C.c_int(pred.shape[-1]), C.c_float(float(eta)),
+                            C.c_int(int(use_cfg)), C.c_float(float(cfg_scale) if use_cfg else 0.0), C.c_int(int(eps_pred)),
+                            C.c_int(int(clip_denoised)), lib.ptr(sample), lib.ptr(px0), lib.current_stream()),
+            "umd_ddim_step")
+  return {"sample": sample, "pred_xstart": px0, "rng": rng}
+
+
+def reference_timesteps(num_train_steps, sampling_steps):
+  """gaussian_diffusion.py:236-237: arange(T-1, 0, step=-T//sampling_steps) with 0 appended (Python floor division
+  of the NEGATED length, so the stride is ceil(T / sampling_steps))."""
+  step = -num_train_steps // sampling_steps
+  ts = list(range(num_train_steps - 1, 0, step))
+  ts.append(0)
+  return ts
+
+
+def ddim_sample_loop(gd, apply_fn, rng, shape, ys=None, clip_denoised=False, sampling_steps=250, denoised_fn=None,
+                     cfg_scale=None, eta=1.0, *, noises=None):
+  """gaussian_diffusion.py:213-280.  `shape` is an array-like whose .shape gives [n,H,W,C]; `noises` (optional)
+  supplies the draws in reference order: the initial image, one per scan step, one for the final call.
+  Returns ({"sample": pred_xstart of the final t=0 call, "rng", "y"}, rng)."""
+  import torch
+  shp = tuple(shape.shape)
+  n = shp[0]
+  if ys is not None:
+    assert ys.shape[0] == n, "ys must have the same batch size as shape"
+  dev = gd["betas"].device
+  rng = _as_generator(rng, dev)
+  model_kwargs = dict(y=ys, cfg_scale=cfg_scale)
+  it = iter(noises) if noises is not None else None
+  draw = (lambda: next(it).to(device=dev, dtype=torch.float32)) if it is not None else (lambda: _normal(rng, shp, dev))
+  img = draw().contiguous()
+  ts = reference_timesteps(int(gd["betas"].numel()), sampling_steps)
+  assert len(ts) >= sampling_steps + 1, "sampling_steps must not exceed what the stride provides (reference would index out of range)"
+  for k in range(sampling_steps):
+    t_curr = torch.full((n, 1), ts[k], dtype=torch.int32, device=dev)
+    t_next = torch.full((n, 1), ts[k + 1], dtype=torch.int32, device=dev)
+    out = ddim_sample(gd, apply_fn, img, t_curr, t_next, rng, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                      model_kwargs=model_kwargs, eta=eta, noise=draw())
+    img = out["sample"]
+  final = ddim_sample(gd, apply_fn, img, torch.zeros((n, 1), dtype=torch.int32, device=dev), None, rng,
+                      clip_denoised=clip_denoised, denoised_fn=denoised_fn, model_kwargs=model_kwargs, eta=eta, noise=draw())
+  return {"sample": final["pred_xstart"], "rng": rng, "y": ys}, rng

@@ -44,7 +44,13 @@ class ViTAE:
     arena = init_arena(self.layout, int(seed), device, nonzero_adaln=nonzero_adaln)
     return {"params": tree_from_arena(self.layout, arena)}
 
-  def apply(self, variables, image, *, t=None, y=None, cfg_scale=None, mask=0.0, train=False, rngs=None):
+  def apply_raw(self, variables, image, *, t=None, y=None, cfg_scale=None):
+    """Inference forward that leaves the classifier-free-guidance combine (ae.py:192-195) to the consumer: with
+    cfg_scale the result is the doubled batch [2n,H,W,2C], conditional rows first (the DDIM kernel combines them)."""
+    pred, _ = self.apply(variables, image, t=t, y=y, cfg_scale=cfg_scale, _combine=False)
+    return pred
+
+  def apply(self, variables, image, *, t=None, y=None, cfg_scale=None, mask=0.0, train=False, rngs=None, _combine=True):
     """ae.py:176-197.  Returns (pred [n,H,W,2C], {"mask": [n,H,W,1] | None, "pre_logits": [n,D]})."""
     cfg = self.cfg
     rngs = rngs or {}
@@ -72,7 +78,7 @@ class ViTAE:
                              keep1=cfg.num_patches, masked0=masked, masked1=False, ids_shuffle=ids_shuffle,
                              ids_restore=ids_restore, want_pred=True, train=False)
     pred = res.pred
-    if cfg_scale is not None:  # ae.py:192-195
+    if cfg_scale is not None and _combine:  # ae.py:192-195
       un, co = pred[n // 2:], pred[:n // 2]
       pred = un + cfg_scale * (co - un)
     out = {"mask": None, "pre_logits": res.pre_logits}
