@@ -54,17 +54,24 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + STAGE_OUT_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
+// nn.gelu (tanh form, vit.py:55) and its derivative, written as explicit FMA chains: the fc1 / fc2-dgrad GEMMs have
+// K = 768 only, so their epilogues (these functions once per output element) must stay well under the main loop's
+// ~3000 cycles per 256 x 256 tile to hide behind it.  5 FP + 1 MUFU and 10 FP + 1 MUFU per element.
 __device__ __forceinline__ float gelu_tanh(float u) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (u + k1 * u * u * u);
-  return 0.5f * u * (1.f + tanh_fast(inner));
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float u2 = u * u;
+  const float t = tanh_fast(u * fmaf(u2, k0k1, k0));
+  const float hu = 0.5f * u;
+  return fmaf(hu, t, hu);
 }
 __device__ __forceinline__ float gelu_tanh_grad(float u) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u2 = u * u;
-  float inner = k0 * (u + k1 * u * u2);
-  float t = tanh_fast(inner);
-  return 0.5f * (1.f + t) + 0.5f * u * (1.f - t * t) * k0 * (1.f + 3.f * k1 * u2);
+  const float k0 = 0.7978845608028654f, k0k1 = 0.7978845608028654f * 0.044715f;
+  const float u2 = u * u;
+  const float t = tanh_fast(u * fmaf(u2, k0k1, k0));
+  const float q = fmaf(u2, 3.f * k0k1, k0);        // k0 (1 + 3 k1 u^2)
+  const float s = fmaf(-t, t, 1.f);                // 1 - tanh^2
+  const float w = (0.5f * u) * s;
+  return fmaf(w, q, fmaf(0.5f, t, 0.5f));
 }
 
 struct WorkItem {
@@ -319,7 +326,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               mbar_wait(&aux_bar[ew], (aux_uses++) & 1);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const uint4 uu = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
+                const uint4 uu = ld_shared_v4(smem_u32(my_row) + ((j ^ sw) << 4));
                 const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -333,9 +340,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
-                  make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              st_shared_v4(smem_u32(my_row) + ((j ^ sw) << 4), pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
             }
             fence_proxy_async();
             __syncwarp();
@@ -354,8 +360,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float g[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) g[q] = gelu_tanh(v[8 * j + q]);
-                *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) =
-                    make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+                st_shared_v4(smem_u32(my_row) + ((j ^ sw) << 4), pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]),
+                             pack_bf16x2(g[6], g[7]));
               }
               fence_proxy_async();
               __syncwarp();
