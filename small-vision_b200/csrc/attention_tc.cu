@@ -460,13 +460,45 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_arrive_named(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// 64-long dot product of a bf16 row in 128B-swizzled shared memory (row start address, row & 7) with a row held in
+// registers as eight 16-byte chunks in logical order
+__device__ __forceinline__ float dot64_swz(uint32_t row_addr, int r7, const uint4 (&w)[8]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 a = ld_shared_v4(row_addr + ((c ^ r7) << 4));
+    acc += bf16_lo(a.x) * bf16_lo(w[c].x) + bf16_hi(a.x) * bf16_hi(w[c].x) + bf16_lo(a.y) * bf16_lo(w[c].y) +
+           bf16_hi(a.y) * bf16_hi(w[c].y) + bf16_lo(a.z) * bf16_lo(w[c].z) + bf16_hi(a.z) * bf16_hi(w[c].z) +
+           bf16_lo(a.w) * bf16_lo(w[c].w) + bf16_hi(a.w) * bf16_hi(w[c].w);
+  }
+  return acc;
+}
+__device__ __forceinline__ void load_row_swz(uint32_t base, int row, uint4 (&w)[8]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) w[c] = ld_shared_v4(base + row * AT_ROW + ((c ^ (row & 7)) << 4));
+}
+// 16 consecutive bf16 of a swizzled row (columns [16 part, 16 part + 16)) as floats
+__device__ __forceinline__ void load_cols16_swz(uint32_t base, int row, int part, float (&f)[16]) {
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint4 a = ld_shared_v4(base + row * AT_ROW + (((2 * part + k) ^ (row & 7)) << 4));
+    f[8 * k + 0] = bf16_lo(a.x); f[8 * k + 1] = bf16_hi(a.x); f[8 * k + 2] = bf16_lo(a.y); f[8 * k + 3] = bf16_hi(a.y);
+    f[8 * k + 4] = bf16_lo(a.z); f[8 * k + 5] = bf16_hi(a.z); f[8 * k + 6] = bf16_lo(a.w); f[8 * k + 7] = bf16_hi(a.w);
+  }
+}
+
 struct BwdParams {
   const __nv_bfloat16* out;
   const __nv_bfloat16* dout;
   const float* lse;
   __nv_bfloat16* dqkv;
   int row_base;
-  int S, SP, nt, H;
+  int S, SP, H;
+  int nt;     // 128-row tiles (queries and keys) that run on the tensor cores
+  int ntail;  // trailing rows S - 128 nt (1..AT_TAIL) handled on the idle control warps, else 0
   int nbuf;  // TMEM score buffers (2 when nt <= 2)
   int prefetch;  // issue the next block's scores ahead of this block's accumulation (needs nbuf == 2)
   int stagger_ctas, stagger_ns;
@@ -511,6 +543,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   uint64_t* bar_acc = bars + 8;
   uint64_t* bar_accfree = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // tail scratch (only with ntail > 0), each [AT_TAIL][SP] fp32: for tail key t and query x  P and dS (sPA, sDSA);
+  // for tail query t and key x  P and dS (sPB, sDSB); then [9][64] partial sums of the tail rows' own outputs
+  float* sPA = reinterpret_cast<float*>(bars + 16);
+  float* sDSA = sPA + AT_TAIL * SP;
+  float* sPB = sDSA + AT_TAIL * SP;
+  float* sDSB = sPB + AT_TAIL * SP;
+  float* sRed = sDSB + AT_TAIL * SP;
+  const int M0 = 128 * nt;                       // rows [0, M0) go through the MMA path
+  const int SPm = p.ntail > 0 ? M0 : SP;         // ... padded extent of that part
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -565,7 +606,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       prefetch_rows(&td128, &td16, h2 * AT_DH, s2, SP);
       prefetch_rows(&to128, &to16, h2 * AT_DH, s2, SP);
     }
-  } else if (warp == 1) {
+  }
+  if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged, see forward)
     constexpr uint32_t idesc_kt = make_idesc_bf16(128, 64, false, true);   // A K-major (P^T / dS^T), B MN-major (dO / Q)
     constexpr uint32_t idesc_mn = make_idesc_bf16(128, 64, true, true);    // A MN-major (dS), B MN-major (K)
@@ -587,10 +629,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     TL(0, 0);
     int step = 0;
     // S^T = K_j Q_i^T and dP^T = V_j dO_i^T for 64-query half hh of block n = (j, i).  Steps are issued in order.
-    auto halves_of = [&](int n) { return (min(128, SP - 128 * (n % nt)) + 63) >> 6; };
+    auto halves_of = [&](int n) { return (min(128, SPm - 128 * (n % nt)) + 63) >> 6; };
     auto issue_step = [&](int n, int hh) {
       const int j = n / nt, i = n - j * nt;
-      const int nq = min(128, SP - 128 * i);
+      const int nq = min(128, SPm - 128 * i);
       const int b = step % nbuf, u = step / nbuf;
       if (u > 0) {
         mbar_wait(&bar_sfree[b], (u - 1) & 1);
@@ -617,7 +659,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     for (int hh = 0; hh < halves_of(0); ++hh) issue_step(0, hh);
     for (int n = 0; n < nblk; ++n) {
       const int j = n / nt, i = n - j * nt;
-      const int nq = min(128, SP - 128 * i), nkv = min(128, SP - 128 * j);
+      const int nq = min(128, SPm - 128 * i), nkv = min(128, SPm - 128 * j);
       const int nh = (nq + 63) >> 6;
       // Score steps of the next block that can run ahead of this block's accumulation: all of them with two
       // TMEM score buffers, the first half with one (its buffer is free as soon as the softmax warps have read
@@ -707,6 +749,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     }
     TL(4, 4);
     bar_softmax_n<AT_BWD_SM>();
+    if (p.ntail > 0) bar_arrive_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta are complete
     TL(4, 1);
     const float sl2 = p.scale_log2;
     const int r7 = r & 7;
@@ -715,7 +758,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     bool store_pending = false;
     for (int j = 0; j < nt; ++j) {
       for (int i = 0; i < nt; ++i) {
-        const int nq = min(128, SP - 128 * i);
+        const int nq = min(128, SPm - 128 * i);
         const int nh = (nq + 63) >> 6;
         for (int hh = 0; hh < nh; ++hh, ++step) {
           const int b = step % nbuf, u = step / nbuf;
@@ -780,6 +823,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
         tmem_ld_wait_dep16(a1);
         tc_fence_before();
         mbar_arrive(bar_accfree);
+        if (p.ntail > 0) {
+          // tail queries t against this thread's key x:  dV[x] += P[t][x] dO[t],  dK[x] += dS[t][x] Q[t]
+          if (j == 0) bar_sync_named(4, AT_BWD_SM + AT_TAIL_THREADS);   // the tail warps have filled the scratch
+          const int x = j * 128 + r;
+          for (int t = 0; t < p.ntail; ++t) {
+            const float pb = sPB[t * SP + x], dsb = sDSB[t * SP + x];
+            float f[16];
+            load_cols16_swz(smem_u32(sdO), M0 + t, hf, f);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a0[c] = __float_as_uint(fmaf(pb, f[c], __uint_as_float(a0[c])));
+            load_cols16_swz(smem_u32(sQ), M0 + t, hf, f);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a1[c] = __float_as_uint(fmaf(dsb, f[c], __uint_as_float(a1[c])));
+          }
+        }
         const float sc = p.scale;
 #pragma unroll
         for (int c = 0; c < 16; c += 8) {
@@ -810,6 +868,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       uint32_t a0[16];
       tmem_ld_32x16(t_lane + col_dq + 64 * i + 16 * hf, a0);
       tmem_ld_wait_dep16(a0);
+      if (p.ntail > 0) {   // tail keys t against this thread's query x:  dQ[x] += dS[t][x] K[t]
+        const int x = i * 128 + r;
+        for (int t = 0; t < p.ntail; ++t) {
+          const float dsa = sDSA[t * SP + x];
+          float f[16];
+          load_cols16_swz(smem_u32(sK), M0 + t, hf, f);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) a0[c] = __float_as_uint(fmaf(dsa, f[c], __uint_as_float(a0[c])));
+        }
+      }
       const float sc = p.scale;
       const uint32_t stage = pt_row + i * AT_SLAB;   // slabs 0,1 of P^T, then slab 0 of dS^T (contiguous)
 #pragma unroll
@@ -825,6 +893,77 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       for (int i = 0; i < nt; ++i) tma_store_3d(&tmdq, sPt + i * AT_SLAB, h * AT_DH, i * 128, sample);
       bulk_commit();
       bulk_wait_read<0>();
+    }
+  } else if (p.ntail > 0) {
+    // ------------------------------------------------------------------ tail rows on CUDA cores (warps 0, 2, 3)
+    // S = 128 nt + ntail (257-token decoders, the 260-token label-conditioned encoder): a third tile per dimension
+    // would cost five more (j, i) blocks and the second TMEM score buffer.  For tail key t (row M0 + t) and every
+    // query x:  P = exp2(q_x k_t sl2 - lse_x),  dS = P (dO_x v_t - delta_x);  for tail query t and every key x < M0:
+    // P = exp2(q_t k_x sl2 - lse_t),  dS = P (dO_t v_x - delta_t).  The rows' own outputs are reduced here; what they
+    // add to the rows of the main tiles is applied by the softmax warps in the dK / dV / dQ epilogues.
+    __syncwarp();
+    const int tt = (warp == 0 ? 0 : warp - 1) * 32 + lane;   // 0..95
+    const int tw = tt >> 5;
+    const float sl2 = p.scale_log2;
+    const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV), o_u = smem_u32(sdO);
+    mbar_wait(bar_ld, 0);
+    bar_sync_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta written by the softmax warps
+    for (int t = 0; t < p.ntail; ++t) {
+      const int rt = M0 + t;
+      const float lse_t = sLse[rt], delta_t = sDelta[rt];
+      uint4 w[8];
+      load_row_swz(k_u, rt, w);
+      for (int x = tt; x < S; x += AT_TAIL_THREADS)
+        sPA[t * SP + x] = ex2(fmaf(dot64_swz(q_u + x * AT_ROW, x & 7, w), sl2, -sLse[x]));
+      load_row_swz(v_u, rt, w);
+      for (int x = tt; x < S; x += AT_TAIL_THREADS)
+        sDSA[t * SP + x] = sPA[t * SP + x] * (dot64_swz(o_u + x * AT_ROW, x & 7, w) - sDelta[x]);
+      load_row_swz(q_u, rt, w);
+      for (int x = tt; x < M0; x += AT_TAIL_THREADS)
+        sPB[t * SP + x] = ex2(fmaf(dot64_swz(k_u + x * AT_ROW, x & 7, w), sl2, -lse_t));
+      load_row_swz(o_u, rt, w);
+      for (int x = tt; x < M0; x += AT_TAIL_THREADS)
+        sDSB[t * SP + x] = sPB[t * SP + x] * (dot64_swz(v_u + x * AT_ROW, x & 7, w) - delta_t);
+    }
+    bar_sync_named(2, AT_TAIL_THREADS);
+    bar_arrive_named(4, AT_BWD_SM + AT_TAIL_THREADS);   // scratch complete: the epilogues may read it
+    // the tail rows' own gradients: lane owns columns 2 lane, 2 lane + 1; warp tw takes rows tw, tw + 3, ...
+    const uint32_t coff = ((lane & 3) << 2);
+    for (int t = 0; t < p.ntail; ++t) {
+      float v0 = 0.f, v1 = 0.f, k0 = 0.f, k1 = 0.f, g0 = 0.f, g1 = 0.f;
+      for (int x = tw; x < S; x += 3) {
+        const uint32_t off = x * AT_ROW + (((lane >> 2) ^ (x & 7)) << 4) + coff;
+        const float pa = sPA[t * SP + x], dsa = sDSA[t * SP + x];
+        uint32_t u = ld_shared_b32(o_u + off);
+        v0 = fmaf(pa, bf16_lo(u), v0); v1 = fmaf(pa, bf16_hi(u), v1);          // dV[k_t] = sum_x P dO_x
+        u = ld_shared_b32(q_u + off);
+        k0 = fmaf(dsa, bf16_lo(u), k0); k1 = fmaf(dsa, bf16_hi(u), k1);        // dK[k_t] = sum_x dS Q_x
+        if (x < M0) {
+          const float dsb = sDSB[t * SP + x];
+          u = ld_shared_b32(k_u + off);
+          g0 = fmaf(dsb, bf16_lo(u), g0); g1 = fmaf(dsb, bf16_hi(u), g1);      // dQ[q_t] = sum_x dS K_x
+        }
+      }
+      if (tw == 0) {   // ... plus the tail keys against this tail query
+        for (int t2 = 0; t2 < p.ntail; ++t2) {
+          const int x = M0 + t2;
+          const float dsa = sDSA[t2 * SP + M0 + t];
+          const uint32_t u = ld_shared_b32(k_u + x * AT_ROW + (((lane >> 2) ^ (x & 7)) << 4) + coff);
+          g0 = fmaf(dsa, bf16_lo(u), g0); g1 = fmaf(dsa, bf16_hi(u), g1);
+        }
+      }
+      float* red = sRed + tw * 192 + 2 * lane;
+      red[0] = v0; red[1] = v1; red[64] = k0; red[65] = k1; red[128] = g0; red[129] = g1;
+      bar_sync_named(2, AT_TAIL_THREADS);
+      if (tw == 0) {
+        const float* rr = sRed + 2 * lane;
+        const float sc = p.scale;
+        __nv_bfloat16* orow = p.dqkv + static_cast<long long>(row0 + M0 + t) * 3 * D + h * AT_DH + 2 * lane;
+        *reinterpret_cast<uint32_t*>(orow + 2 * D) = pack_bf16x2(rr[0] + rr[192] + rr[384], rr[1] + rr[193] + rr[385]);
+        *reinterpret_cast<uint32_t*>(orow + D) = pack_bf16x2((rr[64] + rr[256] + rr[448]) * sc, (rr[65] + rr[257] + rr[449]) * sc);
+        *reinterpret_cast<uint32_t*>(orow) = pack_bf16x2((rr[128] + rr[320] + rr[512]) * sc, (rr[129] + rr[321] + rr[513]) * sc);
+      }
+      bar_sync_named(2, AT_TAIL_THREADS);
     }
   }
 
@@ -846,16 +985,32 @@ int tail_rows(int S) {
   const int t = ((S + 15) & ~15) % 128;
   return t ? t : 16;
 }
-// S = 128 * tiles + tail: a tail of 1..AT_TAIL rows behind at least one full tile is computed on CUDA cores
-void split_tail(int S, int* tiles, int* tail) {
+// S = 128 * tiles + tail: a tail of 1..max_tail rows behind at least one full tile is computed on CUDA cores
+void split_tail(int S, int max_tail, int* tiles, int* tail) {
   const int t = S % 128;
-  if (S > 128 && t >= 1 && t <= AT_TAIL) {
+  if (S > 128 && t >= 1 && t <= max_tail) {
     *tiles = S / 128;
     *tail = t;
   } else {
     *tiles = (S + 127) / 128;
     *tail = 0;
   }
+}
+// Largest tail that goes to the control warps.  The three tail warps share their sub-partitions with the softmax
+// warps, so the tail work must stay well below the main loop: measured on B200, one tail row pays in both directions
+// (257 tokens: forward 0.53 -> 0.41 ms, backward 1.10 -> 0.81 ms per decoder layer) while the four rows of the
+// 260-token label-conditioned encoder do not (forward 0.27 -> 0.35 ms, backward 0.55 -> 0.86 ms), so the default
+// limit is 1; the kernels handle up to AT_TAIL (tests raise the limit through umd_debug_attn_tail_limits).
+int g_tail_limit[2] = {-1, -1};
+int tail_limit(bool backward) {
+  if (g_tail_limit[0] < 0) {
+    const char* f = getenv("UMD_ATTN_TAIL_FWD_MAX");
+    const char* b = getenv("UMD_ATTN_TAIL_BWD_MAX");
+    g_tail_limit[0] = f ? atoi(f) : 1;
+    g_tail_limit[1] = b ? atoi(b) : 1;
+    for (int k = 0; k < 2; ++k) g_tail_limit[k] = g_tail_limit[k] < 0 ? 0 : (g_tail_limit[k] > AT_TAIL ? AT_TAIL : g_tail_limit[k]);
+  }
+  return g_tail_limit[backward ? 1 : 0];
 }
 // Every CTA of these kernels runs the same load -> compute -> store sequence for the same time, so a grid that
 // starts in lockstep stays in lockstep and hammers HBM in bursts.  Offsetting the start of the first wave spreads
@@ -911,7 +1066,7 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     FwdParams p;
     p.out = a.out; p.lse = a.lse; p.row_base = seg[k].row_base;
     p.S = S; p.SP = (p.S + 15) & ~15; p.H = a.H;
-    split_tail(S, &p.nqt, &p.ntail);
+    split_tail(S, tail_limit(false), &p.nqt, &p.ntail);
     p.o_col = (p.SP + 31) & ~31;
     p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
     p.scale_log2 = a.scale * LOG2E;
@@ -965,7 +1120,8 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     p.lse_bulk = ((S * a.H * 4) % 16 == 0) && ((static_cast<long long>(seg[k].row_base) * a.H * 4) % 16 == 0) &&
                  ((reinterpret_cast<uintptr_t>(a.lse) & 15) == 0) && (((S + 15) & ~15) * AT_ROW + S * a.H * 4 <= 4 * AT_SLAB);
     p.out = a.out; p.dout = a.dout; p.lse = a.lse; p.dqkv = a.dqkv; p.row_base = seg[k].row_base;
-    p.S = S; p.SP = (p.S + 15) & ~15; p.nt = (p.S + 127) / 128; p.H = a.H;
+    p.S = S; p.SP = (p.S + 15) & ~15; p.H = a.H;
+    split_tail(S, tail_limit(true), &p.nt, &p.ntail);
     p.nbuf = p.nt <= 2 ? 2 : 1;
     { const char* e = getenv("UMD_ATTN_PREFETCH"); p.prefetch = e ? atoi(e) != 0 : 1; }
     p.scale = a.scale; p.scale_log2 = a.scale * LOG2E;
@@ -976,6 +1132,7 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
     p.ahead = pf ? sm_count() : 0;
     int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 256 + 1024;   // + 3 KB of static shared memory
+    if (p.ntail > 0) smem += (4 * AT_TAIL * p.SP + 9 * 64) * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
     attn_bwd_tc_kernel<<<n * a.H, AT_BWD_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
     ++g_launch_count;
@@ -985,6 +1142,16 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
 }
 
 }  // namespace umd
+
+// test hook: largest tail (0..4) routed to the control warps, forward / backward; negative = back to the defaults
+extern "C" void umd_debug_attn_tail_limits(int fwd_max, int bwd_max) {
+  if (fwd_max < 0 || bwd_max < 0) {
+    umd::g_tail_limit[0] = umd::g_tail_limit[1] = -1;
+    return;
+  }
+  umd::g_tail_limit[0] = fwd_max > umd::AT_TAIL ? umd::AT_TAIL : fwd_max;
+  umd::g_tail_limit[1] = bwd_max > umd::AT_TAIL ? umd::AT_TAIL : bwd_max;
+}
 
 // debug aid (tools/attn_timeline.py): device buffer of 11 x 64 clock64() stamps written by CTA 0 of the backward kernel
 extern "C" void umd_debug_attn_timeline(long long* device_buf) { umd::g_attn_timeline = device_buf; }

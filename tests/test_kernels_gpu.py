@@ -196,6 +196,47 @@ def test_attention_fwd_bwd(n0, s0, n1, s1, H, impl, monkeypatch):
     assert r < 2e-2, f"d{name} rel-L2 {r}"
 
 
+@pytest.mark.parametrize("n0,s0,n1,s1,H", [(2, 258, 0, 0, 6), (2, 260, 1, 129, 4), (1, 131, 2, 257, 12), (3, 132, 0, 0, 2)])
+def test_attention_tail_rows_on_control_warps(n0, s0, n1, s1, H):
+  """Tails of 1..4 rows behind a full 128-row tile computed on the idle control warps, forward and backward (the
+  default only routes a 1-row tail there; the hook raises the limit to the kernels' maximum)."""
+  lib = _lib()
+  L = lib.load()
+  L.umd_debug_attn_tail_limits(4, 4)
+  try:
+    Dh, D = 64, H * 64
+    rows = n0 * s0 + n1 * s1
+    g = torch.Generator().manual_seed(rows)
+    qkv = (torch.randn(rows, 3 * D, generator=g) * 1.2).to(torch.bfloat16)
+    dout = torch.randn(rows, D, generator=g).to(torch.bfloat16)
+    ref_in = qkv.float().requires_grad_(True)
+    ref = _attn_ref(ref_in, n0, s0, n1, s1, H, Dh)
+    ref.backward(dout.float())
+    qg, dg = qkv.to(DEV), dout.to(DEV)
+    out = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+    lse = torch.empty(rows, H, device=DEV)
+    lib.check(L.umd_attention_fwd(lib.ptr(qg), lib.ptr(out), lib.ptr(lse), n0, s0, n1, s1, H, Dh, lib.current_stream()), "attn fwd")
+    assert U.rel_l2(out.float().cpu(), ref.detach()) < 1e-2
+    assert torch.allclose(out.float().cpu(), ref.detach(), rtol=2 ** -6, atol=2e-2)
+    dqkv = torch.zeros(rows, 3 * D, device=DEV, dtype=torch.bfloat16)
+    lib.check(L.umd_attention_bwd(lib.ptr(qg), lib.ptr(out), lib.ptr(dg), lib.ptr(lse), lib.ptr(dqkv), n0, s0, n1, s1, H, Dh,
+                                  lib.current_stream()), "attn bwd")
+    torch.cuda.synchronize()
+    gr = ref_in.grad
+    for j, name in enumerate("qkv"):
+      r = U.rel_l2(dqkv.float().cpu()[:, j * D:(j + 1) * D], gr[:, j * D:(j + 1) * D])
+      assert r < 2e-2, f"d{name} rel-L2 {r}"
+    # the tail rows themselves (written by the control warps, not by the TMA-store epilogues)
+    for n, s, base in ((n0, s0, 0), (n1, s1, n0 * s0)):
+      if n == 0 or s % 128 == 0 or s % 128 > 4:
+        continue
+      idx = torch.cat([torch.arange(base + k * s + (s // 128) * 128, base + (k + 1) * s) for k in range(n)])
+      assert U.rel_l2(out.float().cpu()[idx], ref.detach()[idx]) < 1e-2
+      assert U.rel_l2(dqkv.float().cpu()[idx], gr[idx]) < 2e-2
+  finally:
+    L.umd_debug_attn_tail_limits(-1, -1)
+
+
 # ------------------------------------------------------------------------------------------ optimiser
 @pytest.mark.parametrize("count,clip_active,ema", [(0, True, False), (5, False, True), (200, True, True)])
 def test_adamw_step_matches_oracle(count, clip_active, ema):
