@@ -466,15 +466,18 @@ __device__ __forceinline__ void bar_arrive_named(int id, int nthreads) {
 // 64-long dot product of a bf16 row in 128B-swizzled shared memory (row start address, row & 7) with a row held in
 // registers as eight 16-byte chunks in logical order
 __device__ __forceinline__ float dot64_swz(uint32_t row_addr, int r7, const uint4 (&w)[8]) {
-  float acc = 0.f;
+  uint4 a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = ld_shared_v4(row_addr + ((c ^ r7) << 4));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // four chains: the dot product is latency- not throughput-bound
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const uint4 a = ld_shared_v4(row_addr + ((c ^ r7) << 4));
-    acc += bf16_lo(a.x) * bf16_lo(w[c].x) + bf16_hi(a.x) * bf16_hi(w[c].x) + bf16_lo(a.y) * bf16_lo(w[c].y) +
-           bf16_hi(a.y) * bf16_hi(w[c].y) + bf16_lo(a.z) * bf16_lo(w[c].z) + bf16_hi(a.z) * bf16_hi(w[c].z) +
-           bf16_lo(a.w) * bf16_lo(w[c].w) + bf16_hi(a.w) * bf16_hi(w[c].w);
+    acc[0] = fmaf(bf16_lo(a[c].x), bf16_lo(w[c].x), fmaf(bf16_hi(a[c].x), bf16_hi(w[c].x), acc[0]));
+    acc[1] = fmaf(bf16_lo(a[c].y), bf16_lo(w[c].y), fmaf(bf16_hi(a[c].y), bf16_hi(w[c].y), acc[1]));
+    acc[2] = fmaf(bf16_lo(a[c].z), bf16_lo(w[c].z), fmaf(bf16_hi(a[c].z), bf16_hi(w[c].z), acc[2]));
+    acc[3] = fmaf(bf16_lo(a[c].w), bf16_lo(w[c].w), fmaf(bf16_hi(a[c].w), bf16_hi(w[c].w), acc[3]));
   }
-  return acc;
+  return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 __device__ __forceinline__ void load_row_swz(uint32_t base, int row, uint4 (&w)[8]) {
 #pragma unroll
@@ -869,6 +872,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       tmem_ld_32x16(t_lane + col_dq + 64 * i + 16 * hf, a0);
       tmem_ld_wait_dep16(a0);
       if (p.ntail > 0) {   // tail keys t against this thread's query x:  dQ[x] += dS[t][x] K[t]
+        if (i == 0) bar_sync_named(5, AT_BWD_SM + AT_TAIL_THREADS);
         const int x = i * 128 + r;
         for (int t = 0; t < p.ntail; ++t) {
           const float dsa = sDSA[t * SP + x];
@@ -908,16 +912,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV), o_u = smem_u32(sdO);
     mbar_wait(bar_ld, 0);
     bar_sync_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta written by the softmax warps
+    // tail queries first: the dK / dV epilogue of key tile 0 is the first consumer
     for (int t = 0; t < p.ntail; ++t) {
       const int rt = M0 + t;
       const float lse_t = sLse[rt], delta_t = sDelta[rt];
       uint4 w[8];
-      load_row_swz(k_u, rt, w);
-      for (int x = tt; x < S; x += AT_TAIL_THREADS)
-        sPA[t * SP + x] = ex2(fmaf(dot64_swz(q_u + x * AT_ROW, x & 7, w), sl2, -sLse[x]));
-      load_row_swz(v_u, rt, w);
-      for (int x = tt; x < S; x += AT_TAIL_THREADS)
-        sDSA[t * SP + x] = sPA[t * SP + x] * (dot64_swz(o_u + x * AT_ROW, x & 7, w) - sDelta[x]);
       load_row_swz(q_u, rt, w);
       for (int x = tt; x < M0; x += AT_TAIL_THREADS)
         sPB[t * SP + x] = ex2(fmaf(dot64_swz(k_u + x * AT_ROW, x & 7, w), sl2, -lse_t));
@@ -925,8 +924,19 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       for (int x = tt; x < M0; x += AT_TAIL_THREADS)
         sDSB[t * SP + x] = sPB[t * SP + x] * (dot64_swz(v_u + x * AT_ROW, x & 7, w) - delta_t);
     }
+    bar_arrive_named(4, AT_BWD_SM + AT_TAIL_THREADS);   // sPB / sDSB complete (bar.arrive orders the writes before it)
+    for (int t = 0; t < p.ntail; ++t) {
+      const int rt = M0 + t;
+      uint4 w[8];
+      load_row_swz(k_u, rt, w);
+      for (int x = tt; x < S; x += AT_TAIL_THREADS)
+        sPA[t * SP + x] = ex2(fmaf(dot64_swz(q_u + x * AT_ROW, x & 7, w), sl2, -sLse[x]));
+      load_row_swz(v_u, rt, w);
+      for (int x = tt; x < S; x += AT_TAIL_THREADS)
+        sDSA[t * SP + x] = sPA[t * SP + x] * (dot64_swz(o_u + x * AT_ROW, x & 7, w) - sDelta[x]);
+    }
+    bar_arrive_named(5, AT_BWD_SM + AT_TAIL_THREADS);   // sPA / sDSA complete: the dQ epilogue may read them
     bar_sync_named(2, AT_TAIL_THREADS);
-    bar_arrive_named(4, AT_BWD_SM + AT_TAIL_THREADS);   // scratch complete: the epilogues may read it
     // the tail rows' own gradients: lane owns columns 2 lane, 2 lane + 1; warp tw takes rows tw, tw + 3, ...
     const uint32_t coff = ((lane & 3) << 2);
     for (int t = 0; t < p.ntail; ++t) {
