@@ -343,8 +343,9 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_summary.json")
     if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture
       with open(tpath) as f:
-        traffic = json.load(f).get("traffic_bytes_per_launch_mean")
-      traffic_src = "profiles/r01_ncu_gemm_summary.json (6 captured launches, mean)"
+        tj = json.load(f)
+      traffic = tj.get("traffic_bytes_per_launch_mean")
+      traffic_src = "profiles/r01_ncu_gemm_summary.json (%d captured launches, mean)" % len(tj.get("launches", []))
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 forward/dgrad GEMMs)", "achieved": gemm_tf,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
                 "traffic": traffic, "traffic_source": traffic_src,
