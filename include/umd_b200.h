@@ -133,6 +133,16 @@ int umd_ln_modulate_bwd(const void* dy, int dy_is_bf16, const float* x, const fl
                         const float* gamma, const float* beta, const float* scale, long long ldmod, int n0, int s0,
                         int n1, int s1, int D, float* dx, int accumulate, float* dshift, float* dscale, long long ldd,
                         float* dgamma, float* dbeta, umd_stream_t stream);
+/* The same backward fused with the gate backward of the branch whose residual add produced x (models/vit.py:89-94,
+ * 106-108: x = x_prev + gate[sample] * z): with dx_new the value written to dx,
+ *   dz = gate * dx_new (bf16, required), dgate[sample] += sum_t z * dx_new (needs z; may be null),
+ *   dbias += gate * sum_t dx_new (bias of the Dense that produced z; may be null).  gate null = 1.
+ * dgate / dbias are accumulated with atomic adds — zero them first. */
+int umd_ln_modulate_bwd_gated(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, const float* beta, const float* scale, long long ldmod, int n0, int s0,
+                              int n1, int s1, int D, float* dx, int accumulate, float* dshift, float* dscale, long long ldd,
+                              float* dgamma, float* dbeta, void* dz_bf16, const void* z_bf16, const float* gate,
+                              long long ldgate, float* dgate, long long lddgate, float* dbias, umd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimiser over the flat arena (train_ae.py:124-152,365-374): global-norm clip + AdamW (bf16 mu)

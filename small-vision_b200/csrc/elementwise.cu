@@ -48,8 +48,11 @@ __device__ __forceinline__ float4 load_row4(const __nv_bfloat16* p) {
 // (vit.py:78-80,96-98,163; modulate vit.py:13-16; final modulation ae.py:166-170).
 // One warp per output row; lane owns float4 columns lane*4 + 128*i.
 // =========================================================================================
+#ifndef LN_FWD_MIN_CTAS
+#define LN_FWD_MIN_CTAS 6
+#endif
 template <int NV, typename OutT>
-__global__ void __launch_bounds__(256) ln_mod_fwd_kernel(LnFwdArgs a) {
+__global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= a.rows_out) return;
@@ -74,18 +77,20 @@ __global__ void __launch_bounds__(256) ln_mod_fwd_kernel(LnFwdArgs a) {
     // every load of the row is issued before the first store: x_out may alias x, so a store in between would
     // pin all later loads behind it
     uint2 braw[NV];
-    float4 g[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane * 4 + 128 * i;
       v[i] = *reinterpret_cast<const float4*>(src + c);
       braw[i] = (bp && !is_cond) ? *reinterpret_cast<const uint2*>(bp + c) : make_uint2(0u, 0u);
-      g[i] = gp ? *reinterpret_cast<const float4*>(gp + c) : make_float4(1.f, 1.f, 1.f, 1.f);
     }
+    // the per-sample gate row is cache-resident: it is fetched chunk by chunk next to its use so that the registers
+    // hold HBM loads in flight instead (40 registers per thread = six CTAs, 48 warps per SM)
+    const float* __restrict__ gpr = gp;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      v[i].x += g[i].x * bf16_lo(braw[i].x); v[i].y += g[i].y * bf16_hi(braw[i].x);
-      v[i].z += g[i].z * bf16_lo(braw[i].y); v[i].w += g[i].w * bf16_hi(braw[i].y);
+      const float4 g = gpr ? *reinterpret_cast<const float4*>(gpr + lane * 4 + 128 * i) : make_float4(1.f, 1.f, 1.f, 1.f);
+      v[i].x += g.x * bf16_lo(braw[i].x); v[i].y += g.y * bf16_hi(braw[i].x);
+      v[i].z += g.z * bf16_lo(braw[i].y); v[i].w += g.w * bf16_hi(braw[i].y);
     }
     if (a.x_out) {
 #pragma unroll

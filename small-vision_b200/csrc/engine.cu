@@ -728,6 +728,22 @@ extern "C" int umd_ln_modulate_bwd(const void* dy, int dy_is_bf16, const float* 
   a.ldd = ldd; a.dgamma = dgamma; a.dbeta = dbeta;
   return ln_mod_bwd(a, D, n0 + n1, dy_is_bf16 != 0, static_cast<cudaStream_t>(stream));
 }
+extern "C" int umd_ln_modulate_bwd_gated(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                         const float* gamma, const float* beta, const float* scale, long long ldmod, int n0,
+                                         int s0, int n1, int s1, int D, float* dx, int accumulate, float* dshift,
+                                         float* dscale, long long ldd, float* dgamma, float* dbeta, void* dz_bf16,
+                                         const void* z_bf16, const float* gate, long long ldgate, float* dgate,
+                                         long long lddgate, float* dbias, umd_stream_t stream) {
+  LnBwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dy = dy; a.x = x; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.scale = scale; a.ldmod = ldmod;
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.dx = dx; a.accumulate = accumulate; a.dshift = dshift; a.dscale = dscale;
+  a.ldd = ldd; a.dgamma = dgamma; a.dbeta = dbeta;
+  a.g_dz = static_cast<__nv_bfloat16*>(dz_bf16); a.g_z = static_cast<const __nv_bfloat16*>(z_bf16); a.g_gate = gate;
+  a.g_ldgate = ldgate; a.g_dgate = dgate; a.g_lddgate = lddgate; a.g_dbias = dbias;
+  UMD_REQUIRE(dz_bf16 != nullptr, "umd_ln_modulate_bwd_gated: dz is required (use umd_ln_modulate_bwd without a gate stage)");
+  return ln_mod_bwd(a, D, n0 + n1, dy_is_bf16 != 0, static_cast<cudaStream_t>(stream));
+}
 extern "C" int umd_cast_f32_to_bf16(const float* x, long long n, void* out, umd_stream_t stream) {
   return cast_bf16(x, n, out, static_cast<cudaStream_t>(stream));
 }

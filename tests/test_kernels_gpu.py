@@ -148,6 +148,66 @@ def test_ln_modulate_fwd_bwd(D, n0, s0, n1, s1, mod):
     assert float(dmod[:, 2 * D:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("D", [384, 768])
+@pytest.mark.parametrize("n0,s0,n1,s1", [(3, 164, 2, 68), (2, 257, 0, 0)])
+@pytest.mark.parametrize("with_gate", [True, False])
+def test_ln_modulate_bwd_with_fused_gate_stage(D, n0, s0, n1, s1, with_gate):
+  """x = x_prev + gate[sample] * (h + bias) feeds the LayerNorm (vit.py:89-98): one launch returns the stream gradient,
+  dz = gate * dx (bf16), dgate and the bias gradient next to the LayerNorm's own parameter gradients (App. E 1, 4-6)."""
+  lib = _lib()
+  L = lib.load()
+  g = torch.Generator().manual_seed(D + s0)
+  rows, B = n0 * s0 + n1 * s1, n0 + n1
+  sample = torch.cat([torch.arange(n0).repeat_interleave(s0), n0 + torch.arange(n1).repeat_interleave(s1)])
+  x_prev = torch.randn(rows, D, generator=g)
+  h = torch.randn(rows, D, generator=g).to(torch.bfloat16).float()
+  bias = torch.zeros(D, requires_grad=True)
+  gate = (0.5 * torch.randn(B, D, generator=g)).requires_grad_(True) if with_gate else None
+  gamma = (1 + 0.1 * torch.randn(D, generator=g)).requires_grad_(True)
+  beta = (0.1 * torch.randn(D, generator=g)).requires_grad_(True)
+  modt = (0.2 * torch.randn(B, 2 * D, generator=g)).requires_grad_(True)
+  z = (h + bias).requires_grad_(True)
+  z.retain_grad()
+  x = x_prev + (gate[sample] * z if with_gate else z)
+  x.retain_grad()
+  y = _ln_ref(x, gamma, beta, modt[:, :D], modt[:, D:], n0, s0, n1, s1)
+  dy = torch.randn(rows, D, generator=g).to(torch.bfloat16)
+  dx0 = torch.randn(rows, D, generator=g)
+  (y * dy.float()).sum().backward(retain_graph=True)
+  ln_dx = x.grad.clone()
+  for leaf in (x, z, bias, gamma, beta, modt) + ((gate,) if with_gate else ()):
+    leaf.grad = None
+  ((y * dy.float()).sum() + (x * dx0).sum()).backward()
+  xd = x.detach()
+  mean = xd.mean(-1)
+  rstd = 1.0 / torch.sqrt(xd.var(-1, unbiased=False) + 1e-6)
+  dx = dx0.to(DEV).clone()
+  dmod = torch.zeros(B, 2 * D, device=DEV)
+  dgamma, dbeta, dbias = (torch.zeros(D, device=DEV) for _ in range(3))
+  dgate = torch.zeros(B, D, device=DEV)
+  dz = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+  mg, gg = modt.detach().to(DEV), (gate.detach().to(DEV) if with_gate else None)
+  null = C.c_void_p(0)
+  # device copies are kept alive in named tensors: a temporary would be freed (and its memory reused) before the launch
+  dyg, xg, meang, rstdg = dy.to(DEV), xd.to(DEV), mean.to(DEV), rstd.to(DEV)
+  gammag, betag, zg = gamma.detach().to(DEV), beta.detach().to(DEV), z.detach().to(torch.bfloat16).to(DEV)
+  lib.check(L.umd_ln_modulate_bwd_gated(
+      lib.ptr(dyg), 1, lib.ptr(xg), lib.ptr(meang), lib.ptr(rstdg), lib.ptr(gammag), lib.ptr(betag),
+      C.c_void_p(mg.data_ptr() + 4 * D), C.c_longlong(2 * D), n0, s0, n1, s1, D, lib.ptr(dx), 1,
+      C.c_void_p(dmod.data_ptr()), C.c_void_p(dmod.data_ptr() + 4 * D), C.c_longlong(2 * D), lib.ptr(dgamma), lib.ptr(dbeta),
+      lib.ptr(dz), lib.ptr(zg), lib.ptr(gg) if with_gate else null, C.c_longlong(D),
+      lib.ptr(dgate) if with_gate else null, C.c_longlong(D), lib.ptr(dbias), lib.current_stream()), "ln bwd gated")
+  torch.cuda.synchronize()
+  assert U.rel_l2(dx.cpu(), x.grad) < 1e-4                     # dx_new = dx0 + LayerNorm backward
+  assert U.rel_l2(dx.cpu() - dx0, ln_dx) < 1e-3
+  assert U.rel_l2(dz.float().cpu(), z.grad) < 5e-3             # bf16 output
+  assert U.rel_l2(dbias.cpu(), bias.grad) < 1e-4
+  assert U.rel_l2(dgamma.cpu(), gamma.grad) < 1e-4 and U.rel_l2(dbeta.cpu(), beta.grad) < 1e-4
+  assert U.rel_l2(dmod.cpu(), modt.grad) < 1e-4
+  if with_gate:
+    assert U.rel_l2(dgate.cpu(), gate.grad) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------ attention
 def _attn_ref(qkv, n0, s0, n1, s1, H, Dh):
   D = H * Dh
