@@ -48,105 +48,124 @@ __device__ __forceinline__ float4 load_row4(const __nv_bfloat16* p) {
 // (vit.py:78-80,96-98,163; modulate vit.py:13-16; final modulation ae.py:166-170).
 // One warp per output row; lane owns float4 columns lane*4 + 128*i.
 // =========================================================================================
+// Work decomposition: grid (sample, row chunk), one warp per row, a warp walks over its rows of the chunk.  All rows of
+// a CTA belong to one sample, so the per-column coefficients are combined once per CTA into shared memory:
+//   y = xhat * A + B,   A = gamma (1 + scale[n]),   B = beta (1 + scale[n]) + shift[n],   G = gate[n]
+// A row then costs 12 + 6 shared-memory reads per thread instead of 24 + 6 cached global loads (gamma, beta, shift,
+// scale, gate), which had the L1 data path at 65 % (ncu) and capped the kernel at ~4.4 TB/s (tools/ubench/rowcopy.cu:
+// the same row-per-warp streams without the coefficient loads reach 6.8 TB/s), and no row -> sample division is left.
 #ifndef LN_FWD_MIN_CTAS
-#define LN_FWD_MIN_CTAS 6
+#define LN_FWD_MIN_CTAS 4
 #endif
 template <int NV, typename OutT>
-__global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdArgs a) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
-  if (r >= a.rows_out) return;
-  int in_row, sample;
-  if (a.gather_L > 0) {
-    sample = r / a.gather_L;
-    in_row = row_of(a.rm, sample, a.gather_off + (r - sample * a.gather_L));
-  } else {
-    in_row = r;
-    sample = (a.shift || a.scale) ? sample_of(a.rm, r) : 0;
-  }
+__global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdArgs a, int rows_per_chunk) {
   constexpr int D = NV * 128;
-  const float* xp = a.x + static_cast<long long>(in_row) * D;
-  float4 v[NV];
-  float s = 0.f, s2 = 0.f;
-  if (a.res_branch || a.cond_row || a.x_out) {
-    if (a.gather_L <= 0) sample = sample_of(a.rm, r);
-    const bool is_cond = a.cond_row && token_of(a.rm, in_row) == 0;
-    const __nv_bfloat16* bp = a.res_branch ? a.res_branch + static_cast<long long>(in_row) * D : nullptr;
-    const float* gp = a.res_gate ? a.res_gate + static_cast<long long>(sample) * a.ldgate : nullptr;
-    const float* src = is_cond ? a.cond_row + static_cast<long long>(sample) * D : xp;
-    // every load of the row is issued before the first store: x_out may alias x, so a store in between would
+  __shared__ __align__(16) float sA[D];
+  __shared__ __align__(16) float sB[D];
+  __shared__ __align__(16) float sG[D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x;
+  const int S = a.gather_L > 0 ? a.gather_L : seq_of(a.rm, n);
+  const int tok_begin = blockIdx.y * rows_per_chunk;
+  if (tok_begin >= S) return;
+  const int tok_end = min(S, tok_begin + rows_per_chunk);
+  {
+    const float* shp = a.shift ? a.shift + static_cast<long long>(n) * a.ldmod : nullptr;
+    const float* scp = a.scale ? a.scale + static_cast<long long>(n) * a.ldmod : nullptr;
+    const float* gp = (a.res_branch && a.res_gate) ? a.res_gate + static_cast<long long>(n) * a.ldgate : nullptr;
+    for (int c = threadIdx.x; c < D; c += 256) {
+      const float sc1 = scp ? 1.f + scp[c] : 1.f;
+      sA[c] = a.gamma[c] * sc1;
+      sB[c] = a.beta[c] * sc1 + (shp ? shp[c] : 0.f);
+      sG[c] = gp ? gp[c] : 1.f;
+    }
+  }
+  __syncthreads();
+  for (int tok = tok_begin + warp; tok < tok_end; tok += 8) {
+    int r, in_row;
+    if (a.gather_L > 0) {
+      r = n * a.gather_L + tok;
+      in_row = row_of(a.rm, n, a.gather_off + tok);
+    } else {
+      r = in_row = row_of(a.rm, n, tok);
+    }
+    const bool is_cond = a.cond_row && (a.gather_L > 0 ? a.gather_off + tok : tok) == 0;
+    const float* src = is_cond ? a.cond_row + static_cast<long long>(n) * D : a.x + static_cast<long long>(in_row) * D;
+    const __nv_bfloat16* bp = (a.res_branch && !is_cond) ? a.res_branch + static_cast<long long>(in_row) * D : nullptr;
+    // every HBM load of the row is issued before the first store: x_out may alias x, so a store in between would
     // pin all later loads behind it
+    float4 v[NV];
     uint2 braw[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane * 4 + 128 * i;
       v[i] = *reinterpret_cast<const float4*>(src + c);
-      braw[i] = (bp && !is_cond) ? *reinterpret_cast<const uint2*>(bp + c) : make_uint2(0u, 0u);
+      braw[i] = bp ? *reinterpret_cast<const uint2*>(bp + c) : make_uint2(0u, 0u);
     }
-    // the per-sample gate row is cache-resident: it is fetched chunk by chunk next to its use so that the registers
-    // hold HBM loads in flight instead (40 registers per thread = six CTAs, 48 warps per SM)
-    const float* __restrict__ gpr = gp;
+    if (bp) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 g = gpr ? *reinterpret_cast<const float4*>(gpr + lane * 4 + 128 * i) : make_float4(1.f, 1.f, 1.f, 1.f);
-      v[i].x += g.x * bf16_lo(braw[i].x); v[i].y += g.y * bf16_hi(braw[i].x);
-      v[i].z += g.z * bf16_lo(braw[i].y); v[i].w += g.w * bf16_hi(braw[i].y);
+      for (int i = 0; i < NV; ++i) {
+        const float4 g = *reinterpret_cast<const float4*>(&sG[lane * 4 + 128 * i]);
+        v[i].x += g.x * bf16_lo(braw[i].x); v[i].y += g.y * bf16_hi(braw[i].x);
+        v[i].z += g.z * bf16_lo(braw[i].y); v[i].w += g.w * bf16_hi(braw[i].y);
+      }
     }
     if (a.x_out) {
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(in_row) * D + lane * 4 + 128 * i) = v[i];
     }
-  } else {
+    float s = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xp + lane * 4 + 128 * i);
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
-    s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
-  }
-  s = warp_sum(s);
-  s2 = warp_sum(s2);
-  const float mean = s * (1.f / D);
-  const float var = fmaxf(s2 * (1.f / D) - mean * mean, 0.f);
-  const float rstd = rsqrtf(var + 1e-6f);
-  if (lane == 0) {
-    if (a.mean) a.mean[r] = mean;
-    if (a.rstd) a.rstd[r] = rstd;
-  }
-  // the parameter vectors never alias the output: restrict lets their loads move ahead of the row's stores
-  const float* __restrict__ shp = a.shift ? a.shift + static_cast<long long>(sample) * a.ldmod : nullptr;
-  const float* __restrict__ scp = a.scale ? a.scale + static_cast<long long>(sample) * a.ldmod : nullptr;
-  const float* __restrict__ gammap = a.gamma;
-  const float* __restrict__ betap = a.beta;
-  OutT* __restrict__ op = reinterpret_cast<OutT*>(a.out) + static_cast<long long>(r) * D;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int c = lane * 4 + 128 * i;
-    float4 g = *reinterpret_cast<const float4*>(gammap + c);
-    float4 b = *reinterpret_cast<const float4*>(betap + c);
-    float y0 = (v[i].x - mean) * rstd * g.x + b.x;
-    float y1 = (v[i].y - mean) * rstd * g.y + b.y;
-    float y2 = (v[i].z - mean) * rstd * g.z + b.z;
-    float y3 = (v[i].w - mean) * rstd * g.w + b.w;
-    if (scp) {
-      float4 sc = *reinterpret_cast<const float4*>(scp + c);
-      y0 *= (1.f + sc.x); y1 *= (1.f + sc.y); y2 *= (1.f + sc.z); y3 *= (1.f + sc.w);
+    for (int i = 0; i < NV; ++i) {
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+      s2 += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
     }
-    if (shp) {
-      float4 sh = *reinterpret_cast<const float4*>(shp + c);
-      y0 += sh.x; y1 += sh.y; y2 += sh.z; y3 += sh.w;
+    s = warp_sum(s);
+    s2 = warp_sum(s2);
+    const float mean = s * (1.f / D);
+    const float var = fmaxf(s2 * (1.f / D) - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + 1e-6f);
+    if (lane == 0) {
+      if (a.mean) a.mean[r] = mean;
+      if (a.rstd) a.rstd[r] = rstd;
     }
-    store_row4(op + c, y0, y1, y2, y3);
+    OutT* __restrict__ op = reinterpret_cast<OutT*>(a.out) + static_cast<long long>(r) * D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane * 4 + 128 * i;
+      const float4 A = *reinterpret_cast<const float4*>(&sA[c]);
+      const float4 B = *reinterpret_cast<const float4*>(&sB[c]);
+      store_row4(op + c, fmaf((v[i].x - mean) * rstd, A.x, B.x), fmaf((v[i].y - mean) * rstd, A.y, B.y),
+                 fmaf((v[i].z - mean) * rstd, A.z, B.z), fmaf((v[i].w - mean) * rstd, A.w, B.w));
+    }
   }
 }
 
 template <typename OutT>
 static int ln_fwd_dispatch(const LnFwdArgs& a, int D, cudaStream_t st) {
-  const int grid = ceil_div(a.rows_out, 8);
+  static int target_rows = 0;
+  if (target_rows == 0) {
+    const char* e = getenv("UMD_LN_FWD_ROWS");
+    target_rows = e ? atoi(e) : 32;
+    if (target_rows < 8) target_rows = 8;
+  }
+  int nsamples, smax;
+  if (a.gather_L > 0) {
+    nsamples = a.rows_out / a.gather_L;
+    smax = a.gather_L;
+  } else {
+    const bool second = a.rows_out > a.rm.split_row;
+    nsamples = second ? a.rm.n0 + (a.rows_out - a.rm.split_row) / a.rm.s1 : a.rows_out / a.rm.s0;
+    smax = a.rm.n0 > 0 ? a.rm.s0 : 0;
+    if (second && a.rm.s1 > smax) smax = a.rm.s1;
+  }
+  if (nsamples <= 0 || smax <= 0) return UMD_OK;
+  const int nchunks = ceil_div(smax, target_rows);
+  const int rpc = ceil_div(smax, nchunks);
+  const dim3 grid(nsamples, nchunks);
   switch (D / 128) {
-#define CASE(NV) case NV: ln_mod_fwd_kernel<NV, OutT><<<grid, 256, 0, st>>>(a); break;
+#define CASE(NV) case NV: ln_mod_fwd_kernel<NV, OutT><<<grid, 256, 0, st>>>(a, rpc); break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     default: set_error("ln_mod_fwd: width %d unsupported (need multiple of 128, <= 1024)", D); return UMD_ERR_UNSUPPORTED;
@@ -174,16 +193,27 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
 // Work decomposition: grid (sample, row chunk); a row is shared by W = 1 or 2 warps (W = 2 halves the per-thread
 // column state so that two CTAs fit on an SM); the per-sample sums leave by atomicAdd (several chunks per sample),
 // so the caller zeroes dshift / dscale / g_dgate beforehand.
+#ifndef LN_BWD_CTAS
+#define LN_BWD_CTAS 2
+#endif
 template <int NV, typename DyT, bool GATE>
-__global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int rows_per_chunk) {
+__global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs a, int rows_per_chunk) {
   constexpr int D = NV * 128;
   constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;  // warps per row
   constexpr int NL = NV / W;                            // float4 columns per lane
   constexpr int RP = 8 / W;                             // rows in flight per CTA
   constexpr int CPT = (D + 255) / 256;                  // columns per thread in the final cross-warp reductions
-  __shared__ float red[RP][D];
-  __shared__ float s_gs[D];                             // gamma * (1 + scale): d xhat = dy * s_gs
+  // sbuf: with the gate stage, the per-column sums A3 = sum_t z dx and A4 = sum_t dx of the RP rows in flight live
+  // here instead of in 24 registers per thread (each element is owned by one thread: plain read-modify-write); after
+  // the row loop the same memory is the scratch of the cross-warp reductions
+  extern __shared__ float4 ln_bwd_dyn_smem[];           // (GATE ? 2 : 1) * RP * D floats (see ln_bwd_smem_bytes)
+  float* sbuf = reinterpret_cast<float*>(ln_bwd_dyn_smem);
+  __shared__ __align__(16) float s_gs[D];               // gamma * (1 + scale): d xhat = dy * s_gs
+  __shared__ __align__(16) float s_gate[GATE ? D : 4];  // gate[n] (or 1): dz = gate * dx
   __shared__ float2 part[2][RP][2];
+  float (*red)[D] = reinterpret_cast<float (*)[D]>(sbuf);
+  float* acc3 = sbuf;
+  float* acc4 = sbuf + RP * D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rp = warp / W, half = warp % W;
   const int n = blockIdx.x;
@@ -192,16 +222,25 @@ __global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int row
   if (tok_begin >= S) return;
   const int tok_end = min(S, tok_begin + rows_per_chunk);
   const float* scp = a.scale ? a.scale + static_cast<long long>(n) * a.ldmod : nullptr;
-  for (int c = threadIdx.x; c < D; c += 256) s_gs[c] = a.gamma[c] * (scp ? 1.f + scp[c] : 1.f);
-  __syncthreads();
   const float* gatep = (GATE && a.g_gate) ? a.g_gate + static_cast<long long>(n) * a.g_ldgate : nullptr;
+  for (int c = threadIdx.x; c < D; c += 256) {
+    s_gs[c] = a.gamma[c] * (scp ? 1.f + scp[c] : 1.f);
+    if (GATE) s_gate[c] = gatep ? gatep[c] : 1.f;
+  }
+  __syncthreads();
   const int col0 = half * NL * 128 + lane * 4;
   // Every per-column sum of App. E steps 4-5 is a combination of A1 = sum_t dy and A2 = sum_t dy * xhat:
   //   dshift = A1, dscale = gamma A2 + beta A1, dbeta += (1+scale) A1, dgamma += (1+scale) A2;
   // the gate stage adds A3 = sum_t z dx and A4 = sum_t dx.
-  float4 A1[NL], A2[NL], A3[NL], A4[NL];
+  float4 A1[NL], A2[NL];
 #pragma unroll
-  for (int i = 0; i < NL; ++i) A1[i] = A2[i] = A3[i] = A4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NL; ++i) {
+    A1[i] = A2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (GATE) {
+      *reinterpret_cast<float4*>(&acc3[rp * D + col0 + 128 * i]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(&acc4[rp * D + col0 + 128 * i]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   int it = 0;
   for (int tok = tok_begin + rp; tok < tok_end; tok += RP) {
     const int xrow = row_of(a.rm, n, tok);
@@ -222,13 +261,18 @@ __global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int row
         if (a.accumulate) o = *reinterpret_cast<const float4*>(dxp + c);
         else *reinterpret_cast<float4*>(dxp + c) = o;
         if (GATE) {
-          float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (gatep) g = *reinterpret_cast<const float4*>(gatep + c);
+          const float4 g = *reinterpret_cast<const float4*>(&s_gate[c]);
           store_row4(a.g_dz + static_cast<long long>(xrow) * D + c, g.x * o.x, g.y * o.y, g.z * o.z, g.w * o.w);
-          A4[i].x += o.x; A4[i].y += o.y; A4[i].z += o.z; A4[i].w += o.w;
+          float4* p4 = reinterpret_cast<float4*>(&acc4[rp * D + c]);
+          float4 t4 = *p4;
+          t4.x += o.x; t4.y += o.y; t4.z += o.z; t4.w += o.w;
+          *p4 = t4;
           if (a.g_dgate) {
             const float4 z = load_row4(a.g_z + static_cast<long long>(xrow) * D + c);
-            A3[i].x += z.x * o.x; A3[i].y += z.y * o.y; A3[i].z += z.z * o.z; A3[i].w += z.w * o.w;
+            float4* p3 = reinterpret_cast<float4*>(&acc3[rp * D + c]);
+            float4 t3 = *p3;
+            t3.x += z.x * o.x; t3.y += z.y * o.y; t3.z += z.z * o.z; t3.w += z.w * o.w;
+            *p3 = t3;
           }
         }
       }
@@ -293,13 +337,18 @@ __global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int row
       }
       *reinterpret_cast<float4*>(dxp + c) = o;
       if (GATE) {
-        float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (gatep) g = *reinterpret_cast<const float4*>(gatep + c);
+        const float4 g = *reinterpret_cast<const float4*>(&s_gate[c]);
         store_row4(a.g_dz + static_cast<long long>(xrow) * D + c, g.x * o.x, g.y * o.y, g.z * o.z, g.w * o.w);
-        A4[i].x += o.x; A4[i].y += o.y; A4[i].z += o.z; A4[i].w += o.w;
+        float4* p4 = reinterpret_cast<float4*>(&acc4[rp * D + c]);
+        float4 t4 = *p4;
+        t4.x += o.x; t4.y += o.y; t4.z += o.z; t4.w += o.w;
+        *p4 = t4;
         if (want_z) {
-          A3[i].x += bf16_lo(zraw[i].x) * o.x; A3[i].y += bf16_hi(zraw[i].x) * o.y;
-          A3[i].z += bf16_lo(zraw[i].y) * o.z; A3[i].w += bf16_hi(zraw[i].y) * o.w;
+          float4* p3 = reinterpret_cast<float4*>(&acc3[rp * D + c]);
+          float4 t3 = *p3;
+          t3.x += bf16_lo(zraw[i].x) * o.x; t3.y += bf16_hi(zraw[i].x) * o.y;
+          t3.z += bf16_lo(zraw[i].y) * o.z; t3.w += bf16_hi(zraw[i].y) * o.w;
+          *p3 = t3;
         }
       }
     }
@@ -322,6 +371,24 @@ __global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int row
     }
   };
   float r1[CPT], r2[CPT];
+  if (GATE) {
+    // A4 / A3 are already in shared memory: sum the RP rows, then the scratch is free for A1 / A2
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+      const int c = threadIdx.x + 256 * k;
+      if (c < D) {
+        float t4 = 0.f, t3 = 0.f;
+#pragma unroll
+        for (int w = 0; w < RP; ++w) {
+          t4 += acc4[w * D + c];
+          t3 += acc3[w * D + c];
+        }
+        if (a.g_dbias) atomicAdd(a.g_dbias + c, s_gate[c] * t4);
+        if (a.g_dgate) atomicAdd(a.g_dgate + static_cast<long long>(n) * a.g_lddgate + c, t3);
+      }
+    }
+  }
   reduce(A1, r1);
   reduce(A2, r2);
 #pragma unroll
@@ -335,18 +402,22 @@ __global__ void __launch_bounds__(256, 2) ln_mod_bwd_kernel(LnBwdArgs a, int row
       atomicAdd(a.dbeta + c, sc1 * r1[k]);
     }
   }
-  if (GATE) {
-    reduce(A4, r1);
-    if (a.g_dgate) reduce(A3, r2);
-#pragma unroll
-    for (int k = 0; k < CPT; ++k) {
-      const int c = threadIdx.x + 256 * k;
-      if (c < D) {
-        if (a.g_dbias) atomicAdd(a.g_dbias + c, (gatep ? gatep[c] : 1.f) * r1[k]);
-        if (a.g_dgate) atomicAdd(a.g_dgate + static_cast<long long>(n) * a.g_lddgate + c, r2[k]);
-      }
+}
+
+template <int NV, typename DyT, bool GATE>
+static int ln_bwd_launch(const LnBwdArgs& a, dim3 grid, int rpc, cudaStream_t st) {
+  constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;
+  constexpr int BYTES = (GATE ? 2 : 1) * (8 / W) * NV * 128 * 4;
+  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE>;
+  if (BYTES > 48 * 1024) {
+    static bool cfg = false;
+    if (!cfg) {
+      UMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));
+      cfg = true;
     }
   }
+  kern<<<grid, 256, BYTES, st>>>(a, rpc);
+  return UMD_OK;
 }
 
 template <typename DyT>
@@ -366,8 +437,8 @@ static int ln_bwd_dispatch(const LnBwdArgs& a, int D, int nsamples, cudaStream_t
   switch (D / 128) {
 #define CASE(NV)                                                                     \
   case NV:                                                                           \
-    if (gate) ln_mod_bwd_kernel<NV, DyT, true><<<grid, 256, 0, st>>>(a, rpc);        \
-    else ln_mod_bwd_kernel<NV, DyT, false><<<grid, 256, 0, st>>>(a, rpc);            \
+    if (gate) UMD_TRY((ln_bwd_launch<NV, DyT, true>(a, grid, rpc, st)));             \
+    else UMD_TRY((ln_bwd_launch<NV, DyT, false>(a, grid, rpc, st)));                 \
     break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
