@@ -15,9 +15,12 @@
 //             dK_j += dS^T Q_i (K-major A) and dQ_i += dS K_j (the same tile read as an MN-major A) accumulate
 //             in TMEM; dK/dV leave after the query loop, dQ after the key loop.
 //
-// Warp roles (384 threads): warp 0 lane 0 TMA producer, warp 1 lane 0 MMA issuer, warp 2 TMEM allocator,
-// warps 4..11 softmax / epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the score columns, so
-// every SM sub-partition runs two softmax warps (latency hiding) and each row's work is split over two threads.
+// Warp roles: warp 0 TMA producer (one lane), warp 1 MMA issuer, warp 2 TMEM allocator, warps 4.. softmax / epilogue:
+// warp w owns TMEM lanes 32*(w%4) .. +31 and one part of the score columns.  Softmax is bound by MUFU.EX2 (16 lanes /
+// clk / SM) and by the TMEM read rate (~100-130 B / clk / SM), and its dependent chain load -> FFMA -> EX2 -> pack ->
+// store only reaches the MUFU rate with four warps per SM sub-partition (tools/ubench/pipes.cu), hence 16 softmax
+// warps per CTA (or two 8-warp CTAs per SM for short sequences).  Warps 0, 2, 3 are idle after set-up and take the
+// one-row tail of 257-token sequences (see split_tail).  Measurements and dead ends: profiles/r01_notes.md.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -52,11 +55,6 @@ __device__ __forceinline__ float ex2(float x) {
 __device__ __forceinline__ void bar_softmax() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 template <int NT>
 __device__ __forceinline__ void bar_softmax_n() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
-
-// 16-byte chunk `chunk` (0..7) of row r of a [rows][64] bf16 slab in the 128B-swizzled layout TMA / UMMA use.
-__device__ __forceinline__ void st_swz(uint8_t* slab, int r, int chunk, uint4 v) {
-  *reinterpret_cast<uint4*>(slab + r * AT_ROW + ((chunk ^ (r & 7)) << 4)) = v;
-}
 
 // rows [0, rows) of one sample (tensor map dims: column, row in sample, sample; rows >= S are zero-filled).
 // tm16 is the tensor map whose box holds the rows % 128 tail rows (a multiple of 16).
@@ -504,7 +502,6 @@ struct BwdParams {
   int ntail;  // trailing rows S - 128 nt (1..AT_TAIL) handled on the idle control warps, else 0
   int nbuf;  // TMEM score buffers (2 when nt <= 2)
   int prefetch;  // issue the next block's scores ahead of this block's accumulation (needs nbuf == 2)
-  int stagger_ctas, stagger_ns;
   int lse_bulk;  // the sample's [S][H] lse block is 16-byte aligned: fetch it with one bulk copy
   int ahead;     // L2 prefetch distance in CTAs (0 = off)
   int tl_cta;
@@ -519,7 +516,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
                    const __grid_constant__ CUtensorMap to16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if (static_cast<int>(blockIdx.x) < p.stagger_ctas) __nanosleep((blockIdx.x & 7) * p.stagger_ns);
   const int S = p.S, SP = p.SP, nt = p.nt, nbuf = p.nbuf;
   const int D = p.H * AT_DH;
   const int h = blockIdx.x % p.H;
@@ -1022,19 +1018,6 @@ int tail_limit(bool backward) {
   }
   return g_tail_limit[backward ? 1 : 0];
 }
-// Every CTA of these kernels runs the same load -> compute -> store sequence for the same time, so a grid that
-// starts in lockstep stays in lockstep and hammers HBM in bursts.  Offsetting the start of the first wave spreads
-// the phases for the rest of the launch.  Only worth it when the grid runs for several waves.
-void stagger_params(int ctas, int* n_ctas, int* ns) {
-  static int env_ns = -1;
-  if (env_ns < 0) {
-    const char* e = getenv("UMD_ATTN_STAGGER_NS");
-    env_ns = e ? atoi(e) : 0;
-  }
-  const int sms = sm_count();
-  *n_ctas = (ctas >= 4 * sms) ? sms : 0;
-  *ns = env_ns;
-}
 int segments(const RowMap& rm, int nsamples, Segment (&seg)[2]) {
   int k = 0;
   const int n0 = rm.n0 < nsamples ? rm.n0 : nsamples;
@@ -1137,7 +1120,6 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     p.scale = a.scale; p.scale_log2 = a.scale * LOG2E;
     p.tl = g_attn_timeline;
     { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
-    stagger_params(n * a.H, &p.stagger_ctas, &p.stagger_ns);
     static int pf = -1;
     if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
     p.ahead = pf ? sm_count() : 0;
