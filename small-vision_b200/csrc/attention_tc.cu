@@ -1003,17 +1003,19 @@ void split_tail(int S, int max_tail, int* tiles, int* tail) {
   }
 }
 // Largest tail that goes to the control warps.  The three tail warps share their sub-partitions with the softmax
-// warps, so the tail work must stay well below the main loop: measured on B200, one tail row pays in both directions
-// (257 tokens: forward 0.53 -> 0.41 ms, backward 1.10 -> 0.81 ms per decoder layer) while the four rows of the
-// 260-token label-conditioned encoder do not (forward 0.27 -> 0.35 ms, backward 0.55 -> 0.86 ms), so the default
-// limit is 1; the kernels handle up to AT_TAIL (tests raise the limit through umd_debug_attn_tail_limits).
+// warps, so the tail work must stay well below the main loop.  Measured on B200 per layer (512 samples, 12 heads):
+//   257 tokens (every adaLN decoder):       forward 0.53 -> 0.41 ms, backward 1.10 -> 0.77 ms
+//   258 tokens (decoder with a cond token): forward 0.53 -> 0.45 ms, backward 1.11 -> 1.01 ms
+//   260 tokens (label-conditioned encoder, 256 samples): forward 0.27 -> 0.35 ms, backward 0.55 -> 0.86 ms (worse)
+// hence the default limit of 2 rows; the kernels handle up to AT_TAIL (tests raise the limit through
+// umd_debug_attn_tail_limits).
 int g_tail_limit[2] = {-1, -1};
 int tail_limit(bool backward) {
   if (g_tail_limit[0] < 0) {
     const char* f = getenv("UMD_ATTN_TAIL_FWD_MAX");
     const char* b = getenv("UMD_ATTN_TAIL_BWD_MAX");
-    g_tail_limit[0] = f ? atoi(f) : 1;
-    g_tail_limit[1] = b ? atoi(b) : 1;
+    g_tail_limit[0] = f ? atoi(f) : 2;
+    g_tail_limit[1] = b ? atoi(b) : 2;
     for (int k = 0; k < 2; ++k) g_tail_limit[k] = g_tail_limit[k] < 0 ? 0 : (g_tail_limit[k] > AT_TAIL ? AT_TAIL : g_tail_limit[k]);
   }
   return g_tail_limit[backward ? 1 : 0];

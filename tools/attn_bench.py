@@ -29,7 +29,7 @@ def main():
   H, Dh = 12, 64
   D = H * Dh
   for name, n0, s0, n1, s1 in (("decoder", 512, 257, 0, 0), ("encoder", 256, 164, 256, 68), ("enc_noise", 256, 164, 0, 0),
-                               ("enc_mae", 0, 0, 256, 68), ("dit_enc", 256, 260, 0, 0)):
+                               ("enc_mae", 0, 0, 256, 68), ("dit_enc", 256, 260, 0, 0), ("mae_dec", 512, 258, 0, 0)):
     rows = n0 * s0 + n1 * s1
     qkv = torch.randn(rows, 3 * D, device="cuda").to(torch.bfloat16)
     dout = torch.randn(rows, D, device="cuda").to(torch.bfloat16)
