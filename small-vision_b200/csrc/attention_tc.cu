@@ -534,7 +534,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   __shared__ __align__(16) float sLse[AT_STAT_N];     // lse * log2e
   __shared__ __align__(16) float sDelta[AT_STAT_N];   // rowsum(dO * O)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + 2 * AT_SLAB);
-  uint64_t* bar_ld = bars + 0;
+  uint64_t* bar_ld = bars + 0;      // Q, K, V have landed (the last of the two load groups)
+  uint64_t* bar_ld0 = bars + 11;    // dO, O and the lse block have landed: delta can be formed while Q, K, V stream in
   uint64_t* bar_s = bars + 1;       // [2]
   uint64_t* bar_sfree = bars + 3;   // [2]
   uint64_t* bar_p = bars + 5;       // [2] one per 64-query half
@@ -564,6 +565,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_ld, 1);
+    mbar_init(bar_ld0, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
       mbar_init(&bar_sfree[i], AT_BWD_SM);
@@ -589,13 +591,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     // O (for delta) and this sample's [S][H] block of log-sum-exps are parked in the P^T / dS^T tile region,
     // which has no other use until the first score tile has been processed
     const uint32_t lse_bytes = p.lse_bulk ? static_cast<uint32_t>(S) * p.H * 4u : 0u;
-    mbar_expect_tx(bar_ld, 5u * SP * AT_ROW + lse_bytes);
+    mbar_expect_tx(bar_ld0, 2u * SP * AT_ROW + lse_bytes);
+    load_rows(sdO, &td128, &td16, bar_ld0, h * AT_DH, sample, SP);
+    load_rows(sPt, &to128, &to16, bar_ld0, h * AT_DH, sample, SP);
+    if (p.lse_bulk) bulk_load_1d(sPt + SP * AT_ROW, p.lse + static_cast<long long>(row0) * p.H, lse_bytes, bar_ld0);
+    mbar_expect_tx(bar_ld, 3u * SP * AT_ROW);
     load_rows(sK, &tq128, &tq16, bar_ld, D + h * AT_DH, sample, SP);
     load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, sample, SP);
     load_rows(sV, &tq128, &tq16, bar_ld, 2 * D + h * AT_DH, sample, SP);
-    load_rows(sdO, &td128, &td16, bar_ld, h * AT_DH, sample, SP);
-    load_rows(sPt, &to128, &to16, bar_ld, h * AT_DH, sample, SP);
-    if (p.lse_bulk) bulk_load_1d(sPt + SP * AT_ROW, p.lse + static_cast<long long>(row0) * p.H, lse_bytes, bar_ld);
     const int nxt = blockIdx.x + p.ahead;
     if (p.ahead > 0 && nxt < static_cast<int>(gridDim.x)) {
       const int h2 = nxt % p.H, s2 = nxt / p.H;
@@ -623,6 +626,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const uint64_t st_k = make_smem_desc_sw128(smem_u32(sdSt), 0, 1024);   // dS^T as K-major A
     const uint64_t st_mn = make_smem_desc_sw128(smem_u32(sdSt), AT_SLAB, 1024);  // dS^T tile as MN-major A (= dS)
     const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && lane == 0;
+    mbar_wait(bar_ld0, 0);
     mbar_wait(bar_ld, 0);
     tc_fence_after();
     TL(0, 0);
@@ -727,7 +731,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       float lse_direct = 0.f;
       if (!p.lse_bulk && tid < S) lse_direct = p.lse[static_cast<long long>(row0 + tid) * p.H + h];
       TL(4, 2);
-      mbar_wait(bar_ld, 0);
+      mbar_wait(bar_ld0, 0);
       TL(4, 3);
       const int q = tid;   // AT_BWD_SM >= AT_MAX_S: one query row per thread
       if (q < SP) {
@@ -906,6 +910,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const int tw = tt >> 5;
     const float sl2 = p.scale_log2;
     const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV), o_u = smem_u32(sdO);
+    mbar_wait(bar_ld0, 0);
     mbar_wait(bar_ld, 0);
     bar_sync_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta written by the softmax warps
     // tail queries first: the dK / dV epilogue of key tile 0 is the first consumer
