@@ -164,3 +164,45 @@ def test_mae_branch_gives_zero_gradient_to_eps_half_of_final_conv():
   gk = g["final_conv"]["kernel"]
   assert float(gk[..., 3:].abs().max()) == 0.0 and float(gk[..., :3].abs().max()) > 0.0
   assert float(g["final_conv"]["bias"][3:].abs().max()) == 0.0
+
+
+def test_evaluator_predict_functions_match_oracle():
+  """train_ae.py:384-470: representation at t = 0 and of a noised input, MAE reconstruction
+  with its mask, and the denoising evaluation loss, on supplied draws."""
+  from small_vision_b200 import evaluators as E
+  from small_vision_b200.diffusion import create_gaussian_diffusion, to_device
+  model, ocfg = U.make_models("S/4", adaln=True, num_classes=None, depth=2, dec_depth=1)
+  params = U.perturb_init(model, 5, DEV)
+  oparams = U.cpu_tree(params)
+  gd = create_gaussian_diffusion("cosine", 1000)
+  state = {"params": params, "gd": to_device(gd, DEV), "rng": 0}
+  g = torch.Generator().manual_seed(9)
+  n, C = 4, 3
+  image = torch.rand(n, 64, 64, C, generator=g) * 2 - 1
+  noise = torch.randn(n, 64, 64, C, generator=g)
+  t = torch.randint(0, 1000, (n, 1), generator=g, dtype=torch.int32)
+  mn = torch.rand(n, model.cfg.num_patches, generator=g)
+  batch = {"image": image.to(DEV), "_rand": {"noise": noise.to(DEV), "t": t.to(DEV), "mae_noise": mn.to(DEV)}}
+  # predict_fn
+  _, out = E.make_predict_fn(model)(state, batch)
+  _, oout = O.model_apply(oparams, ocfg, image, t=torch.zeros(n, 1, dtype=torch.int32))
+  assert U.rel_l2(out["pre_logits"].cpu(), oout["pre_logits"]) <= U.TOL_PRED_REL_L2
+  # noised representation at t = 50
+  _, out = E.create_noised_pred_fn(model, 50)(state, batch)
+  t50 = torch.full((n, 1), 50, dtype=torch.int32)
+  _, oout = O.model_apply(oparams, ocfg, O.q_sample(gd, image, t50, noise), t=t50 + 1)
+  assert U.rel_l2(out["pre_logits"].cpu(), oout["pre_logits"]) <= U.TOL_PRED_REL_L2
+  # MAE reconstruction
+  px0, mask = E.make_eval_patch_fn(model, 0.75)(state, batch)
+  opred, oout = O.model_apply(oparams, ocfg, image, t=torch.zeros(n, 1, dtype=torch.int32), mask=0.75, mask_noise=mn)
+  assert torch.equal(mask.cpu(), oout["mask"])
+  assert U.rel_l2(px0.cpu(), opred[..., :C]) <= U.TOL_PRED_REL_L2
+  # evaluation loss
+  loss, x_t, pred_x0, pred_x0_eps = E.make_eval_loss_fn(model)(state, batch)
+  ox_t = O.q_sample(gd, image, t, noise)
+  opred, _ = O.model_apply(oparams, ocfg, ox_t, t=t + 1)
+  oloss = (torch.mean((opred[..., C:] - noise) ** 2) + torch.mean((opred[..., :C] - image) ** 2)) / 2
+  assert abs(float(loss) - float(oloss)) <= U.TOL_LOSS_REL * abs(float(oloss))
+  assert torch.allclose(x_t.cpu(), ox_t, rtol=1e-5, atol=1e-6)
+  assert U.rel_l2(pred_x0.cpu(), opred[..., :C]) <= U.TOL_PRED_REL_L2
+  assert U.rel_l2(pred_x0_eps.cpu(), O.predict_xstart_from_eps(gd, ox_t, t, opred[..., C:])) <= U.TOL_PRED_REL_L2
