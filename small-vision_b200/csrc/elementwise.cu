@@ -196,7 +196,11 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
 #ifndef LN_BWD_CTAS
 #define LN_BWD_CTAS 2
 #endif
-template <int NV, typename DyT, bool GATE>
+// STAGED: a row's operands (x, dy, the dx to accumulate into, z) are brought into shared memory by per-thread cp.async
+// one row ahead of their use instead of being loaded into registers when the row starts: with 126 registers per
+// thread only eight rows fit into an SM's register file at once, and a warp pair had no loads in flight while it
+// reduced and stored its row; the shared-memory slots keep a second row per warp pair in flight at all times.
+template <int NV, typename DyT, bool GATE, bool STAGED>
 __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs a, int rows_per_chunk) {
   constexpr int D = NV * 128;
   constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;  // warps per row
@@ -214,6 +218,10 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
   float (*red)[D] = reinterpret_cast<float (*)[D]>(sbuf);
   float* acc3 = sbuf;
   float* acc4 = sbuf + RP * D;
+  // staging slots (STAGED): per warp two slots of [x | dx | dy | z], each part lane-major (conflict-free 16 / 8 B)
+  constexpr int DYB = sizeof(DyT) == 2 ? 8 : 16;
+  constexpr int OFF_PV = NL * 512, OFF_DY = 2 * NL * 512, OFF_Z = OFF_DY + NL * 32 * DYB;
+  constexpr int SLOT_BYTES = OFF_Z + NL * 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rp = warp / W, half = warp % W;
   const int n = blockIdx.x;
@@ -242,7 +250,30 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
     }
   }
   int it = 0;
-  for (int tok = tok_begin + rp; tok < tok_end; tok += RP) {
+  const bool want_z_s = GATE && a.g_dgate;
+  const uint32_t stage_u = smem_u32(sbuf + (GATE ? 2 : 1) * RP * D) + (threadIdx.x >> 5) * 2 * SLOT_BYTES;
+  auto stage_row = [&](int tok, int slot) {
+    const long long off = static_cast<long long>(row_of(a.rm, n, tok)) * D + col0;
+    const uint32_t sb = stage_u + slot * SLOT_BYTES;
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+      cp_async16(sb + (i * 32 + lane) * 16, a.x + off + 128 * i);
+      if (a.accumulate) cp_async16(sb + OFF_PV + (i * 32 + lane) * 16, a.dx + off + 128 * i);
+      if (DYB == 8) cp_async8(sb + OFF_DY + (i * 32 + lane) * 8, reinterpret_cast<const DyT*>(a.dy) + off + 128 * i);
+      else cp_async16(sb + OFF_DY + (i * 32 + lane) * 16, reinterpret_cast<const DyT*>(a.dy) + off + 128 * i);
+      if (want_z_s) cp_async8(sb + OFF_Z + (i * 32 + lane) * 8, a.g_z + off + 128 * i);
+    }
+    cp_async_commit();
+  };
+  float mean_c = 0.f, rstd_c = 0.f;
+  int slot = 0;
+  if (STAGED && tok_begin + rp < tok_end) {
+    stage_row(tok_begin + rp, 0);
+    const int r0 = row_of(a.rm, n, tok_begin + rp);
+    mean_c = a.mean[r0];
+    rstd_c = a.rstd[r0];
+  }
+  for (int tok = tok_begin + rp; tok < tok_end; tok += RP, slot ^= 1) {
     const int xrow = row_of(a.rm, n, tok);
     float* dxp = a.dx + static_cast<long long>(xrow) * D;
     int drow = xrow;
@@ -278,9 +309,28 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
       }
       continue;
     }
-    const float mean = a.mean[drow], rstd = a.rstd[drow];
+    float mean, rstd;
     const float* xp = a.x + static_cast<long long>(xrow) * D;
     const DyT* dyp = reinterpret_cast<const DyT*>(a.dy) + static_cast<long long>(drow) * D;
+    const uint32_t sb = stage_u + slot * SLOT_BYTES;
+    if (STAGED) {
+      // next row of this warp pair into the other slot (its previous content was consumed one iteration ago), then
+      // wait for everything but that newest group: the current row has landed
+      mean = mean_c;
+      rstd = rstd_c;
+      if (tok + RP < tok_end) {
+        stage_row(tok + RP, slot ^ 1);
+        const int rn = row_of(a.rm, n, tok + RP);
+        mean_c = a.mean[rn];
+        rstd_c = a.rstd[rn];
+      } else {
+        cp_async_commit();
+      }
+      cp_async_wait<1>();
+    } else {
+      mean = a.mean[drow];
+      rstd = a.rstd[drow];
+    }
     float4 xh[NL], dh[NL];
     float m1 = 0.f, m2 = 0.f;
     // everything this row needs from HBM is requested up front (the second half of the row's work would otherwise
@@ -291,14 +341,33 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
       const int c = col0 + 128 * i;
-      pv[i] = a.accumulate ? *reinterpret_cast<const float4*>(dxp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-      zraw[i] = want_z ? *reinterpret_cast<const uint2*>(a.g_z + static_cast<long long>(xrow) * D + c) : make_uint2(0u, 0u);
+      if (STAGED) {
+        const uint4 pr = a.accumulate ? ld_shared_v4(sb + OFF_PV + (i * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
+        pv[i] = make_float4(__uint_as_float(pr.x), __uint_as_float(pr.y), __uint_as_float(pr.z), __uint_as_float(pr.w));
+        zraw[i] = want_z ? ld_shared_v2(sb + OFF_Z + (i * 32 + lane) * 8) : make_uint2(0u, 0u);
+      } else {
+        pv[i] = a.accumulate ? *reinterpret_cast<const float4*>(dxp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        zraw[i] = want_z ? *reinterpret_cast<const uint2*>(a.g_z + static_cast<long long>(xrow) * D + c) : make_uint2(0u, 0u);
+      }
     }
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
       const int c = col0 + 128 * i;
-      const float4 xv = *reinterpret_cast<const float4*>(xp + c);
-      const float4 dy = load_row4(dyp + c);
+      float4 xv, dy;
+      if (STAGED) {
+        const uint4 xr = ld_shared_v4(sb + (i * 32 + lane) * 16);
+        xv = make_float4(__uint_as_float(xr.x), __uint_as_float(xr.y), __uint_as_float(xr.z), __uint_as_float(xr.w));
+        if (DYB == 8) {
+          const uint2 dr = ld_shared_v2(sb + OFF_DY + (i * 32 + lane) * 8);
+          dy = make_float4(bf16_lo(dr.x), bf16_hi(dr.x), bf16_lo(dr.y), bf16_hi(dr.y));
+        } else {
+          const uint4 dr = ld_shared_v4(sb + OFF_DY + (i * 32 + lane) * 16);
+          dy = make_float4(__uint_as_float(dr.x), __uint_as_float(dr.y), __uint_as_float(dr.z), __uint_as_float(dr.w));
+        }
+      } else {
+        xv = *reinterpret_cast<const float4*>(xp + c);
+        dy = load_row4(dyp + c);
+      }
       const float4 gs = *reinterpret_cast<const float4*>(&s_gs[c]);
       xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
       A1[i].x += dy.x; A1[i].y += dy.y; A1[i].z += dy.z; A1[i].w += dy.w;
@@ -404,20 +473,35 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
   }
 }
 
-template <int NV, typename DyT, bool GATE>
-static int ln_bwd_launch(const LnBwdArgs& a, dim3 grid, int rpc, cudaStream_t st) {
-  constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;
-  constexpr int BYTES = (GATE ? 2 : 1) * (8 / W) * NV * 128 * 4;
-  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE>;
-  if (BYTES > 48 * 1024) {
+template <int NV, typename DyT, bool GATE, bool STAGED>
+static int ln_bwd_launch_cfg(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cudaStream_t st) {
+  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE, STAGED>;
+  if (bytes > 48 * 1024) {
     static bool cfg = false;
     if (!cfg) {
-      UMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));
+      UMD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
       cfg = true;
     }
   }
-  kern<<<grid, 256, BYTES, st>>>(a, rpc);
+  kern<<<grid, 256, bytes, st>>>(a, rpc);
   return UMD_OK;
+}
+template <int NV, typename DyT, bool GATE>
+static int ln_bwd_launch(const LnBwdArgs& a, dim3 grid, int rpc, cudaStream_t st) {
+  constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;
+  constexpr int NL = NV / W;
+  constexpr int BYTES = (GATE ? 2 : 1) * (8 / W) * NV * 128 * 4;
+  constexpr int DYB = sizeof(DyT) == 2 ? 8 : 16;
+  constexpr int STAGE_BYTES = 8 * 2 * (2 * NL * 512 + NL * 32 * DYB + NL * 256);
+  static int staged_on = -1;
+  if (staged_on < 0) {
+    const char* e = getenv("UMD_LN_BWD_STAGED");
+    staged_on = e ? atoi(e) : 1;
+  }
+  // the staged variant needs every row of the grid to be a LayerNorm row (no gather window) and two CTAs per SM
+  if (staged_on && a.gather_L <= 0 && BYTES + STAGE_BYTES <= 110 * 1024)
+    return ln_bwd_launch_cfg<NV, DyT, GATE, true>(a, grid, rpc, BYTES + STAGE_BYTES, st);
+  return ln_bwd_launch_cfg<NV, DyT, GATE, false>(a, grid, rpc, BYTES, st);
 }
 
 template <typename DyT>
