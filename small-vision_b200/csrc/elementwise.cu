@@ -1049,16 +1049,25 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedArgs a, const float
     }
     __syncthreads();
     if (active) {
-      for (int rr = 0; rr < nr; ++rr) {
-        const float4 d = *reinterpret_cast<const float4*>(dx + xrow_s[rr] * a.D + cg * 4);
+      // four rows of dx in flight per thread (one dependent load per iteration left the kernel at ~1.2 TB/s)
+      for (int rr = 0; rr < nr; rr += 4) {
+        float4 d[4];
 #pragma unroll
-        for (int e = 0; e < KE; ++e) {
-          const float pv = pe[rr][e];
-          acc[e].x += pv * d.x; acc[e].y += pv * d.y; acc[e].z += pv * d.z; acc[e].w += pv * d.w;
-        }
-        if (blockIdx.y == 0) {
-          accb.x += d.x; accb.y += d.y; accb.z += d.z; accb.w += d.w;
-          red_add_v4(dpos + static_cast<long long>(pid_s[rr]) * a.D + cg * 4, d.x, d.y, d.z, d.w);
+        for (int u = 0; u < 4; ++u)
+          d[u] = (rr + u < nr) ? *reinterpret_cast<const float4*>(dx + xrow_s[rr + u] * a.D + cg * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (rr + u < nr) {
+#pragma unroll
+            for (int e = 0; e < KE; ++e) {
+              const float pv = pe[rr + u][e];
+              acc[e].x += pv * d[u].x; acc[e].y += pv * d[u].y; acc[e].z += pv * d[u].z; acc[e].w += pv * d[u].w;
+            }
+            if (blockIdx.y == 0) {
+              accb.x += d[u].x; accb.y += d[u].y; accb.z += d[u].z; accb.w += d[u].w;
+              red_add_v4(dpos + static_cast<long long>(pid_s[rr + u]) * a.D + cg * 4, d[u].x, d[u].y, d[u].z, d[u].w);
+            }
+          }
         }
       }
     }
