@@ -156,17 +156,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint8_t* sP = sV + SP * AT_ROW;          // nslab slabs [128 q][64 kv]
   constexpr int NQ = TWO ? 2 : 4;
   constexpr int SMT = 128 * NQ;                                    // softmax / epilogue threads
-  float* sMax = reinterpret_cast<float*>(sP + nslab * AT_SLAB);    // [NQ parts][128 rows]
-  float* sSum = sMax + 512;                                        // [NQ parts][128 rows]
-  float* sTs = sSum + 512;                                         // [AT_MAX_S] tail-row scores / probabilities
+  uint8_t* sStage = sP + nslab * AT_SLAB;  // [128 q][64] output tile on its way to the TMA store
+  float* sMax = reinterpret_cast<float*>(sStage + AT_SLAB);        // [NQ parts][128 rows]
+  float* sSum = sMax + 512;                                        // [2 tiles in flight][NQ parts][128 rows]
+  float* sTs = sSum + 1024;                                        // [AT_MAX_S] tail-row scores / probabilities
   float* sTr = sTs + AT_MAX_S;                                     // [3][64] tail-row partial outputs, [8] reductions
   uint64_t* bars = reinterpret_cast<uint64_t*>(sTr + 3 * 64 + 16);
   uint64_t* bar_k = bars + 0;    // K and the first query tile have landed
   uint64_t* bar_v = bars + 1;    // V and the remaining query rows have landed
   uint64_t* bar_s = bars + 2;    // scores of the current tile are in TMEM
-  uint64_t* bar_o = bars + 3;    // P V of the current tile is in TMEM
-  uint64_t* bar_p = bars + 4;    // P of the current tile is in shared memory (and S, O_{i-1} have been read)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* bar_p = bars + 3;    // P of the current tile is in shared memory (and S has been read)
+  uint64_t* bar_o = bars + 4;    // [2] P V of tile i is in TMEM accumulator i & 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -178,7 +179,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     mbar_init(bar_k, 1);
     mbar_init(bar_v, 1);
     mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
+    mbar_init(&bar_o[0], 1);
+    mbar_init(&bar_o[1], 1);
     mbar_init(bar_p, SMT);
     fence_barrier_init();
   }
@@ -242,11 +244,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     mbar_wait(bar_v, 0);
     tc_fence_after();
     for (int i = 0; i < nqt; ++i) {
-      // bar_p(i): every softmax thread has finished reading S(i) and writing P(i), and (program order) has long
-      // finished the epilogue of tile i-1 -> both the O accumulator and the S columns may be overwritten
+      // bar_p(i): every softmax thread has finished reading S(i) and writing P(i).  The next tile's scores go first
+      // (the softmax warps start on them while P V runs); O_i goes to accumulator i & 1, whose previous content
+      // (O_{i-2}) was read by the epilogue that precedes the arrival on bar_p(i-1) in program order.
       mbar_wait(bar_p, i & 1);
       tc_fence_after();
       TL(3, i);
+      if (i + 1 < nqt) {
+        TL(1, i + 1);
+        issue_qk(i + 1);
+        TL(2, i + 1);
+      }
+      const uint32_t o_acc = tmem_base + p.o_col + 64 * (i & 1);
       if (elect_one()) {
         uint64_t pa = p_desc, vb = v_desc;
         int kk = 0;
@@ -254,22 +263,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         for (; kk + 4 <= ksteps; kk += 4) {  // one 64-key slab of P per iteration
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_base + p.o_col, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv,
-                        (kk + k) > 0 ? 1u : 0u);
+            umma_f16_ss(o_acc, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv, (kk + k) > 0 ? 1u : 0u);
           pa += AT_SLAB / 16;
           vb += 4 * (16 * AT_ROW / 16);
         }
         for (int k = 0; kk < ksteps; ++kk, ++k)
-          umma_f16_ss(tmem_base + p.o_col, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv, kk > 0 ? 1u : 0u);
-        umma_commit(bar_o);
+          umma_f16_ss(o_acc, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv, kk > 0 ? 1u : 0u);
+        umma_commit(&bar_o[i & 1]);
       }
       __syncwarp();
-      // the next tile's scores run right behind P V of this one, while the softmax warps do the epilogue
-      if (i + 1 < nqt) {
-        TL(1, i + 1);
-        issue_qk(i + 1);
-        TL(2, i + 1);
-      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
@@ -286,10 +288,48 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const int tid = threadIdx.x - 128;
     const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
     TL(4, 0);
+    const uint32_t stage_row = smem_u32(sStage) + r * AT_ROW;
+    // epilogue of tile i: O_i / rowsum -> bf16 -> staging tile -> TMA store (clipped at S), log-sum-exp
+    auto epilogue = [&](int i, float ms) {
+      constexpr int OC = 64 / NQ;          // output columns per part
+      if (tid == 0) bulk_wait_read<0>();   // the previous store has finished reading the staging tile
+      mbar_wait(&bar_o[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      TL(8, i);
+      uint32_t o0[OC];
+      if constexpr (OC == 32) {
+        tmem_ld_32x32(t_lane + p.o_col + 64 * (i & 1) + OC * hf, o0);
+        tmem_ld_wait_dep32(o0);
+      } else {
+        tmem_ld_32x16(t_lane + p.o_col + 64 * (i & 1) + OC * hf, o0);
+        tmem_ld_wait_dep16(o0);
+      }
+      tc_fence_before();
+      bar_softmax_n<SMT>();                // partial sums of all parts are visible; staging tile is free
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) sum += sSum[(i & 1) * 512 + q * 128 + r];
+      const int row = i * 128 + r;
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int j = 0; j < OC; j += 8) {
+        st_shared_v4(stage_row + ((((OC / 8) * hf + (j >> 3)) ^ r7) << 4),
+                     pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
+                     pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
+      }
+      fence_proxy_async();
+      bar_softmax_n<SMT>();
+      if (tid == 0) {
+        tma_store_3d(&tmo, sStage, h * AT_DH, i * 128, sample);
+        bulk_commit();
+      }
+      if (row < S && p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
+      TL(9, i);
+    };
+    float ms_prev = 0.f;
     for (int i = 0; i < nqt; ++i) {
-      // the previous tile's output store must have finished reading its staging slab (slab 0 of P) before pass 2
-      // of this tile rewrites it; the max-exchange barrier below orders the other threads behind this wait
-      if (i > 0 && tid == 0) bulk_wait_read<0>();
       mbar_wait(bar_s, i & 1);
       tc_fence_after();
       TL(5, i);
@@ -315,6 +355,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 #pragma unroll
       for (int q = 1; q < NQ; ++q) m = fmaxf(m, sMax[((hf + q) % NQ) * 128 + r]);
       const float ms = m * sl2;
+      // P V of the previous tile reads the P slabs that pass 2 is about to overwrite (its Q K^T successor was issued
+      // ahead of it, so S(i) can be ready before P V(i-1) has finished): wait for its completion first
+      if (i > 0) mbar_wait(&bar_o[(i - 1) & 1], ((i - 1) >> 1) & 1);
       // pass 2: p = exp2(s * scale*log2e - max), partial row sum, bf16 P -> shared memory
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -333,47 +376,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_p);
-      float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      sSum[hf * 128 + r] = sum;
+      sSum[(i & 1) * 512 + hf * 128 + r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       TL(7, i);
-      // epilogue: O / rowsum; each half owns 32 of the 64 output columns
-      mbar_wait(bar_o, i & 1);
-      tc_fence_after();
-      TL(8, i);
-      constexpr int OC = 64 / NQ;          // output columns per part
-      uint32_t o0[OC];
-      if constexpr (OC == 32) {
-        tmem_ld_32x32(t_lane + p.o_col + OC * hf, o0);
-        tmem_ld_wait_dep32(o0);
-      } else {
-        tmem_ld_32x16(t_lane + p.o_col + OC * hf, o0);
-        tmem_ld_wait_dep16(o0);
-      }
-      tc_fence_before();
-      bar_softmax_n<SMT>();                // partial sums of all parts are visible
-#pragma unroll
-      for (int q = 1; q < NQ; ++q) sum += sSum[((hf + q) % NQ) * 128 + r];
-      // O / rowsum leaves as one [128 x 64] bf16 tile: staged in slab 0 of the P buffer (dead once PV has
-      // completed) and written by a TMA store whose tensor map clips the rows of the tile that lie beyond S
-      const int row = i * 128 + r;
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int j = 0; j < OC; j += 8) {
-        st_shared_v4(sp_row + ((((OC / 8) * hf + (j >> 3)) ^ r7) << 4),
-                     pack_bf16x2(__uint_as_float(o0[j]) * inv, __uint_as_float(o0[j + 1]) * inv),
-                     pack_bf16x2(__uint_as_float(o0[j + 2]) * inv, __uint_as_float(o0[j + 3]) * inv),
-                     pack_bf16x2(__uint_as_float(o0[j + 4]) * inv, __uint_as_float(o0[j + 5]) * inv),
-                     pack_bf16x2(__uint_as_float(o0[j + 6]) * inv, __uint_as_float(o0[j + 7]) * inv));
-      }
-      fence_proxy_async();
-      bar_softmax_n<SMT>();
-      if (tid == 0) {
-        tma_store_3d(&tmo, sP, h * AT_DH, i * 128, sample);
-        bulk_commit();
-      }
-      if (row < S && p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
-      TL(9, i);
+      // the epilogue of the PREVIOUS tile runs here, behind this tile's softmax: its P V finished long ago, and this
+      // tile's P V (and the next tile's Q K^T) proceed meanwhile
+      if (i > 0) epilogue(i - 1, ms_prev);
+      ms_prev = ms;
     }
+    epilogue(nqt - 1, ms_prev);
     if (tid == 0) bulk_wait_read<0>();
   } else if (!TWO && p.ntail > 0) {
     // ------------------------------------------------------------------ query tail on CUDA cores (warps 0, 2, 3;
@@ -1068,7 +1078,7 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     p.S = S; p.SP = (p.S + 15) & ~15; p.H = a.H;
     split_tail(S, tail_limit(false), &p.nqt, &p.ntail);
     p.o_col = (p.SP + 31) & ~31;
-    p.tmem_cols = (p.o_col + 64 <= 256) ? 256 : 512;
+    p.tmem_cols = (p.o_col + 128 <= 256) ? 256 : 512;   // scores + two output accumulators
     p.scale_log2 = a.scale * LOG2E;
     p.tl = g_attn_timeline;
     { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
@@ -1076,7 +1086,7 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
     const int nslab = (p.SP + 63) / 64;
     const int qrows = p.nqt * 128 > p.SP ? p.nqt * 128 : p.SP;
-    int smem = (qrows + 2 * p.SP) * AT_ROW + nslab * AT_SLAB + 4096 /*row stats*/ + (AT_MAX_S + 208) * 4 /*tail scratch*/ + 256 + 1024;
+    int smem = (qrows + 2 * p.SP) * AT_ROW + (nslab + 1) * AT_SLAB /*P + output staging*/ + 6144 /*row stats*/ + (AT_MAX_S + 208) * 4 /*tail scratch*/ + 256 + 1024;
     // a CTA that allocates 256 TMEM columns may share its SM with exactly one other
     if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
     if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;
