@@ -171,31 +171,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer: runs BEFORE the set-up barrier
+    // (it owns the two load barriers), so the loads are in flight while TMEM is allocated and the CTA synchronises.
+    // Two completion groups so that Q_0 K^T can start once half of the bytes are in.
     tma_prefetch_desc(&tm128);
     tma_prefetch_desc(&tm16);
     tma_prefetch_desc(&tmo);
-  }
-  if (warp == 1 && lane == 0) {
     mbar_init(bar_k, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(&bar_o[0], 1);
-    mbar_init(&bar_o[1], 1);
-    mbar_init(bar_p, SMT);
     fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    // two completion groups so that Q_0 K^T can start once half of the bytes are in
     const int q0rows = min(128, SP);
     mbar_expect_tx(bar_k, static_cast<uint32_t>(SP + q0rows) * AT_ROW);
     load_rows_from(sK, &tm128, &tm16, bar_k, D + h * AT_DH, sample, 0, SP);
@@ -211,6 +195,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       prefetch_rows(&tm128, &tm16, 2 * D + h2 * AT_DH, s2, SP);
     }
   }
+  if (warp == 1 && lane == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(&bar_o[0], 1);
+    mbar_init(&bar_o[1], 1);
+    mbar_init(bar_p, SMT);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
   if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged; the tcgen05
     // instructions themselves run under elect.sync so that descriptors stay in uniform registers)
@@ -565,6 +565,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer: before the set-up barrier (it owns
+    // the two load barriers), so the loads are in flight while TMEM is allocated and the CTA synchronises
     tma_prefetch_desc(&tq128);
     tma_prefetch_desc(&tq16);
     tma_prefetch_desc(&td128);
@@ -572,32 +574,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     tma_prefetch_desc(&tmdq);
     tma_prefetch_desc(&to128);
     tma_prefetch_desc(&to16);
-  }
-  if (warp == 1 && lane == 0) {
     mbar_init(bar_ld, 1);
     mbar_init(bar_ld0, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_sfree[i], AT_BWD_SM);
-      mbar_init(&bar_p[i], AT_BWD_SM);
-    }
-    mbar_init(bar_tfree, 1);
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_accfree, AT_BWD_SM);
     fence_barrier_init();
-  }
-  if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t col_dv = nbuf * 128, col_dk = col_dv + 64, col_dq = col_dv + 128;
-
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer
     // O (for delta) and this sample's [S][H] block of log-sum-exps are parked in the P^T / dS^T tile region,
     // which has no other use until the first score tile has been processed
     const uint32_t lse_bytes = p.lse_bulk ? static_cast<uint32_t>(S) * p.H * 4u : 0u;
@@ -619,6 +598,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       prefetch_rows(&to128, &to16, h2 * AT_DH, s2, SP);
     }
   }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_s[i], 1);
+      mbar_init(&bar_sfree[i], AT_BWD_SM);
+      mbar_init(&bar_p[i], AT_BWD_SM);
+    }
+    mbar_init(bar_tfree, 1);
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_accfree, AT_BWD_SM);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t col_dv = nbuf * 128, col_dk = col_dv + 64, col_dq = col_dv + 128;
+
   if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-converged, see forward)
     constexpr uint32_t idesc_kt = make_idesc_bf16(128, 64, false, true);   // A K-major (P^T / dS^T), B MN-major (dO / Q)
