@@ -92,7 +92,8 @@ struct FwdParams {
   int nqt;       // 128-query tiles that run on the tensor cores
   int ntail;     // trailing query rows (S = 128 nqt + ntail, ntail <= AT_TAIL) computed on the idle control warps
   int o_col, tmem_cols;
-  int ahead;     // CTAs resident on the device at once: the L2 prefetch distance
+  int ahead;     // L2 prefetch of this CTA's next item on / off
+  int nitems;    // (sample, head) pairs of the segment
   float scale_log2;
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py)
@@ -143,11 +144,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
                    const __grid_constant__ CUtensorMap tmo, const FwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Persistent: the CTA walks over (sample, head) items blockIdx.x, blockIdx.x + gridDim.x, ...  TMEM, barriers and
+  // roles are set up once; barrier phases run on (k = item count of this CTA, g = k * nqt + tile).  A CTA per item
+  // paid ~2 us of launch, set-up and tear-down for every ~8 us of work.
   const int S = p.S, SP = p.SP, nqt = p.nqt;
   const int D = p.H * AT_DH;
-  const int h = blockIdx.x % p.H;
-  const int sample = blockIdx.x / p.H;   // within the segment
-  const int row0 = p.row_base + sample * S;
   const int nslab = (SP + 63) >> 6;
   const int qrows = max(nqt * 128, SP);
   uint8_t* sQ = smem;                      // qrows rows (rows >= SP stay unwritten: they only feed unused lanes)
@@ -166,20 +167,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
   uint64_t* bar_v = bars + 1;    // V and the remaining query rows have landed
   uint64_t* bar_s = bars + 2;    // scores of the current tile are in TMEM
   uint64_t* bar_p = bars + 3;    // P of the current tile is in shared memory (and S has been read)
-  uint64_t* bar_o = bars + 4;    // [2] P V of tile i is in TMEM accumulator i & 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_o = bars + 4;    // [2] P V of tile g is in TMEM accumulator g & 1
+  uint64_t* bar_free = bars + 6; // every MMA of the item has completed: Q, K, V may be overwritten (once per item)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer: runs BEFORE the set-up barrier
-    // (it owns the two load barriers), so the loads are in flight while TMEM is allocated and the CTA synchronises.
-    // Two completion groups so that Q_0 K^T can start once half of the bytes are in.
-    tma_prefetch_desc(&tm128);
-    tma_prefetch_desc(&tm16);
-    tma_prefetch_desc(&tmo);
-    mbar_init(bar_k, 1);
-    mbar_init(bar_v, 1);
-    fence_barrier_init();
+  // loads of one item: two completion groups so that Q_0 K^T can start once half of the bytes are in; then an L2
+  // prefetch of the item this CTA takes next
+  auto issue_loads = [&](int item) {
+    const int h = item % p.H, sample = item / p.H;
     const int q0rows = min(128, SP);
     mbar_expect_tx(bar_k, static_cast<uint32_t>(SP + q0rows) * AT_ROW);
     load_rows_from(sK, &tm128, &tm16, bar_k, D + h * AT_DH, sample, 0, SP);
@@ -187,18 +183,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     mbar_expect_tx(bar_v, static_cast<uint32_t>(2 * SP - q0rows) * AT_ROW);
     load_rows_from(sV, &tm128, &tm16, bar_v, 2 * D + h * AT_DH, sample, 0, SP);
     if (SP > q0rows) load_rows_from(sQ, &tm128, &tm16, bar_v, h * AT_DH, sample, 128, SP);
-    const int nxt = blockIdx.x + p.ahead;
-    if (p.ahead > 0 && nxt < static_cast<int>(gridDim.x)) {
+    const int nxt = item + static_cast<int>(gridDim.x);
+    if (p.ahead > 0 && nxt < p.nitems) {
       const int h2 = nxt % p.H, s2 = nxt / p.H;
       prefetch_rows(&tm128, &tm16, D + h2 * AT_DH, s2, SP);
       prefetch_rows(&tm128, &tm16, h2 * AT_DH, s2, SP);
       prefetch_rows(&tm128, &tm16, 2 * D + h2 * AT_DH, s2, SP);
     }
+  };
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer: the first item's loads go out
+    // BEFORE the set-up barrier (this thread owns the two load barriers), so they are in flight while TMEM is
+    // allocated and the CTA synchronises
+    tma_prefetch_desc(&tm128);
+    tma_prefetch_desc(&tm16);
+    tma_prefetch_desc(&tmo);
+    mbar_init(bar_k, 1);
+    mbar_init(bar_v, 1);
+    fence_barrier_init();
+    issue_loads(blockIdx.x);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(bar_s, 1);
     mbar_init(&bar_o[0], 1);
     mbar_init(&bar_o[1], 1);
+    mbar_init(bar_free, 1);
     mbar_init(bar_p, SMT);
     fence_barrier_init();
   }
@@ -218,10 +227,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 8192, 1024);
     const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP), 0, 1024);
     const int ksteps = SP >> 4;
-    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && lane == 0;
-    mbar_wait(bar_k, 0);
-    tc_fence_after();
-    TL(0, 0);
+    bool tl_on = false;
     // S = Q_i K^T for query tile i (two column chunks when SP > 256).  (Descriptors of the two score chunks are
     // rebuilt per tile: a hoisted form of this short sequence produced wrong columns >= 256 on hardware.)
     auto issue_qk = [&](int i) {
@@ -238,16 +244,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       }
       __syncwarp();
     };
+    int k = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++k) {
+    tl_on = p.tl != nullptr && item == p.tl_cta && lane == 0;
+    // (the S columns are free: this warp waited for bar_p of the previous item's last tile before its P V)
+    mbar_wait(bar_k, k & 1);
+    tc_fence_after();
+    TL(0, 0);
     TL(1, 0);
     issue_qk(0);
     TL(2, 0);
-    mbar_wait(bar_v, 0);
+    mbar_wait(bar_v, k & 1);
     tc_fence_after();
     for (int i = 0; i < nqt; ++i) {
+      const int g = k * nqt + i;
       // bar_p(i): every softmax thread has finished reading S(i) and writing P(i).  The next tile's scores go first
       // (the softmax warps start on them while P V runs); O_i goes to accumulator i & 1, whose previous content
       // (O_{i-2}) was read by the epilogue that precedes the arrival on bar_p(i-1) in program order.
-      mbar_wait(bar_p, i & 1);
+      mbar_wait(bar_p, g & 1);
       tc_fence_after();
       TL(3, i);
       if (i + 1 < nqt) {
@@ -255,7 +269,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         issue_qk(i + 1);
         TL(2, i + 1);
       }
-      const uint32_t o_acc = tmem_base + p.o_col + 64 * (i & 1);
+      const uint32_t o_acc = tmem_base + p.o_col + 64 * (g & 1);
       if (elect_one()) {
         uint64_t pa = p_desc, vb = v_desc;
         int kk = 0;
@@ -269,10 +283,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         }
         for (int k = 0; kk < ksteps; ++kk, ++k)
           umma_f16_ss(o_acc, pa + 2 * k, vb + static_cast<uint64_t>(k * (16 * AT_ROW / 16)), idesc_pv, kk > 0 ? 1u : 0u);
-        umma_commit(&bar_o[i & 1]);
+        umma_commit(&bar_o[g & 1]);
+        if (i == nqt - 1) umma_commit(bar_free);
       }
       __syncwarp();
     }
+    }  // items
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax + epilogue
     const int quad = warp & 3;
@@ -286,29 +302,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
     const int units = SP >> 4, ubase = units / NQ, urem = units % NQ;
     const int cb = 16 * (hf * ubase + min(hf, urem)), ce = cb + 16 * (ubase + (hf < urem ? 1 : 0));
     const int tid = threadIdx.x - 128;
-    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
-    TL(4, 0);
+    bool tl_on = false;
     const uint32_t stage_row = smem_u32(sStage) + r * AT_ROW;
-    // epilogue of tile i: O_i / rowsum -> bf16 -> staging tile -> TMA store (clipped at S), log-sum-exp
-    auto epilogue = [&](int i, float ms) {
+    int h = 0, sample = 0, row0 = 0, k = 0;
+    // epilogue of tile i (global tile number g): O / rowsum -> bf16 -> staging tile -> TMA store (clipped at S), lse
+    auto epilogue = [&](int i, int g, float ms) {
       constexpr int OC = 64 / NQ;          // output columns per part
       if (tid == 0) bulk_wait_read<0>();   // the previous store has finished reading the staging tile
-      mbar_wait(&bar_o[i & 1], (i >> 1) & 1);
+      mbar_wait(&bar_o[g & 1], (g >> 1) & 1);
       tc_fence_after();
       TL(8, i);
       uint32_t o0[OC];
       if constexpr (OC == 32) {
-        tmem_ld_32x32(t_lane + p.o_col + 64 * (i & 1) + OC * hf, o0);
+        tmem_ld_32x32(t_lane + p.o_col + 64 * (g & 1) + OC * hf, o0);
         tmem_ld_wait_dep32(o0);
       } else {
-        tmem_ld_32x16(t_lane + p.o_col + 64 * (i & 1) + OC * hf, o0);
+        tmem_ld_32x16(t_lane + p.o_col + 64 * (g & 1) + OC * hf, o0);
         tmem_ld_wait_dep16(o0);
       }
       tc_fence_before();
       bar_softmax_n<SMT>();                // partial sums of all parts are visible; staging tile is free
       float sum = 0.f;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) sum += sSum[(i & 1) * 512 + q * 128 + r];
+      for (int q = 0; q < NQ; ++q) sum += sSum[(g & 1) * 512 + q * 128 + r];
       const int row = i * 128 + r;
       const float inv = 1.f / sum;
 #pragma unroll
@@ -328,9 +344,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       if (row < S && p.lse && hf == 0) p.lse[static_cast<long long>(row0 + row) * p.H + h] = (ms + log2f(sum)) * LN2;
       TL(9, i);
     };
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++k) {
+    h = item % p.H;
+    sample = item / p.H;
+    row0 = p.row_base + sample * S;
+    tl_on = p.tl != nullptr && item == p.tl_cta && tid == 0;
+    TL(4, 0);
     float ms_prev = 0.f;
     for (int i = 0; i < nqt; ++i) {
-      mbar_wait(bar_s, i & 1);
+      const int g = k * nqt + i;
+      mbar_wait(bar_s, g & 1);
       tc_fence_after();
       TL(5, i);
       // pass 1: maximum of the raw logits over this thread's columns (32 at a time; a 16-column remainder last)
@@ -357,7 +380,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       const float ms = m * sl2;
       // P V of the previous tile reads the P slabs that pass 2 is about to overwrite (its Q K^T successor was issued
       // ahead of it, so S(i) can be ready before P V(i-1) has finished): wait for its completion first
-      if (i > 0) mbar_wait(&bar_o[(i - 1) & 1], ((i - 1) >> 1) & 1);
+      if (i > 0) mbar_wait(&bar_o[(g - 1) & 1], ((g - 1) >> 1) & 1);
       // pass 2: p = exp2(s * scale*log2e - max), partial row sum, bf16 P -> shared memory
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
@@ -376,28 +399,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_p);
-      sSum[(i & 1) * 512 + hf * 128 + r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      sSum[(g & 1) * 512 + hf * 128 + r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       TL(7, i);
       // the epilogue of the PREVIOUS tile runs here, behind this tile's softmax: its P V finished long ago, and this
       // tile's P V (and the next tile's Q K^T) proceed meanwhile
-      if (i > 0) epilogue(i - 1, ms_prev);
+      if (i > 0) epilogue(i - 1, g - 1, ms_prev);
       ms_prev = ms;
     }
-    epilogue(nqt - 1, ms_prev);
+    // last tile of the item: straight away (the next item's loads are only just being issued)
+    epilogue(nqt - 1, k * nqt + nqt - 1, ms_prev);
+    }  // items
     if (tid == 0) bulk_wait_read<0>();
-  } else if (!TWO && p.ntail > 0) {
-    // ------------------------------------------------------------------ query tail on CUDA cores (warps 0, 2, 3;
-    // compiled only into the one-CTA-per-SM variant: the launcher sends every shape with a tail there)
+  } else {
+    // ------------------------------------------------------------------ warps 0, 2, 3: the producer thread issues the
+    // loads of the following items; with a query tail (one-CTA-per-SM variant only: the launcher sends every shape with
+    // a tail there) all 96 threads compute the tail rows on CUDA cores.
     // S = 128 nqt + ntail with ntail <= AT_TAIL (every decoder of the reference has 257 tokens, the label-conditioned
     // encoder 260): a third query tile would run the whole softmax for one to four live rows.  The idle control
     // warps compute those rows from the K / V / Q tiles already in shared memory instead.
-    __syncwarp();
     const int tt = (warp == 0 ? 0 : warp - 1) * 32 + lane;   // 0..95
     const int tw = tt >> 5;
     const float sl2 = p.scale_log2;
     const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV);
-    mbar_wait(bar_k, 0);
-    mbar_wait(bar_v, 0);
+    const int ntail = TWO ? 0 : p.ntail;
+    int k = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++k) {
+    if (warp == 0 && lane == 0 && k > 0) {
+      // Q, K, V of the previous item are dead once the P V of its last tile has completed (the tail threads passed
+      // their last named barrier of that item before this point).  A barrier of its own, completed once per item:
+      // waiting on bar_o's parity from here could alias with an earlier phase.
+      mbar_wait(bar_free, (k - 1) & 1);
+      issue_loads(item);
+    }
+    __syncwarp();
+    if (ntail == 0) continue;
+    const int h = item % p.H, sample = item / p.H;
+    const int row0 = p.row_base + sample * S;
+    mbar_wait(bar_k, k & 1);
+    mbar_wait(bar_v, k & 1);
     for (int t = 0; t < p.ntail; ++t) {
       const int qrow = nqt * 128 + t;
       // scores of query qrow against every key: one key per thread, 64-long dot product on packed bf16 pairs
@@ -452,8 +491,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm128, const __grid_const
         *reinterpret_cast<uint32_t*>(p.out + static_cast<long long>(row0 + qrow) * D + h * AT_DH + 2 * lane) = pack_bf16x2(o0, o1);
         if (lane == 0 && p.lse) p.lse[static_cast<long long>(row0 + qrow) * p.H + h] = (mx + log2f(sum)) * LN2;
       }
-      bar_sync_named(2, AT_TAIL_THREADS);   // scratch is reused by the next tail row
+      bar_sync_named(2, AT_TAIL_THREADS);   // scratch is reused by the next tail row (and K / V / Q by the next item)
     }
+    }  // items
   }
 
   __syncwarp();
@@ -1091,11 +1131,14 @@ int attention_fwd_tc(const AttnArgs& a, cudaStream_t st) {
     if (p.tmem_cols == 256 && smem < 80 * 1024) smem = 80 * 1024;
     if (p.tmem_cols == 512 && smem < 120 * 1024) smem = 120 * 1024;
     const bool two = p.tmem_cols == 256 && smem <= 113 * 1024 && p.ntail == 0;
-    p.ahead = pf ? sm_count() * (two ? 2 : 1) : 0;
+    p.ahead = pf;
+    p.nitems = n * a.H;
+    const int resident = sm_count() * (two ? 2 : 1);
+    const int grid = p.nitems < resident ? p.nitems : resident;
     if (two)
-      attn_fwd_tc_kernel<true><<<n * a.H, 384, smem, st>>>(tm128, tm16, tmo, p);
+      attn_fwd_tc_kernel<true><<<grid, 384, smem, st>>>(tm128, tm16, tmo, p);
     else
-      attn_fwd_tc_kernel<false><<<n * a.H, 640, smem, st>>>(tm128, tm16, tmo, p);
+      attn_fwd_tc_kernel<false><<<grid, 640, smem, st>>>(tm128, tm16, tmo, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }

@@ -297,6 +297,49 @@ def test_attention_tail_rows_on_control_warps(n0, s0, n1, s1, H):
     L.umd_debug_attn_tail_limits(-1, -1)
 
 
+@pytest.mark.parametrize("n0,s0,n1,s1,H", [(40, 257, 64, 68, 12), (30, 260, 0, 0, 12), (28, 164, 0, 0, 12), (0, 0, 52, 129, 6)])
+def test_attention_persistent_ctas_walk_over_many_items(n0, s0, n1, s1, H):
+  """More (sample, head) items than resident CTAs (148, or 296 for the two-CTA-per-SM variant): every CTA of the
+  forward kernel processes several items back to back (barrier phases, TMEM accumulators and shared-memory tiles are
+  reused across items); one- and three-tile shapes, with and without a tail row.  Backward on the same inputs."""
+  lib = _lib()
+  L = lib.load()
+  Dh, D = 64, H * 64
+  rows = n0 * s0 + n1 * s1
+  g = torch.Generator().manual_seed(rows)
+  qkv = (torch.randn(rows, 3 * D, generator=g) * 1.2).to(torch.bfloat16)
+  dout = torch.randn(rows, D, generator=g).to(torch.bfloat16)
+  ref_in = qkv.float().requires_grad_(True)
+  ref = _attn_ref(ref_in, n0, s0, n1, s1, H, Dh)
+  ref.backward(dout.float())
+  qg, dg = qkv.to(DEV), dout.to(DEV)
+  out = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+  lse = torch.empty(rows, H, device=DEV)
+  for _ in range(2):   # twice: the second call starts from warm caches and a different CTA / item timing
+    out.zero_()
+    lib.check(L.umd_attention_fwd(lib.ptr(qg), lib.ptr(out), lib.ptr(lse), n0, s0, n1, s1, H, Dh, lib.current_stream()), "attn fwd")
+    torch.cuda.synchronize()
+    assert U.rel_l2(out.float().cpu(), ref.detach()) < 1e-2
+    assert torch.allclose(out.float().cpu(), ref.detach(), rtol=2 ** -6, atol=2e-2)
+  # lse against the reference's log-sum-exp of the scaled logits
+  r = 0
+  for n, s in ((n0, s0), (n1, s1)):
+    if n == 0:
+      continue
+    blk = qkv.float()[r:r + n * s].reshape(n, s, 3, H, Dh)
+    logits = torch.einsum("bqhd,bkhd->bqhk", blk[:, :, 0] / math.sqrt(Dh), blk[:, :, 1])
+    want = torch.logsumexp(logits, -1).reshape(n * s, H)
+    assert torch.allclose(lse.cpu()[r:r + n * s], want, rtol=1e-3, atol=2e-2)
+    r += n * s
+  dqkv = torch.zeros(rows, 3 * D, device=DEV, dtype=torch.bfloat16)
+  lib.check(L.umd_attention_bwd(lib.ptr(qg), lib.ptr(out), lib.ptr(dg), lib.ptr(lse), lib.ptr(dqkv), n0, s0, n1, s1, H, Dh,
+                                lib.current_stream()), "attn bwd")
+  torch.cuda.synchronize()
+  for j, name in enumerate("qkv"):
+    rr = U.rel_l2(dqkv.float().cpu()[:, j * D:(j + 1) * D], ref_in.grad[:, j * D:(j + 1) * D])
+    assert rr < 2e-2, f"d{name} rel-L2 {rr}"
+
+
 # ------------------------------------------------------------------------------------------ optimiser
 @pytest.mark.parametrize("count,clip_active,ema", [(0, True, False), (5, False, True), (200, True, True)])
 def test_adamw_step_matches_oracle(count, clip_active, ema):
