@@ -54,6 +54,14 @@ def test_full_size_gradient_is_mean_of_shard_gradients():
 
 
 def test_full_size_step_is_repeatable():
+  """Same inputs, same loss bit for bit; gradients up to the order of fp32 atomic adds.  Two regimes, measured with
+  tools/repeat_check.py (per-leaf deltas over repeated steps):
+    * leaves of the main stream (blocks, embeddings, final layers): split-K and column-sum atomics only reorder fp32
+      additions -> ~1e-7 relative;
+    * the conditioning trunks (time / label Dense layers, label table): their input gradient dcond is the sum of the
+      adaLN gradients that the LayerNorm-backward CTAs of one sample add atomically, and is then cast to bf16 for the
+      trunk's GEMMs -> an order-dependent last bit occasionally flips a bf16 rounding, which shows as discrete
+      ~5e-5 changes in those leaves (1e-6 .. 2e-5 of the whole arena)."""
   from small_vision_b200.config import TrainConfig
   from small_vision_b200.params import tree_from_arena
   model, _ = U.make_models("B/4", adaln=True)
@@ -63,6 +71,16 @@ def test_full_size_step_is_repeatable():
   g1, l1 = _grads(model, tcfg, tree_from_arena(model.layout, params.arena.clone()), batch, rand)
   g2, l2 = _grads(model, tcfg, tree_from_arena(model.layout, params.arena.clone()), batch, rand)
   assert l1 == l2
-  rel = float((g1 - g2).double().norm() / g1.double().norm())
-  assert rel <= 1e-5, rel          # split-K and column sums use fp32 atomics: order-dependent in the last bits
   assert torch.isfinite(g1).all()
+  cond_leaf = lambda path: path[0] in ("time_trunk", "label_trunk", "label_emb")
+  main_d2 = main_n2 = 0.0
+  for lf in model.layout.leaves:
+    a, b = g1[lf.offset:lf.offset + lf.size].double(), g2[lf.offset:lf.offset + lf.size].double()
+    if cond_leaf(lf.path):
+      rel = float((a - b).norm() / (a.norm() + 1e-30))
+      assert rel <= 5e-4, ("/".join(lf.path), rel)
+    else:
+      main_d2 += float((a - b).pow(2).sum())
+      main_n2 += float(a.pow(2).sum())
+  rel_main = (main_d2 / main_n2) ** 0.5
+  assert rel_main <= 2e-6, rel_main
