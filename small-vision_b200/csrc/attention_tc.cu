@@ -553,7 +553,8 @@ struct BwdParams {
   int nbuf;  // TMEM score buffers (2 when nt <= 2)
   int prefetch;  // issue the next block's scores ahead of this block's accumulation (needs nbuf == 2)
   int lse_bulk;  // the sample's [S][H] lse block is 16-byte aligned: fetch it with one bulk copy
-  int ahead;     // L2 prefetch distance in CTAs (0 = off)
+  int ahead;     // L2 prefetch of this CTA's next item on / off
+  int nitems;    // (sample, head) pairs of the segment
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py): CTA 0 records clock64() at its sync points
   float scale, scale_log2;
@@ -566,11 +567,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
                    const __grid_constant__ CUtensorMap to16, const BwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // Persistent like the forward: the CTA walks over (sample, head) items blockIdx.x, blockIdx.x + gridDim.x, ...;
+  // step / block / key-tile counters run on across items so that every barrier keeps its phase sequence.
   const int S = p.S, SP = p.SP, nt = p.nt, nbuf = p.nbuf;
   const int D = p.H * AT_DH;
-  const int h = blockIdx.x % p.H;
-  const int sample = blockIdx.x / p.H;   // within the segment
-  const int row0 = p.row_base + sample * S;
   // K and V are also read as 128-row A operands: the reads past row SP of K land in V, those of V in the
   // P^T tile — allocated memory whose content only reaches TMEM lanes that are masked below.
   uint8_t* sQ = smem;
@@ -586,6 +586,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + 2 * AT_SLAB);
   uint64_t* bar_ld = bars + 0;      // Q, K, V have landed (the last of the two load groups)
   uint64_t* bar_ld0 = bars + 11;    // dO, O and the lse block have landed: delta can be formed while Q, K, V stream in
+  uint64_t* bar_done = bars + 12;   // the softmax warps have finished the item (its operands, tiles and accumulators are free)
   uint64_t* bar_s = bars + 1;       // [2]
   uint64_t* bar_sfree = bars + 3;   // [2]
   uint64_t* bar_p = bars + 5;       // [2] one per 64-query half
@@ -604,19 +605,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   const int SPm = p.ntail > 0 ? M0 : SP;         // ... padded extent of that part
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------------------------------ TMA producer: before the set-up barrier (it owns
-    // the two load barriers), so the loads are in flight while TMEM is allocated and the CTA synchronises
-    tma_prefetch_desc(&tq128);
-    tma_prefetch_desc(&tq16);
-    tma_prefetch_desc(&td128);
-    tma_prefetch_desc(&td16);
-    tma_prefetch_desc(&tmdq);
-    tma_prefetch_desc(&to128);
-    tma_prefetch_desc(&to16);
-    mbar_init(bar_ld, 1);
-    mbar_init(bar_ld0, 1);
-    fence_barrier_init();
+  auto issue_loads = [&](int item) {
+    const int h = item % p.H, sample = item / p.H;
+    const int row0 = p.row_base + sample * S;
     // O (for delta) and this sample's [S][H] block of log-sum-exps are parked in the P^T / dS^T tile region,
     // which has no other use until the first score tile has been processed
     const uint32_t lse_bytes = p.lse_bulk ? static_cast<uint32_t>(S) * p.H * 4u : 0u;
@@ -628,8 +619,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     load_rows(sK, &tq128, &tq16, bar_ld, D + h * AT_DH, sample, SP);
     load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, sample, SP);
     load_rows(sV, &tq128, &tq16, bar_ld, 2 * D + h * AT_DH, sample, SP);
-    const int nxt = blockIdx.x + p.ahead;
-    if (p.ahead > 0 && nxt < static_cast<int>(gridDim.x)) {
+    const int nxt = item + static_cast<int>(gridDim.x);
+    if (p.ahead > 0 && nxt < p.nitems) {
       const int h2 = nxt % p.H, s2 = nxt / p.H;
       prefetch_rows(&tq128, &tq16, D + h2 * AT_DH, s2, SP);
       prefetch_rows(&tq128, &tq16, h2 * AT_DH, s2, SP);
@@ -637,6 +628,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       prefetch_rows(&td128, &td16, h2 * AT_DH, s2, SP);
       prefetch_rows(&to128, &to16, h2 * AT_DH, s2, SP);
     }
+  };
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer: the first item's loads go out before
+    // the set-up barrier (this thread owns the two load barriers), in flight while TMEM is allocated
+    tma_prefetch_desc(&tq128);
+    tma_prefetch_desc(&tq16);
+    tma_prefetch_desc(&td128);
+    tma_prefetch_desc(&td16);
+    tma_prefetch_desc(&tmdq);
+    tma_prefetch_desc(&to128);
+    tma_prefetch_desc(&to16);
+    mbar_init(bar_ld, 1);
+    mbar_init(bar_ld0, 1);
+    fence_barrier_init();
+    issue_loads(blockIdx.x);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -647,6 +653,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     mbar_init(bar_tfree, 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_accfree, AT_BWD_SM);
+    mbar_init(bar_done, AT_BWD_SM);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -675,12 +682,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const uint64_t pt_k = make_smem_desc_sw128(smem_u32(sPt), 0, 1024);    // P^T  as K-major A
     const uint64_t st_k = make_smem_desc_sw128(smem_u32(sdSt), 0, 1024);   // dS^T as K-major A
     const uint64_t st_mn = make_smem_desc_sw128(smem_u32(sdSt), AT_SLAB, 1024);  // dS^T tile as MN-major A (= dS)
-    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && lane == 0;
-    mbar_wait(bar_ld0, 0);
-    mbar_wait(bar_ld, 0);
+    bool tl_on = false;
+    int step = 0;          // score steps issued so far, over all items
+    int jj = 0;            // key tiles finished so far, over all items
+    uint32_t cnt_p[2] = {0, 0};
+    int kit = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++kit) {
+    mbar_wait(bar_ld0, kit & 1);
+    mbar_wait(bar_ld, kit & 1);
+    // the previous item's dQ epilogue has read its TMEM accumulators (and every other consumer is done)
+    if (kit > 0) mbar_wait(bar_done, (kit - 1) & 1);
     tc_fence_after();
     TL(0, 0);
-    int step = 0;
     // S^T = K_j Q_i^T and dP^T = V_j dO_i^T for 64-query half hh of block n = (j, i).  Steps are issued in order.
     auto halves_of = [&](int n) { return (min(128, SPm - 128 * (n % nt)) + 63) >> 6; };
     auto issue_step = [&](int n, int hh) {
@@ -708,7 +721,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       TL(1, step);
     };
     const int nblk = nt * nt;
-    uint32_t cnt_p[2] = {0, 0};
+    tl_on = p.tl != nullptr && item == p.tl_cta && lane == 0;
     for (int hh = 0; hh < halves_of(0); ++hh) issue_step(0, hh);
     for (int n = 0; n < nblk; ++n) {
       const int j = n / nt, i = n - j * nt;
@@ -729,8 +742,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       }
       tc_fence_after();
       TL(2, n);
-      if (i == 0 && j > 0) {
-        mbar_wait(bar_accfree, (j - 1) & 1);
+      if (i == 0 && jj > 0) {   // dV / dK accumulators: the previous key tile's epilogue (of this or the last item) has read them
+        mbar_wait(bar_accfree, (jj - 1) & 1);
         tc_fence_after();
       }
       const int kq = nq >> 4, kkv = nkv >> 4;
@@ -759,19 +772,29 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       umma_commit(bar_tfree);
       if (i == nt - 1) umma_commit(bar_acc);
       }
+      if (i == nt - 1) ++jj;
       __syncwarp();
       TL(3, n);
       if (n + 1 < nblk)
         for (int hh = ahead; hh < halves_of(n + 1); ++hh) issue_step(n + 1, hh);
     }
+    }  // items
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax backward + epilogues
     const int quad = warp & 3;
     const int hf = (warp - 4) >> 2;  // which 16 of the 64 columns of a score half / of an output tile (0..3)
     const int r = quad * 32 + lane;  // key row inside the key tile (TMEM lane); query row in the dQ epilogue
     const int tid = threadIdx.x - 128;
-    const bool tl_on = p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && tid == 0;
+    bool tl_on = false;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const float sl2 = p.scale_log2;
+    const int r7 = r & 7;
+    const uint32_t pt_row = smem_u32(sPt) + r * AT_ROW, st_row = smem_u32(sdSt) + r * AT_ROW;
+    int step = 0, blk = 0, jj = 0, kit = 0;   // counters over all items of this CTA (barrier phases)
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++kit) {
+    const int h = item % p.H, sample = item / p.H;
+    const int row0 = p.row_base + sample * S;
+    tl_on = p.tl != nullptr && item == p.tl_cta && tid == 0;
     TL(4, 0);
     // delta = rowsum(dO * O) and lse in log2 units, both from shared memory, one query row per thread (the
     // 128B swizzle makes the row-per-lane reads conflict-free); the region O and the lse block are read from
@@ -781,7 +804,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       float lse_direct = 0.f;
       if (!p.lse_bulk && tid < S) lse_direct = p.lse[static_cast<long long>(row0 + tid) * p.H + h];
       TL(4, 2);
-      mbar_wait(bar_ld0, 0);
+      mbar_wait(bar_ld0, kit & 1);
       TL(4, 3);
       const int q = tid;   // AT_BWD_SM >= AT_MAX_S: one query row per thread
       if (q < SP) {
@@ -804,12 +827,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     bar_softmax_n<AT_BWD_SM>();
     if (p.ntail > 0) bar_arrive_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta are complete
     TL(4, 1);
-    const float sl2 = p.scale_log2;
-    const int r7 = r & 7;
-    const uint32_t pt_row = smem_u32(sPt) + r * AT_ROW, st_row = smem_u32(sdSt) + r * AT_ROW;
-    int step = 0, blk = 0;
     bool store_pending = false;
-    for (int j = 0; j < nt; ++j) {
+    for (int j = 0; j < nt; ++j, ++jj) {
       for (int i = 0; i < nt; ++i) {
         const int nq = min(128, SPm - 128 * i);
         const int nh = (nq + 63) >> 6;
@@ -865,7 +884,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       }
       // dK_j, dV_j: each half owns 32 of the 64 head-dim columns.  The two [128 x 64] bf16 tiles are staged in the
       // P^T tile (dead: bar_acc covers every MMA issued so far) and leave by TMA stores that clip rows >= S.
-      mbar_wait(bar_acc, j & 1);
+      mbar_wait(bar_acc, jj & 1);
       tc_fence_after();
       TL(9, j);
       {
@@ -948,20 +967,37 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       bulk_commit();
       bulk_wait_read<0>();
     }
-  } else if (p.ntail > 0) {
-    // ------------------------------------------------------------------ tail rows on CUDA cores (warps 0, 2, 3)
+    // item finished: the staging tiles have been read by the stores, the accumulators by the epilogues, the operand
+    // tiles by everybody -> the producer may load the next item, the MMA warp may overwrite TMEM
+    tc_fence_before();
+    bar_softmax_n<AT_BWD_SM>();
+    mbar_arrive(bar_done);
+    }  // items
+  } else {
+    // ------------------------------------------------------------------ warps 0, 2, 3: the producer thread loads the
+    // following items; with a tail all 96 threads compute the tail rows on CUDA cores.
     // S = 128 nt + ntail (257-token decoders, the 260-token label-conditioned encoder): a third tile per dimension
     // would cost five more (j, i) blocks and the second TMEM score buffer.  For tail key t (row M0 + t) and every
     // query x:  P = exp2(q_x k_t sl2 - lse_x),  dS = P (dO_x v_t - delta_x);  for tail query t and every key x < M0:
     // P = exp2(q_t k_x sl2 - lse_t),  dS = P (dO_t v_x - delta_t).  The rows' own outputs are reduced here; what they
     // add to the rows of the main tiles is applied by the softmax warps in the dK / dV / dQ epilogues.
-    __syncwarp();
     const int tt = (warp == 0 ? 0 : warp - 1) * 32 + lane;   // 0..95
     const int tw = tt >> 5;
     const float sl2 = p.scale_log2;
     const uint32_t q_u = smem_u32(sQ), k_u = smem_u32(sK), v_u = smem_u32(sV), o_u = smem_u32(sdO);
-    mbar_wait(bar_ld0, 0);
-    mbar_wait(bar_ld, 0);
+    int kit = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++kit) {
+    if (warp == 0 && lane == 0 && kit > 0) {
+      mbar_wait(bar_done, (kit - 1) & 1);   // softmax warps (hence every MMA) and, in program order, the tail threads are done
+      issue_loads(item);
+    }
+    __syncwarp();
+    if (p.ntail == 0) continue;
+    const int h = item % p.H, sample = item / p.H;
+    const int row0 = p.row_base + sample * S;
+    (void)sample;
+    mbar_wait(bar_ld0, kit & 1);
+    mbar_wait(bar_ld, kit & 1);
     bar_sync_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta written by the softmax warps
     // tail queries first: the dK / dV epilogue of key tile 0 is the first consumer
     for (int t = 0; t < p.ntail; ++t) {
@@ -1026,9 +1062,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       }
       bar_sync_named(2, AT_TAIL_THREADS);
     }
+    }  // items
   }
 
-  if (p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta && threadIdx.x == 128) p.tl[10 * 64 + 1] = clock64();
+  if (p.tl != nullptr && static_cast<int>(blockIdx.x) == p.tl_cta % static_cast<int>(gridDim.x) && threadIdx.x == 128) p.tl[10 * 64 + 1] = clock64();
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -1058,19 +1095,20 @@ void split_tail(int S, int max_tail, int* tiles, int* tail) {
   }
 }
 // Largest tail that goes to the control warps.  The three tail warps share their sub-partitions with the softmax
-// warps, so the tail work must stay well below the main loop.  Measured on B200 per layer (512 samples, 12 heads):
-//   257 tokens (every adaLN decoder):       forward 0.53 -> 0.41 ms, backward 1.10 -> 0.77 ms
-//   258 tokens (decoder with a cond token): forward 0.53 -> 0.45 ms, backward 1.11 -> 1.01 ms
-//   260 tokens (label-conditioned encoder, 256 samples): forward 0.27 -> 0.35 ms, backward 0.55 -> 0.86 ms (worse)
-// hence the default limit of 2 rows; the kernels handle up to AT_TAIL (tests raise the limit through
-// umd_debug_attn_tail_limits).
+// warps, and in the persistent kernels the next item's loads wait for them (they read the operand tiles), so the
+// tail work must stay well below the main loop.  Measured on B200 per layer (512 samples, 12 heads, persistent kernels):
+//   257 tokens (every adaLN decoder):       forward 0.53 -> 0.35 ms, backward 1.05 -> 0.73 ms
+//   258 tokens (decoder with a cond token): forward two rows pay (0.45 -> 0.41 ms); backward 1.05 without, 1.13 with
+//   260 tokens (label-conditioned encoder): four rows are slower than the third tile in both directions
+// hence the default limits: forward 2 rows, backward 1 row; the kernels handle up to AT_TAIL (tests raise the limits
+// through umd_debug_attn_tail_limits).
 int g_tail_limit[2] = {-1, -1};
 int tail_limit(bool backward) {
   if (g_tail_limit[0] < 0) {
     const char* f = getenv("UMD_ATTN_TAIL_FWD_MAX");
     const char* b = getenv("UMD_ATTN_TAIL_BWD_MAX");
     g_tail_limit[0] = f ? atoi(f) : 2;
-    g_tail_limit[1] = b ? atoi(b) : 2;
+    g_tail_limit[1] = b ? atoi(b) : 1;
     for (int k = 0; k < 2; ++k) g_tail_limit[k] = g_tail_limit[k] < 0 ? 0 : (g_tail_limit[k] > AT_TAIL ? AT_TAIL : g_tail_limit[k]);
   }
   return g_tail_limit[backward ? 1 : 0];
@@ -1182,11 +1220,13 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     { const char* e = getenv("UMD_TL_CTA"); p.tl_cta = e ? atoi(e) : 0; }
     static int pf = -1;
     if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
-    p.ahead = pf ? sm_count() : 0;
+    p.ahead = pf;
+    p.nitems = n * a.H;
     int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 256 + 1024;   // + 3 KB of static shared memory
     if (p.ntail > 0) smem += (4 * AT_TAIL * p.SP + 9 * 64) * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
-    attn_bwd_tc_kernel<<<n * a.H, AT_BWD_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
+    const int grid = p.nitems < sm_count() ? p.nitems : sm_count();
+    attn_bwd_tc_kernel<<<grid, AT_BWD_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
     ++g_launch_count;
     UMD_CHECK_CUDA(cudaGetLastError());
   }
