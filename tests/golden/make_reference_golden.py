@@ -1,0 +1,260 @@
+"""Generates tests/golden/reference_golden.pt by EXECUTING THE REFERENCE'S OWN SOURCE FILES.
+
+PROVENANCE: unlike umd_golden.pt (oracle-generated), every number in this fixture is produced by the unmodified
+reference code under /root/reference — `big_vision/models/{ae,vit,embeddings}.py`, `big_vision/gaussian_diffusion.py`
+and the `loss_fn` closure of `big_vision/trainers/train_ae.py::update_fn` (train_ae.py:323-361, lifted out of the
+enclosing function with `ast` at run time, not copied) — imported over `tests/golden/refshim/`, a numpy-float64
+stand-in for the `jax` / `flax.linen` names those files use (JAX/Flax themselves are not installable here, SURVEY.md
+F2).  What the shim restates (library layers) and what is the reference's own code (all wiring, masking, conditioning,
+diffusion formulas, the loss) is listed in refshim/README.md.  Random draws are supplied through the shim's keys, so the
+same draws can be given to the oracle and to the CUDA path.  Parameter gradients: the reference's loss is differenced
+(central, fp64) along seeded parameter directions; the oracle's autograd gradient must reproduce those slopes.
+
+Runs only in the build container (it needs /root/reference):
+  python tests/golden/make_reference_golden.py
+"""
+import ast
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("UMD_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, ROOT)
+
+from tests import util as U  # noqa: E402  (inputs and parameters are drawn by the same helpers the tests use)
+
+CASES = {
+    # name: (model kwargs, train config, batch, n_noise)
+    "umd_s4": (dict(variant="S/4", adaln=True, depth=2, dec_depth=1),
+               dict(mask_ratio=0.375, mask_ratio_no_noise=0.75, no_noise_prob=0.5, use_labels=False), 4, 2),
+    "mae_s4": (dict(variant="S/4", adaln=False, depth=2, dec_depth=1),
+               dict(mask_ratio=0.375, mask_ratio_no_noise=0.75, no_noise_prob=0.5, use_labels=False), 4, 2),
+    "dit_s4": (dict(variant="S/4", adaln=True, num_classes=10, depth=2, dec_depth=1),
+               dict(mask_ratio=0.0, mask_ratio_no_noise=0.75, no_noise_prob=0.0, use_labels=True), 4, 4),
+    "umd_lbl_s4": (dict(variant="S/4", adaln=True, num_classes=10, depth=1, dec_depth=1),
+                   dict(mask_ratio=0.375, mask_ratio_no_noise=0.75, no_noise_prob=0.5, use_labels=True), 4, 2),
+}
+PARAM_SEED, BATCH_SEED, DIR_SEED = 0, 100, 4242
+FD_STEP = 1e-3
+GROUP_DIRECTIONS = 3   # whole-tree directions; plus one direction per top-level parameter group
+
+
+def load_reference():
+  """Imports the reference's files over the shim and lifts loss_fn out of update_fn."""
+  sys.path.insert(0, os.path.join(HERE, "refshim"))
+  sys.path.insert(0, REF)
+  for name in ("big_vision.utils", "big_vision.models.common"):   # imported by vit.py for checkpoint loading only
+    sys.modules[name] = types.ModuleType(name)
+  import jax  # noqa: F401  (the shim)
+  assert "refshim" in jax.__file__
+  from big_vision.models import ae
+  from big_vision import gaussian_diffusion as gd
+  assert ae.__file__.startswith(REF) and gd.__file__.startswith(REF)
+  path = os.path.join(REF, "big_vision", "trainers", "train_ae.py")
+  tree = ast.parse(open(path).read(), filename=path)
+  node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "loss_fn")
+  code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+  return ae, gd, code, (node.lineno, node.end_lineno)
+
+
+class Config(dict):
+  __getattr__ = dict.__getitem__
+
+
+def np64(t):
+  return np.asarray(t.detach().cpu().double().numpy() if isinstance(t, torch.Tensor) else t, dtype=np.float64)
+
+
+def tree64(tree):
+  return {k: (tree64(v) if isinstance(v, dict) else np64(v)) for k, v in tree.items()}
+
+
+def flatten(tree, prefix=()):
+  out = {}
+  for k in sorted(tree):
+    v = tree[k]
+    if isinstance(v, dict):
+      out.update(flatten(v, prefix + (k,)))
+    else:
+      out[prefix + (k,)] = v
+  return out
+
+
+def directions(params, seed=DIR_SEED):
+  """Seeded unit-norm parameter directions: GROUP_DIRECTIONS over the whole tree, then one per top-level group.
+  Regenerated identically by the tests (torch CPU generator, sorted leaf order)."""
+  flat = flatten(params)
+  g = torch.Generator().manual_seed(seed)
+  groups = [None] * GROUP_DIRECTIONS + sorted({k[0] for k in flat})
+  out = []
+  for grp in groups:
+    d = {}
+    for k, v in flat.items():
+      r = torch.randn(tuple(np.shape(v)), generator=g, dtype=torch.float64)
+      d[k] = r if (grp is None or k[0] == grp) else torch.zeros_like(r)
+    nrm = float(torch.sqrt(sum((x ** 2).sum() for x in d.values())))
+    out.append((grp or "*", {k: x / nrm for k, x in d.items()}))
+  return out
+
+
+def shifted(params, d, h):
+  def rec(tree, prefix):
+    return {k: (rec(v, prefix + (k,)) if isinstance(v, dict) else v + h * d[prefix + (k,)].numpy())
+            for k, v in tree.items()}
+  return rec(params, ())
+
+
+def digest(t):
+  return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def build_case(name, ae, gdm, loss_code):
+  import jax
+  import jax.numpy as jnp
+  mkw, tkw, B, n_noise = CASES[name]
+  engine_model, _ = U.make_models(**mkw)
+  params_t = U.cpu_tree(U.perturb_init(engine_model, PARAM_SEED, "cpu"))
+  batch, rand = U.make_batch(engine_model, B, n_noise=n_noise, seed=BATCH_SEED, use_labels=tkw["use_labels"],
+                             device="cpu")
+  params = tree64(params_t)
+  model = ae.Model(**mkw)                                   # the reference's factory (ae.py:220-222)
+  gd = gdm.create_gaussian_diffusion("cosine", 1000)        # gaussian_diffusion.py:32-66
+  n_clean = B - n_noise
+  assert n_clean == int(B * tkw["no_noise_prob"])
+  images = jnp.asarray(np64(batch["image"]))
+  x0_noise, x0_clean = images[:n_noise], images[n_noise:]
+  t = jnp.asarray(rand["t"].numpy().astype(np.int32))
+  noise = jnp.asarray(np64(rand["noise"]))
+  x_t = gdm.q_sample(gd=gd, x_start=x0_noise, t=t, noise=noise)         # gaussian_diffusion.py:84-98
+  labels = jnp.asarray(batch["label"][:n_noise].numpy().astype(np.int32)) if tkw["use_labels"] else None
+  has_lbl = mkw.get("num_classes") is not None
+
+  def keys():
+    drop = rand.get("label_drop_noise")
+    return dict(
+        rng_model=jax.Key(), rng_model_noise=jax.Key(),
+        mae_noise_rng=jax.Key({"uniform": np64(rand["mask_noise_clean"])}),
+        mae_noise_rng_noise=jax.Key({"uniform": np64(rand["mask_noise_noise"])}),
+        cfg_rng=jax.Key({"bernoulli": np.zeros((n_clean,))}),
+        cfg_rng_noise=jax.Key({"bernoulli": np64(drop.double()) if drop is not None else np.zeros((n_noise,))}))
+
+  def reference_loss(p):
+    env = dict(jnp=jnp, model=model, config=Config(diffusion_space=(64, 64, 3), **tkw), B=B, n_noise=n_noise,
+               n_no_noise=n_clean, x_0_noise=x0_noise, x_0_no_noise=x0_clean, x_t_noise=x_t, batched_t=t,
+               labels_t=labels, noise=noise, **keys())
+    exec(loss_code, env)                                     # defines the reference's loss_fn in env
+    return float(env["loss_fn"](p))
+
+  out = {"input_digest": digest(batch["image"]) + digest(rand["noise"]) + digest(rand["mask_noise_clean"]),
+         "param_digest": digest(torch.cat([v.reshape(-1) for _, v in sorted(flatten(params_t).items())])),
+         "x_t": torch.from_numpy(np.asarray(x_t)).float(),
+         "loss": reference_loss(params)}
+  k = keys()
+  if n_clean > 0:
+    pred, o = model.apply({"params": params}, x0_clean, t=jnp.zeros((n_clean, 1), dtype=jnp.int32), train=True,
+                          mask=tkw["mask_ratio_no_noise"],
+                          rngs={"dropout": k["rng_model"], "cfg": k["cfg_rng"], "mae_noise": k["mae_noise_rng"]})
+    out["clean"] = pack(pred, o)
+  if n_noise > 0:
+    pred, o = model.apply({"params": params}, x_t, t=t + 1, y=labels, train=True, mask=tkw["mask_ratio"],
+                          rngs={"dropout": k["rng_model_noise"], "cfg": k["cfg_rng_noise"],
+                                "mae_noise": k["mae_noise_rng_noise"]})
+    out["noise"] = pack(pred, o)
+  slopes = []
+  for grp, d in directions(params_t):
+    lp, lm = reference_loss(shifted(params, d, FD_STEP)), reference_loss(shifted(params, d, -FD_STEP))
+    lp2, lm2 = reference_loss(shifted(params, d, FD_STEP / 2)), reference_loss(shifted(params, d, -FD_STEP / 2))
+    d1, d2 = (lp - lm) / (2 * FD_STEP), (lp2 - lm2) / FD_STEP
+    slopes.append((grp, (4 * d2 - d1) / 3, abs(d2 - d1)))   # Richardson-extrapolated slope, and its error scale
+  out["slopes"] = slopes
+  if has_lbl:   # classifier-free-guidance forward (ae.py:177-195), inference mode, no masking
+    y = jnp.asarray(batch["label"][:2].numpy().astype(np.int32))
+    tt = jnp.asarray(np.array([[500], [17]], dtype=np.int32))
+    pred, o = model.apply({"params": params}, images[:2], t=tt, y=y, cfg_scale=1.5)
+    out["cfg"] = {"pred": torch.from_numpy(np.asarray(pred)).float(), "t": torch.tensor([[500], [17]], dtype=torch.int32),
+                  "cfg_scale": 1.5, "pre_logits": torch.from_numpy(np.asarray(o["pre_logits"])).double()}
+  return out
+
+
+def pack(pred, o):
+  pred = np.asarray(pred)
+  d = {"pred0": torch.from_numpy(pred[0]).float(),                                  # sample 0 in full
+       "pred_sample_means": torch.from_numpy(pred.mean(axis=(1, 2))).double(),      # [n, 2C]
+       "pred_abs_mean": float(np.abs(pred).mean()),
+       "pre_logits": torch.from_numpy(np.asarray(o["pre_logits"])).double()}
+  if o["mask"] is not None:
+    m = np.asarray(o["mask"])[:, ::4, ::4, 0]                                       # one value per 4x4 patch
+    assert set(np.unique(m)) <= {0.0, 1.0}
+    d["patch_mask"] = torch.from_numpy(m.reshape(m.shape[0], -1).astype(np.uint8))
+  return d
+
+
+def diffusion_vectors(gdm):
+  """gaussian_diffusion.py run as is: tables, q_sample, x0/eps conversions, DDIM steps and the DDIM loop."""
+  import jax
+  import jax.numpy as jnp
+  out = {}
+  for sched in ("cosine", "linear"):
+    gd = gdm.create_gaussian_diffusion(sched, 1000)
+    out[f"tables_{sched}"] = {k: torch.from_numpy(np.asarray(v, dtype=np.float64)) for k, v in gd.items()}
+  gd = gdm.create_gaussian_diffusion("cosine", 1000)
+  g = torch.Generator().manual_seed(77)
+  x = torch.randn(4, 8, 8, 3, generator=g, dtype=torch.float64)
+  eps = torch.randn(4, 8, 8, 3, generator=g, dtype=torch.float64)
+  nz = torch.randn(4, 8, 8, 3, generator=g, dtype=torch.float64)
+  t = torch.tensor([[0], [1], [500], [999]], dtype=torch.int32)
+  tn = torch.tensor([[0], [0], [492], [991]], dtype=torch.int32)
+  J = lambda a: jnp.asarray(a.numpy())
+  out["inputs"] = {"x": x, "eps": eps, "noise": nz, "t": t, "t_next": tn}
+  out["q_sample"] = torch.from_numpy(np.asarray(gdm.q_sample(gd=gd, x_start=J(x), t=J(t), noise=J(nz))))
+  out["xstart_from_eps"] = torch.from_numpy(np.asarray(gdm._predict_xstart_from_eps(gd, J(x), J(t), J(eps))))
+  steps = []
+  for eta, clip, use_next in ((0.0, False, True), (1.0, False, True), (0.5, True, True), (1.0, True, False)):
+    r = gdm.ddim_sample(gd, lambda x_t, t, rng, **kw: J(eps), J(x), J(t), J(tn) if use_next else None,
+                        jax.Key({"normal": nz.numpy()}), clip_denoised=clip, eta=eta)
+    steps.append({"eta": eta, "clip": clip, "use_next": use_next,
+                  "sample": torch.from_numpy(np.asarray(r["sample"])),
+                  "pred_xstart": torch.from_numpy(np.asarray(r["pred_xstart"]))})
+  out["ddim_steps"] = steps
+  # whole loop with a closed-form model: eps(x_t, t, y) = 0.3 x_t + 0.01 (t/1000) + 0.05 y
+  S = 5
+  draws = [torch.randn(2, 8, 8, 3, generator=g, dtype=torch.float64) for _ in range(S + 2)]
+  ys = torch.tensor([3, 7], dtype=torch.int32)
+
+  def apply_fn(x_t, t, rng, y=None, cfg_scale=None):
+    return 0.3 * x_t + 0.01 * (np.asarray(t, dtype=np.float64) / 1000.0)[:, :, None, None] \
+        + 0.05 * np.asarray(y, dtype=np.float64)[:, None, None, None]
+  ret, _ = gdm.ddim_sample_loop(gd, apply_fn, jax.Key({"normal": [d.numpy() for d in draws]}),
+                                np.zeros((2, 8, 8, 3)), ys=J(ys), sampling_steps=S, eta=0.7)
+  S_eff = None
+  out["ddim_loop"] = {"draws": torch.stack(draws), "ys": ys, "sampling_steps": S, "eta": 0.7,
+                      "sample": torch.from_numpy(np.asarray(ret["sample"]))}
+  for n, s in ((1000, 250), (1000, 125), (1000, 7), (1000, 1000)):
+    # the time-step grid exactly as ddim_sample_loop builds it (gaussian_diffusion.py:241-242)
+    ts = jnp.append(jnp.arange(n - 1, 0, step=-n // s, dtype=jnp.int32), 0)
+    out[f"timesteps_{n}_{s}"] = torch.from_numpy(np.asarray(ts).astype(np.int64))
+  return out
+
+
+def main():
+  ae, gdm, loss_code, loss_lines = load_reference()
+  gold = {"provenance": "reference source executed over tests/golden/refshim (numpy fp64); loss_fn = train_ae.py:%d-%d"
+                        % loss_lines,
+          "fd_step": FD_STEP, "cases": {}, "diffusion": diffusion_vectors(gdm)}
+  for n in CASES:
+    gold["cases"][n] = build_case(n, ae, gdm, loss_code)
+    c = gold["cases"][n]
+    print(n, "loss", c["loss"], "slopes", [(g, f"{s:.6e}", f"{e:.1e}") for g, s, e in c["slopes"]][:4])
+  path = os.path.join(HERE, "reference_golden.pt")
+  torch.save(gold, path)
+  print(path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+  main()

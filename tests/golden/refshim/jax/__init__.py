@@ -1,0 +1,68 @@
+"""Stand-in for the `jax` top-level names the reference's hot path touches (see ../README.md)."""
+import types as _types
+
+import numpy as _np
+
+from . import numpy  # noqa: F401  (jax.numpy)
+from .numpy import JArr as _JArr
+
+
+class Key:
+  """A PRNG key that carries the draws it will hand out: `draws` maps a kind ('uniform', 'normal',
+  'bernoulli') to an array, or to a list of arrays consumed in call order.  `split` hands the same
+  dictionary on under a derived name so that supplied draws can be addressed per consumer."""
+
+  def __init__(self, draws=None, name="root"):
+    self.draws = draws if draws is not None else {}
+    self.name = name
+
+  def take(self, kind, shape):
+    v = self.draws[kind]
+    if isinstance(v, list):
+      v = v.pop(0)
+    v = _np.asarray(v)
+    assert tuple(v.shape) == tuple(shape), (kind, v.shape, shape)
+    return v.view(_JArr)
+
+
+def _split(key, n=2):
+  subs = key.draws.get("split")
+  if subs is not None:
+    assert len(subs) == n
+    return list(subs)
+  return [key for _ in range(n)]   # list-valued draws are then consumed in call order
+
+
+random = _types.SimpleNamespace(
+    split=_split,
+    uniform=lambda key, shape: key.take("uniform", shape),
+    normal=lambda key, shape: key.take("normal", shape),
+    bernoulli=lambda key, p, shape: key.take("bernoulli", shape).astype(bool),
+)
+
+
+def vmap(fn):
+  def run(*args):
+    return _np.stack([_np.asarray(fn(*[a[i] for a in args])) for i in range(len(args[0]))]).view(_JArr)
+  return run
+
+
+def _scan(f, init, xs):
+  carry = init
+  for x in xs:
+    carry, _ = f(carry, x)
+  return carry, None
+
+
+lax = _types.SimpleNamespace(scan=_scan)
+checkpoint_policies = _types.SimpleNamespace(nothing_saveable=None)
+
+
+class _Init:
+  """Initialisers are never evaluated: parameters are supplied to `apply`."""
+
+  def __getattr__(self, name):
+    return lambda *a, **k: ("init", name)
+
+
+nn = _types.SimpleNamespace(initializers=_Init())
