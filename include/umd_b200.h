@@ -233,6 +233,36 @@ int umd_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const lo
                  const void* params_bf16, float* grads, const umd_io* io, void* workspace, size_t workspace_bytes,
                  umd_bucket_cb cb, void* cb_user, umd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Few-shot ridge probe on `pre_logits`: big_vision/evaluators/fewshot_lsr.py.
+ * All buffers fp32 / int32 device pointers, row-major.  dim = d + 1 (the appended bias feature).
+ * ------------------------------------------------------------------------------------------ */
+/* fewshot_lsr.py:46-47  column mean and population std + 1e-5 of the support features x[n, d]. */
+int umd_fewshot_stats(const float* x, int n, int d, float* mean, float* std_plus_eps, umd_stream_t stream);
+/* fewshot_lsr.py:48-51 (support) and :99-100 (query): out[n, d + 1] = [(x - mean) / std | bias_constant]. */
+int umd_fewshot_whiten(const float* x, const float* mean, const float* std_plus_eps, int n, int d, float bias_constant,
+                       float* out, umd_stream_t stream);
+/* fewshot_lsr.py:54,82  rhs[dim, C] = X^T (2 onehot(y) - 1) from per-class row sums; sums_scratch: (C + 1) * dim floats. */
+int umd_fewshot_xty(const float* xw, const int* y, int n, int dim, int num_classes, float* sums_scratch, float* rhs,
+                    umd_stream_t stream);
+/* fewshot_lsr.py:54  out[n, C] = 2 onehot(y) - 1 (needed as the right-hand side when n < dim, :86-88). */
+int umd_fewshot_targets(const int* y, int n, int num_classes, float* out, umd_stream_t stream);
+/* fp32 product with element strides, C[m, n] = sum_k A[m * a_row_stride + k * a_col_stride] * B[k * b_row_stride +
+ * n * b_col_stride]: x^T x / x x^T (fewshot_lsr.py:81,85), x^T z (:88,108) and x_test w (:111) are all this call. */
+int umd_fewshot_matmul(const float* A, long long a_row_stride, long long a_col_stride, const float* B,
+                       long long b_row_stride, long long b_col_stride, float* C, long long ldc, int M, int N, int K,
+                       umd_stream_t stream);
+/* fewshot_lsr.py:103-108  z = (gram + l2_reg I)^-1 rhs.  The reference applies the inverse through the cached
+ * eigendecomposition (q diag(1 / (eigs + l2)) q^T); here a Cholesky factorisation in fp64 gives the same solution.
+ * gram [n, n] symmetric, rhs / z [n, num_rhs] (may alias); *status (device int) = 0, or 1 + the first non-positive
+ * pivot.  n <= 2048. */
+size_t umd_fewshot_solve_scratch_bytes(int n, int num_rhs);
+int umd_fewshot_ridge_solve(const float* gram, float l2_reg, const float* rhs, int n, int num_rhs, float* z, void* scratch,
+                            size_t scratch_bytes, int* status, umd_stream_t stream);
+/* fewshot_lsr.py:111-112  preds = argmax(scores[n, C], axis 1) (first maximum); *correct = #(preds == labels). */
+int umd_fewshot_accuracy(const float* scores, const int* labels, int n, int num_classes, int* preds_or_null, int* correct,
+                         umd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -554,3 +554,43 @@ def update_step(state, batch, cfg, tc, hp, rand, dtype=torch.float32):
     fn = flatten_tree(new_params)
     new_state["ema_params"] = unflatten_tree({k: d * fn[k] + (1.0 - d) * fe[k] for k in fe})
   return new_state, meas, {"grads": grads, "aux": aux, "x_t": x_t}
+
+
+# ------------------------------------------------------------------------------------------
+# evaluators/fewshot_lsr.py: few-shot ridge probe on pre_logits
+# ------------------------------------------------------------------------------------------
+
+FEWSHOT_BIAS_CONSTANT = 100.0  # fewshot_lsr.py:31
+
+
+def fewshot_precompute_cache(x, y, num_classes):
+  """fewshot_lsr.py:43-97 (_precompute_cache): whiten, append the bias feature, one-hot targets in {-1, 1}, and the
+  eigendecomposition of x^T x (N >= D) or x x^T (D > N)."""
+  mean = x.mean(dim=0, keepdim=True)
+  std = x.std(dim=0, keepdim=True, unbiased=False) + 1e-5
+  x = (x - mean) / std
+  x = torch.cat([x, torch.full((x.shape[0], 1), FEWSHOT_BIAS_CONSTANT, dtype=x.dtype)], dim=1)
+  yy = 2.0 * F.one_hot(y.long(), num_classes).to(x.dtype) - 1.0
+  n, dim = x.shape
+  if n >= dim:
+    eigs, q = torch.linalg.eigh(x.T @ x)
+    rhs, lhs = q.T @ (x.T @ yy), q
+  else:
+    eigs, q = torch.linalg.eigh(x @ x.T)
+    rhs, lhs = q.T @ yy, x.T @ q
+  return {"eigs": eigs, "rhs": rhs, "lhs": lhs, "mean": mean, "std": std}
+
+
+def fewshot_weights(cache, l2_reg):
+  """fewshot_lsr.py:103-108."""
+  scaling = (1.0 / (cache["eigs"] + l2_reg)).reshape(1, -1)
+  return (cache["lhs"] * scaling) @ cache["rhs"]
+
+
+def fewshot_acc(cache, x_test, y_test, l2_reg):
+  """fewshot_lsr.py:94-112 (_eig_fewshot_acc_fn).  Returns (accuracy, preds, scores)."""
+  x_test = (x_test - cache["mean"]) / cache["std"]
+  x_test = torch.cat([x_test, torch.full((x_test.shape[0], 1), FEWSHOT_BIAS_CONSTANT, dtype=x_test.dtype)], dim=1)
+  scores = x_test @ fewshot_weights(cache, l2_reg)
+  preds = scores.argmax(dim=1)
+  return float((preds == y_test.long()).double().mean()), preds, scores

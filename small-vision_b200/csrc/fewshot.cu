@@ -1,0 +1,361 @@
+// Few-shot ridge probe on `pre_logits` (big_vision/evaluators/fewshot_lsr.py:43-116).
+//
+// The reference whitens the support features, appends a constant bias feature (100), regresses one-hot targets in
+// {-1, +1} with an L2 penalty and scores the query set by argmax.  It solves the normal equations through an
+// eigendecomposition so that several penalties share one factorisation; the ridge solution itself is
+//   N >= D:  W = (X^T X + l2 I)^-1 X^T Y          N < D:  W = X^T (X X^T + l2 I)^-1 Y
+// which is what is computed here: Gram matrices and X^T Y in fp32 on the CUDA cores (all kernels HBM/L2 or FMA bound,
+// nothing GEMM-heavy enough for the tensor pipe at D = 769), the symmetric positive-definite solve by a Cholesky
+// factorisation in fp64 (the bias feature puts 1e9 on the diagonal against l2 = 1024: condition ~1e6).
+#include "common.cuh"
+
+namespace umd {
+extern long long g_launch_count;
+
+#define FS_LAUNCH_CHECK()                \
+  do {                                   \
+    ++g_launch_count;                    \
+    UMD_CHECK_CUDA(cudaGetLastError());  \
+  } while (0)
+
+// -----------------------------------------------------------------------------------------
+// Column statistics: mean and population standard deviation (+1e-5) of x[n, d]   (fewshot_lsr.py:46-47)
+// One CTA per 32 columns, 32 x 8 threads: coalesced 128-byte row segments, two passes (mean, then centred squares).
+// -----------------------------------------------------------------------------------------
+__global__ void fs_stats_kernel(const float* __restrict__ x, int n, int d, float* __restrict__ mean,
+                                float* __restrict__ stdv) {
+  __shared__ double red[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const bool live = col < d;
+  double s = 0.0;
+  for (int r = threadIdx.y; r < n; r += 8) s += live ? static_cast<double>(x[static_cast<long long>(r) * d + col]) : 0.0;
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  double m = 0.0;
+  for (int k = 0; k < 8; ++k) m += red[k][threadIdx.x];
+  m /= n;
+  __syncthreads();
+  double q = 0.0;
+  for (int r = threadIdx.y; r < n; r += 8) {
+    const double v = live ? static_cast<double>(x[static_cast<long long>(r) * d + col]) - m : 0.0;
+    q += v * v;
+  }
+  red[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    mean[col] = static_cast<float>(m);
+    stdv[col] = static_cast<float>(sqrt(t / n)) + 1e-5f;
+  }
+}
+
+// out[n, d + 1] = [(x - mean) / std | 100]                                        (fewshot_lsr.py:48-51,99-100)
+__global__ void fs_whiten_kernel(const float* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                 long long n, int d, float bias_constant, float* __restrict__ out) {
+  const long long total = n * (d + 1);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / (d + 1);
+    const int c = static_cast<int>(i - r * (d + 1));
+    out[i] = c < d ? (x[r * d + c] - mean[c]) / stdv[c] : bias_constant;
+  }
+}
+
+// rhs[dim, c] = X^T Y with Y = 2 onehot(y) - 1 (fewshot_lsr.py:54): 2 * (sum of the rows of class c) - (sum of all rows).
+// Pass 1 scatters rows into class sums (fp32 atomics: every class receives `shots` rows), pass 2 finishes.
+__global__ void fs_class_sums_kernel(const float* __restrict__ xw, const int* __restrict__ y, int n, int dim, int c,
+                                     float* __restrict__ sums /*[c + 1, dim], zeroed; row c = total*/) {
+  const int r = blockIdx.x;
+  const int cls = y[r];
+  const float* row = xw + static_cast<long long>(r) * dim;
+  for (int k = threadIdx.x; k < dim; k += blockDim.x) {
+    const float v = row[k];
+    if (cls >= 0 && cls < c) atomicAdd(&sums[static_cast<long long>(cls) * dim + k], v);
+    atomicAdd(&sums[static_cast<long long>(c) * dim + k], v);
+  }
+}
+__global__ void fs_rhs_from_sums_kernel(const float* __restrict__ sums, int dim, int c, float* __restrict__ rhs /*[dim, c]*/) {
+  const long long total = static_cast<long long>(dim) * c;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i / c), cls = static_cast<int>(i - static_cast<long long>(k) * c);
+    rhs[i] = 2.f * sums[static_cast<long long>(cls) * dim + k] - sums[static_cast<long long>(c) * dim + k];
+  }
+}
+// Y[n, c] = 2 onehot(y) - 1 (the N < D branch needs the targets themselves, fewshot_lsr.py:88)
+__global__ void fs_targets_kernel(const int* __restrict__ y, long long n, int c, float* __restrict__ out) {
+  const long long total = n * c;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / c;
+    out[i] = (y[r] == static_cast<int>(i - r * c)) ? 1.f : -1.f;
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// fp32 matrix product on the CUDA cores with arbitrary element strides (so that X^T X, X X^T, X^T Z and X W are the
+// same kernel):  C[m, n] = sum_k A(m, k) B(k, n),  A(m, k) = A[m * a_rs + k * a_cs],  B(k, n) = B[k * b_rs + n * b_cs].
+// 128 x 128 tile per CTA, 256 threads, 8 x 8 outputs per thread, K staged 16 at a time through shared memory
+// (stored k-major so that the inner product reads are conflict-free broadcasts / consecutive words).  Optional
+// split over K (gridDim.z) with atomic accumulation for the tall-skinny Gram products (K = support size).
+// -----------------------------------------------------------------------------------------
+constexpr int FS_TM = 128, FS_TN = 128, FS_TK = 16;
+__global__ void __launch_bounds__(256)
+fs_matmul_kernel(const float* __restrict__ A, long long a_rs, long long a_cs, const float* __restrict__ B, long long b_rs,
+                 long long b_cs, float* __restrict__ C, long long ldc, int M, int N, int K, int k_per_split, int atomic) {
+  __shared__ float As[FS_TK][FS_TM + 4];
+  __shared__ float Bs[FS_TK][FS_TN + 4];
+  const int m0 = blockIdx.y * FS_TM, n0 = blockIdx.x * FS_TN;
+  const int kb = blockIdx.z * k_per_split, ke = min(K, kb + k_per_split);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 x 16 threads, each 8 x 8 (strided by 16)
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  // loader mapping: which of the two strides is unit decides which index runs fastest across threads
+  const bool a_k_fast = (a_cs == 1), b_n_fast = (b_cs == 1);
+  for (int k0 = kb; k0 < ke; k0 += FS_TK) {
+    for (int e = threadIdx.x; e < FS_TM * FS_TK; e += 256) {
+      int mm, kk;
+      if (a_k_fast) { kk = e % FS_TK; mm = e / FS_TK; } else { mm = e % FS_TM; kk = e / FS_TM; }
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < ke) ? A[gm * a_rs + gk * a_cs] : 0.f;
+    }
+    for (int e = threadIdx.x; e < FS_TN * FS_TK; e += 256) {
+      int nn, kk;
+      if (b_n_fast) { nn = e % FS_TN; kk = e / FS_TN; } else { kk = e % FS_TK; nn = e / FS_TK; }
+      const int gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < N && gk < ke) ? B[gk * b_rs + gn * b_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < FS_TK; ++kk) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + ty + 16 * i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int gn = n0 + tx + 16 * j;
+      if (gn >= N) continue;
+      float* dst = C + gm * ldc + gn;
+      if (atomic) atomicAdd(dst, acc[i][j]); else *dst = acc[i][j];
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------------------
+// Ridge solve: (G + l2 I) Z = R for symmetric positive semi-definite G [n, n] (fp32 in) and R [n, c] (fp32 in, Z out).
+// fp64 work copy; one CTA factorises (right-looking Cholesky, column scale + trailing rank-1 update per step; n <= ~1k
+// keeps the matrix L2-resident and the whole factorisation at a few ms), then the two triangular solves run one
+// right-hand side per thread (coalesced across threads, rows of L broadcast).
+// -----------------------------------------------------------------------------------------
+__global__ void fs_load_system_kernel(const float* __restrict__ G, float l2, int n, double* __restrict__ L) {
+  const long long total = static_cast<long long>(n) * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n), c = static_cast<int>(i - static_cast<long long>(r) * n);
+    // symmetrise (atomic split-K accumulation orders differ between the two triangles)
+    const double v = 0.5 * (static_cast<double>(G[i]) + static_cast<double>(G[static_cast<long long>(c) * n + r]));
+    L[i] = v + (r == c ? static_cast<double>(l2) : 0.0);
+  }
+}
+__global__ void __launch_bounds__(1024) fs_cholesky_kernel(double* __restrict__ L, int n, int* __restrict__ status) {
+  __shared__ double col[2048];           // column j below the diagonal, scaled (n <= 2048)
+  __shared__ double diag;
+  for (int j = 0; j < n; ++j) {
+    if (threadIdx.x == 0) {
+      const double d = L[static_cast<long long>(j) * n + j];
+      if (!(d > 0.0)) { *status = j + 1; diag = 1.0; } else diag = sqrt(d);
+    }
+    __syncthreads();
+    const double dj = diag;
+    for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
+      const double v = (i == j) ? dj : L[static_cast<long long>(i) * n + j] / dj;
+      L[static_cast<long long>(i) * n + j] = v;
+      col[i] = v;
+    }
+    __syncthreads();
+    // trailing update of the lower triangle: L[i][k] -= col[i] * col[k], j < k <= i < n; one warp per row, lanes along k
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = j + 1 + warp; i < n; i += nwarps) {
+      const double ci = col[i];
+      double* Li = L + static_cast<long long>(i) * n;
+      for (int k = j + 1 + lane; k <= i; k += 32) Li[k] -= ci * col[k];
+    }
+    __syncthreads();
+  }
+}
+// forward then backward substitution, one right-hand side per thread; Z overwrites R (fp32 in / out, fp64 inside via W)
+__global__ void fs_trisolve_kernel(const double* __restrict__ L, int n, int c, const float* __restrict__ R,
+                                   double* __restrict__ W /*[n, c] scratch*/, float* __restrict__ Z) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= c) return;
+  for (int i = 0; i < n; ++i) {                       // L w = r
+    const double* Li = L + static_cast<long long>(i) * n;
+    double s0 = static_cast<double>(R[static_cast<long long>(i) * c + t]), s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = 0;
+    for (; k + 4 <= i; k += 4) {
+      s0 -= Li[k] * W[static_cast<long long>(k) * c + t];
+      s1 -= Li[k + 1] * W[static_cast<long long>(k + 1) * c + t];
+      s2 -= Li[k + 2] * W[static_cast<long long>(k + 2) * c + t];
+      s3 -= Li[k + 3] * W[static_cast<long long>(k + 3) * c + t];
+    }
+    for (; k < i; ++k) s0 -= Li[k] * W[static_cast<long long>(k) * c + t];
+    W[static_cast<long long>(i) * c + t] = (s0 + s1 + s2 + s3) / Li[i];
+  }
+  for (int i = n - 1; i >= 0; --i) {                  // L^T z = w
+    double s0 = W[static_cast<long long>(i) * c + t], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = i + 1;
+    for (; k + 4 <= n; k += 4) {
+      s0 -= L[static_cast<long long>(k) * n + i] * W[static_cast<long long>(k) * c + t];
+      s1 -= L[static_cast<long long>(k + 1) * n + i] * W[static_cast<long long>(k + 1) * c + t];
+      s2 -= L[static_cast<long long>(k + 2) * n + i] * W[static_cast<long long>(k + 2) * c + t];
+      s3 -= L[static_cast<long long>(k + 3) * n + i] * W[static_cast<long long>(k + 3) * c + t];
+    }
+    for (; k < n; ++k) s0 -= L[static_cast<long long>(k) * n + i] * W[static_cast<long long>(k) * c + t];
+    const double z = (s0 + s1 + s2 + s3) / L[static_cast<long long>(i) * n + i];
+    W[static_cast<long long>(i) * c + t] = z;
+    Z[static_cast<long long>(i) * c + t] = static_cast<float>(z);
+  }
+}
+
+// preds = argmax(scores, axis=1) (first maximum, like jnp.argmax); counts preds == labels  (fewshot_lsr.py:111-112)
+__global__ void fs_accuracy_kernel(const float* __restrict__ scores, const int* __restrict__ labels, int n, int c,
+                                   int* __restrict__ preds_or_null, int* __restrict__ correct) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* row = scores + static_cast<long long>(warp) * c;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int k = lane; k < c; k += 32) {
+    const float v = row[k];
+    if (v > best || (v != v && best == best)) { best = v; arg = k; }   // NaN wins like in jnp.argmax
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    const bool take = (ob > best) || (ob == best && oa < arg) || (ob != ob && (best == best || oa < arg));
+    if (take) { best = ob; arg = oa; }
+  }
+  if (lane == 0) {
+    if (arg == 0x7fffffff) arg = 0;
+    if (preds_or_null) preds_or_null[warp] = arg;
+    if (arg == labels[warp]) atomicAdd(correct, 1);
+  }
+}
+
+static int grid_for(long long total, int threads) {
+  long long g = ceil_div_ll(total, threads);
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+}  // namespace umd
+
+using namespace umd;
+
+extern "C" int umd_fewshot_stats(const float* x, int n, int d, float* mean, float* std_plus_eps, umd_stream_t stream) {
+  UMD_REQUIRE(x && mean && std_plus_eps && n > 0 && d > 0, "umd_fewshot_stats: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fs_stats_kernel<<<static_cast<int>(ceil_div_ll(d, 32)), dim3(32, 8), 0, st>>>(x, n, d, mean, std_plus_eps);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
+extern "C" int umd_fewshot_whiten(const float* x, const float* mean, const float* std_plus_eps, int n, int d,
+                                  float bias_constant, float* out, umd_stream_t stream) {
+  UMD_REQUIRE(x && mean && std_plus_eps && out && n >= 0 && d > 0, "umd_fewshot_whiten: bad argument");
+  if (n == 0) return UMD_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n) * (d + 1);
+  fs_whiten_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, mean, std_plus_eps, n, d, bias_constant, out);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
+extern "C" int umd_fewshot_xty(const float* xw, const int* y, int n, int dim, int num_classes, float* sums_scratch,
+                               float* rhs, umd_stream_t stream) {
+  UMD_REQUIRE(xw && y && sums_scratch && rhs && n > 0 && dim > 0 && num_classes > 0, "umd_fewshot_xty: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UMD_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, sizeof(float) * (num_classes + 1ll) * dim, st));
+  fs_class_sums_kernel<<<n, 256, 0, st>>>(xw, y, n, dim, num_classes, sums_scratch);
+  FS_LAUNCH_CHECK();
+  fs_rhs_from_sums_kernel<<<grid_for(static_cast<long long>(dim) * num_classes, 256), 256, 0, st>>>(sums_scratch, dim,
+                                                                                                    num_classes, rhs);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
+extern "C" int umd_fewshot_targets(const int* y, int n, int num_classes, float* out, umd_stream_t stream) {
+  UMD_REQUIRE(y && out && n > 0 && num_classes > 0, "umd_fewshot_targets: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  fs_targets_kernel<<<grid_for(static_cast<long long>(n) * num_classes, 256), 256, 0, st>>>(y, n, num_classes, out);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
+extern "C" int umd_fewshot_matmul(const float* A, long long a_row_stride, long long a_col_stride, const float* B,
+                                  long long b_row_stride, long long b_col_stride, float* C, long long ldc, int M, int N,
+                                  int K, umd_stream_t stream) {
+  UMD_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && ldc >= N, "umd_fewshot_matmul: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int gx = static_cast<int>(ceil_div_ll(N, FS_TN)), gy = static_cast<int>(ceil_div_ll(M, FS_TM));
+  // split K until the grid fills the machine (Gram products: few tiles, K = support size)
+  int splits = 1;
+  const int tiles = gx * gy, sms = sm_count();
+  if (tiles < 2 * sms && K > 4 * FS_TK * 8) {
+    splits = static_cast<int>(ceil_div_ll(2ll * sms, tiles));
+    const int max_splits = K / (FS_TK * 8);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  int kps = static_cast<int>(ceil_div_ll(ceil_div_ll(K, splits), FS_TK)) * FS_TK;
+  splits = static_cast<int>(ceil_div_ll(K, kps));
+  if (splits > 1) UMD_CHECK_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+  fs_matmul_kernel<<<dim3(gx, gy, splits), 256, 0, st>>>(A, a_row_stride, a_col_stride, B, b_row_stride, b_col_stride, C,
+                                                         ldc, M, N, K, kps, splits > 1 ? 1 : 0);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
+extern "C" size_t umd_fewshot_solve_scratch_bytes(int n, int num_rhs) {
+  if (n <= 0 || num_rhs <= 0) return 0;
+  return sizeof(double) * (static_cast<size_t>(n) * n + static_cast<size_t>(n) * num_rhs) + 256;
+}
+extern "C" int umd_fewshot_ridge_solve(const float* gram, float l2_reg, const float* rhs, int n, int num_rhs, float* z,
+                                       void* scratch, size_t scratch_bytes, int* status, umd_stream_t stream) {
+  UMD_REQUIRE(gram && rhs && z && scratch && status && n > 0 && num_rhs > 0, "umd_fewshot_ridge_solve: bad argument");
+  UMD_REQUIRE(n <= 2048, "umd_fewshot_ridge_solve: n = %d exceeds the single-CTA factorisation limit (2048)", n);
+  UMD_REQUIRE(scratch_bytes >= umd_fewshot_solve_scratch_bytes(n, num_rhs), "umd_fewshot_ridge_solve: scratch too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* L = static_cast<double*>(scratch);
+  double* W = L + static_cast<size_t>(n) * n;
+  UMD_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+  fs_load_system_kernel<<<grid_for(static_cast<long long>(n) * n, 256), 256, 0, st>>>(gram, l2_reg, n, L);
+  FS_LAUNCH_CHECK();
+  fs_cholesky_kernel<<<1, 1024, 0, st>>>(L, n, status);
+  FS_LAUNCH_CHECK();
+  fs_trisolve_kernel<<<static_cast<int>(ceil_div_ll(num_rhs, 64)), 64, 0, st>>>(L, n, num_rhs, rhs, W, z);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
+extern "C" int umd_fewshot_accuracy(const float* scores, const int* labels, int n, int num_classes, int* preds_or_null,
+                                    int* correct, umd_stream_t stream) {
+  UMD_REQUIRE(scores && labels && correct && n > 0 && num_classes > 0, "umd_fewshot_accuracy: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UMD_CHECK_CUDA(cudaMemsetAsync(correct, 0, sizeof(int), st));
+  fs_accuracy_kernel<<<static_cast<int>(ceil_div_ll(static_cast<long long>(n) * 32, 256)), 256, 0, st>>>(
+      scores, labels, n, num_classes, preds_or_null, correct);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}

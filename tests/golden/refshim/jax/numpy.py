@@ -122,8 +122,31 @@ def where(c, a, b):
   return _w(_np.where(c, a, b))
 
 
-def mean(a, axis=None):
-  return _np.asarray(a).mean(axis=axis)
+def mean(a, axis=None, keepdims=False):
+  return _np.asarray(_np.asarray(a).mean(axis=axis, keepdims=keepdims)).view(JArr)
+
+
+def std(a, axis=None, keepdims=False):
+  return _np.asarray(_np.asarray(a).std(axis=axis, keepdims=keepdims)).view(JArr)   # population std, like jnp.std
+
+
+def pad(a, pad_width, constant_values=0):
+  return _w(_np.pad(_np.asarray(a), pad_width, constant_values=constant_values))
+
+
+def ones_like(a):
+  return _w(_np.ones_like(_np.asarray(a)))
+
+
+def argmax(a, axis=None):
+  return _w(_np.argmax(_np.asarray(a), axis=axis))
+
+
+class linalg:  # noqa: N801
+  @staticmethod
+  def eigh(a):
+    w, v = _np.linalg.eigh(_np.asarray(a))
+    return _w(w), _w(v)
 
 
 def sum(a, axis=None):  # noqa: A001
