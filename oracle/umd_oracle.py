@@ -594,3 +594,56 @@ def fewshot_acc(cache, x_test, y_test, l2_reg):
   scores = x_test @ fewshot_weights(cache, l2_reg)
   preds = scores.argmax(dim=1)
   return float((preds == y_test.long()).double().mean()), preds, scores
+
+
+# ------------------------------------------------------------------------------------------
+# Input stage after JPEG decoding.  TensorFlow owns this arithmetic in the reference
+# (tf.image.resize / random_flip_left_right / tf.cast; tensorflow is absent from /root/reference and from this image):
+# PARITY UNPINNED — restated from TensorFlow's published half-pixel-centre bilinear kernel (resize_bilinear_op.cc:
+# in = (out + 0.5) * (in_size / out_size) - 0.5, lower = max(floor(in), 0), upper = min(ceil(in), in_size - 1),
+# lerp = in - floor(in); top/bottom row interpolated along x first, then along y), all in float32.
+# ------------------------------------------------------------------------------------------
+
+
+def _bilinear_axis(in_size, out_size):
+  f32 = np.float32
+  scale = f32(in_size) / f32(out_size)
+  src = (np.arange(out_size, dtype=f32) + f32(0.5)) * scale - f32(0.5)
+  fl = np.floor(src)
+  lower = np.maximum(fl.astype(np.int64), 0)
+  upper = np.minimum(np.ceil(src).astype(np.int64), in_size - 1)
+  return lower, upper, (src - fl).astype(f32)
+
+
+def preprocess_train(images_u8, boxes=None, flips=None, size=None, vmin=-1.0, vmax=1.0, in_min=0.0, in_max=255.0,
+                     clip_values=False):
+  """configs/ae_i1k.py:64-69 after decoding: crop (pp/ops_image.py:234-238) -> get_resize (:75-85: bilinear, clip,
+  cast back to uint8) -> flip_lr (:306-314) -> value_range (pp/ops_general.py:51-60).  numpy float32, no fused
+  multiply-adds.  size: None (source size), int or (h, w).  Returns (float32 [n, Sh, Sw, C], uint8 intermediate)."""
+  f32 = np.float32
+  x = np.asarray(images_u8)
+  n, H, W, C = x.shape
+  Sh, Sw = (H, W) if size is None else ((int(size), int(size)) if np.isscalar(size) else (int(size[0]), int(size[1])))
+  out = np.empty((n, Sh, Sw, C), dtype=f32)
+  mid = np.empty((n, Sh, Sw, C), dtype=np.uint8)
+  for i in range(n):
+    y0, x0, bh, bw = (0, 0, H, W) if boxes is None else [int(v) for v in boxes[i]]
+    crop = x[i, y0:y0 + bh, x0:x0 + bw].astype(f32)
+    yl, yu, ly = _bilinear_axis(bh, Sh)
+    xl, xu, lx = _bilinear_axis(bw, Sw)
+    lx_, ly_ = lx[None, :, None], ly[:, None, None]
+    tl, tr = crop[yl][:, xl], crop[yl][:, xu]
+    bl, br = crop[yu][:, xl], crop[yu][:, xu]
+    top = tl + (tr - tl) * lx_
+    bot = bl + (br - bl) * lx_
+    v = top + (bot - top) * ly_
+    q = np.clip(v, f32(0), f32(255)).astype(np.uint8)            # tf.cast truncates
+    if flips is not None and bool(flips[i]):
+      q = q[:, ::-1]
+    mid[i] = q
+    f = (q.astype(f32) - f32(in_min)) / (f32(in_max) - f32(in_min))
+    f = f32(vmin) + f * (f32(vmax) - f32(vmin))
+    if clip_values:
+      f = np.clip(f, f32(vmin), f32(vmax))
+    out[i] = f
+  return out, mid

@@ -359,3 +359,67 @@ extern "C" int umd_fewshot_accuracy(const float* scores, const int* labels, int 
   FS_LAUNCH_CHECK();
   return UMD_OK;
 }
+
+// =========================================================================================
+// Training input stage on the GPU: the part of the reference's tf.data preprocessing string
+//   decode_jpeg_and_inception_crop(size)|flip_lr|value_range(-1, 1)        (configs/ae_i1k.py:64-69)
+// that follows JPEG decoding — crop window -> tf.image.resize(bilinear, antialias=False) -> clip + cast back to uint8
+// (pp/ops_image.py:75-85) -> horizontal flip (:306-314) -> (x - in_min) / (in_max - in_min) * (vmax - vmin) + vmin
+// (pp/ops_general.py:51-60) — fused into one pass: one thread per output value, uint8 in, fp32 out.
+// The arithmetic follows TensorFlow's half-pixel-centre bilinear kernel operation by operation with non-contracting
+// intrinsics, so the intermediate uint8 image (a truncating cast) and the fp32 result are bit-identical to an IEEE
+// single-precision evaluation in the same order.  HBM-bound: <= 1 B read + 4 B written per output value.
+// =========================================================================================
+namespace umd {
+__global__ void augment_kernel(const unsigned char* __restrict__ src, int Hs, int Ws, int C, const int* __restrict__ boxes,
+                               const unsigned char* __restrict__ flips, int Sh, int Sw, float in_min, float in_max, float vmin,
+                               float vmax, int clip_values, float* __restrict__ out, unsigned char* __restrict__ out_u8,
+                               long long total) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    long long r = i / C;
+    int ox = static_cast<int>(r % Sw);
+    r /= Sw;
+    const int oy = static_cast<int>(r % Sh);
+    const int n = static_cast<int>(r / Sh);
+    int y0 = 0, x0 = 0, bh = Hs, bw = Ws;
+    if (boxes) { y0 = boxes[4 * n]; x0 = boxes[4 * n + 1]; bh = boxes[4 * n + 2]; bw = boxes[4 * n + 3]; }
+    if (flips && flips[n]) ox = Sw - 1 - ox;
+    const float sy = static_cast<float>(bh) / static_cast<float>(Sh), sx = static_cast<float>(bw) / static_cast<float>(Sw);
+    const float fy = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(oy), 0.5f), sy), 0.5f);
+    const float fx = __fsub_rn(__fmul_rn(__fadd_rn(static_cast<float>(ox), 0.5f), sx), 0.5f);
+    const float fy0 = floorf(fy), fx0 = floorf(fx);
+    const int yl = max(static_cast<int>(fy0), 0), yu = min(static_cast<int>(ceilf(fy)), bh - 1);
+    const int xl = max(static_cast<int>(fx0), 0), xu = min(static_cast<int>(ceilf(fx)), bw - 1);
+    const float ly = __fsub_rn(fy, fy0), lx = __fsub_rn(fx, fx0);
+    const unsigned char* img = src + static_cast<long long>(n) * Hs * Ws * C;
+    auto at = [&](int y, int x) { return static_cast<float>(img[(static_cast<long long>(y0 + y) * Ws + (x0 + x)) * C + c]); };
+    const float tl = at(yl, xl), tr = at(yl, xu), bl = at(yu, xl), br = at(yu, xu);
+    const float top = __fadd_rn(tl, __fmul_rn(__fsub_rn(tr, tl), lx));
+    const float bot = __fadd_rn(bl, __fmul_rn(__fsub_rn(br, bl), lx));
+    float v = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    const unsigned char q = static_cast<unsigned char>(v);         // truncation, like tf.cast(float -> uint8)
+    if (out_u8) out_u8[i] = q;
+    float f = __fdiv_rn(__fsub_rn(static_cast<float>(q), in_min), __fsub_rn(in_max, in_min));
+    f = __fadd_rn(vmin, __fmul_rn(f, __fsub_rn(vmax, vmin)));
+    if (clip_values) f = fminf(fmaxf(f, vmin), vmax);
+    out[i] = f;
+  }
+}
+}  // namespace umd
+
+extern "C" int umd_augment_u8(const unsigned char* images, int n, int src_h, int src_w, int channels, const int* boxes_or_null,
+                              const unsigned char* flips_or_null, int out_h, int out_w, float in_min, float in_max, float vmin,
+                              float vmax, int clip_values, float* out, unsigned char* resized_u8_or_null, umd_stream_t stream) {
+  UMD_REQUIRE(images && out && n >= 0 && src_h > 0 && src_w > 0 && channels > 0 && out_h > 0 && out_w > 0, "umd_augment_u8: bad argument");
+  UMD_REQUIRE(in_max != in_min, "umd_augment_u8: in_max == in_min");
+  if (n == 0) return UMD_OK;
+  const long long total = static_cast<long long>(n) * out_h * out_w * channels;
+  augment_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      images, src_h, src_w, channels, boxes_or_null, flips_or_null, out_h, out_w, in_min, in_max, vmin, vmax, clip_values, out,
+      resized_u8_or_null, total);
+  FS_LAUNCH_CHECK();
+  return UMD_OK;
+}
