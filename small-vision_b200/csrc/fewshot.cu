@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(1024) fs_cholesky_kernel(double* __restrict__ 
     for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
       const double v = (i == j) ? dj : L[static_cast<long long>(i) * n + j] / dj;
       L[static_cast<long long>(i) * n + j] = v;
+      L[static_cast<long long>(j) * n + i] = v;      // L^T in the upper triangle: the back substitution reads rows
       col[i] = v;
     }
     __syncthreads();
@@ -200,37 +201,45 @@ __global__ void __launch_bounds__(1024) fs_cholesky_kernel(double* __restrict__ 
     __syncthreads();
   }
 }
-// forward then backward substitution, one right-hand side per thread; Z overwrites R (fp32 in / out, fp64 inside via W)
-__global__ void fs_trisolve_kernel(const double* __restrict__ L, int n, int c, const float* __restrict__ R,
-                                   double* __restrict__ W /*[n, c] scratch*/, float* __restrict__ Z) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= c) return;
-  for (int i = 0; i < n; ++i) {                       // L w = r
-    const double* Li = L + static_cast<long long>(i) * n;
-    double s0 = static_cast<double>(R[static_cast<long long>(i) * c + t]), s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = 0;
-    for (; k + 4 <= i; k += 4) {
-      s0 -= Li[k] * W[static_cast<long long>(k) * c + t];
-      s1 -= Li[k + 1] * W[static_cast<long long>(k + 1) * c + t];
-      s2 -= Li[k + 2] * W[static_cast<long long>(k + 2) * c + t];
-      s3 -= Li[k + 3] * W[static_cast<long long>(k + 3) * c + t];
+// Forward then backward substitution.  A CTA (4 warps) owns `cols` right-hand sides (32, 16 or 8: whatever keeps the
+// fp64 solution block W[n][cols] in shared memory); the dot product of row i is split over 4 * 32 / cols thread groups
+// (k strided), reduced by shuffles inside a warp and through shared memory across warps.  Rows of L (and of L^T, kept
+// in the upper triangle by the factorisation) are read contiguously and broadcast.
+__global__ void __launch_bounds__(128)
+fs_trisolve_kernel(const double* __restrict__ L, int n, int c, int cols, const float* __restrict__ R, float* __restrict__ Z) {
+  extern __shared__ double fs_sm[];
+  double* W = fs_sm;                       // [n][cols]
+  double* part = fs_sm + static_cast<size_t>(n) * cols;   // [4][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = lane % cols, sub = lane / cols, per_warp = 32 / cols;
+  const int kg = warp * per_warp + sub, KG = 4 * per_warp;
+  const int t = blockIdx.x * cols + col;
+  const bool live = t < c;
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int step = 0; step < n; ++step) {
+      const int i = pass == 0 ? step : n - 1 - step;
+      const double* Li = L + static_cast<long long>(i) * n;
+      const int k_lo = pass == 0 ? 0 : i + 1, k_hi = pass == 0 ? i : n;
+      double s0 = 0.0, s1 = 0.0;
+      int k = k_lo + kg;
+      for (; k + KG < k_hi; k += 2 * KG) {
+        s0 += Li[k] * W[static_cast<size_t>(k) * cols + col];
+        s1 += Li[k + KG] * W[static_cast<size_t>(k + KG) * cols + col];
+      }
+      if (k < k_hi) s0 += Li[k] * W[static_cast<size_t>(k) * cols + col];
+      double s = s0 + s1;
+      for (int o = cols; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (sub == 0) part[warp * 32 + col] = s;
+      __syncthreads();
+      if (warp == 0 && sub == 0) {
+        const double r = pass == 0 ? (live ? static_cast<double>(R[static_cast<long long>(i) * c + t]) : 0.0)
+                                   : W[static_cast<size_t>(i) * cols + col];
+        const double w = (r - (part[col] + part[32 + col] + part[64 + col] + part[96 + col])) / Li[i];
+        W[static_cast<size_t>(i) * cols + col] = w;
+        if (pass == 1 && live) Z[static_cast<long long>(i) * c + t] = static_cast<float>(w);
+      }
+      __syncthreads();
     }
-    for (; k < i; ++k) s0 -= Li[k] * W[static_cast<long long>(k) * c + t];
-    W[static_cast<long long>(i) * c + t] = (s0 + s1 + s2 + s3) / Li[i];
-  }
-  for (int i = n - 1; i >= 0; --i) {                  // L^T z = w
-    double s0 = W[static_cast<long long>(i) * c + t], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int k = i + 1;
-    for (; k + 4 <= n; k += 4) {
-      s0 -= L[static_cast<long long>(k) * n + i] * W[static_cast<long long>(k) * c + t];
-      s1 -= L[static_cast<long long>(k + 1) * n + i] * W[static_cast<long long>(k + 1) * c + t];
-      s2 -= L[static_cast<long long>(k + 2) * n + i] * W[static_cast<long long>(k + 2) * c + t];
-      s3 -= L[static_cast<long long>(k + 3) * n + i] * W[static_cast<long long>(k + 3) * c + t];
-    }
-    for (; k < n; ++k) s0 -= L[static_cast<long long>(k) * n + i] * W[static_cast<long long>(k) * c + t];
-    const double z = (s0 + s1 + s2 + s3) / L[static_cast<long long>(i) * n + i];
-    W[static_cast<long long>(i) * c + t] = z;
-    Z[static_cast<long long>(i) * c + t] = static_cast<float>(z);
   }
 }
 
@@ -330,7 +339,8 @@ extern "C" int umd_fewshot_matmul(const float* A, long long a_row_stride, long l
 }
 extern "C" size_t umd_fewshot_solve_scratch_bytes(int n, int num_rhs) {
   if (n <= 0 || num_rhs <= 0) return 0;
-  return sizeof(double) * (static_cast<size_t>(n) * n + static_cast<size_t>(n) * num_rhs) + 256;
+  (void)num_rhs;
+  return sizeof(double) * (static_cast<size_t>(n) * n) + 256;
 }
 extern "C" int umd_fewshot_ridge_solve(const float* gram, float l2_reg, const float* rhs, int n, int num_rhs, float* z,
                                        void* scratch, size_t scratch_bytes, int* status, umd_stream_t stream) {
@@ -339,13 +349,21 @@ extern "C" int umd_fewshot_ridge_solve(const float* gram, float l2_reg, const fl
   UMD_REQUIRE(scratch_bytes >= umd_fewshot_solve_scratch_bytes(n, num_rhs), "umd_fewshot_ridge_solve: scratch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* L = static_cast<double*>(scratch);
-  double* W = L + static_cast<size_t>(n) * n;
   UMD_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   fs_load_system_kernel<<<grid_for(static_cast<long long>(n) * n, 256), 256, 0, st>>>(gram, l2_reg, n, L);
   FS_LAUNCH_CHECK();
   fs_cholesky_kernel<<<1, 1024, 0, st>>>(L, n, status);
   FS_LAUNCH_CHECK();
-  fs_trisolve_kernel<<<static_cast<int>(ceil_div_ll(num_rhs, 64)), 64, 0, st>>>(L, n, num_rhs, rhs, W, z);
+  int cols = 32;
+  while (cols > 8 && (static_cast<size_t>(n) * cols + 128) * sizeof(double) > 200 * 1024) cols >>= 1;
+  const size_t smem = (static_cast<size_t>(n) * cols + 128) * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    UMD_CHECK_CUDA(cudaFuncSetAttribute(fs_trisolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  UMD_REQUIRE(smem <= 227 * 1024, "umd_fewshot_ridge_solve: n = %d does not fit the shared-memory solve", n);
+  fs_trisolve_kernel<<<static_cast<int>(ceil_div_ll(num_rhs, cols)), 128, smem, st>>>(L, n, num_rhs, cols, rhs, z);
   FS_LAUNCH_CHECK();
   return UMD_OK;
 }

@@ -4,8 +4,8 @@ MAE reconstruction with its pixel mask, and the denoising evaluation loss.  Same
 (`train_state`, `batch`) and return values as the reference; the random draws the reference takes from
 `train_state["rng"]` may be supplied in `batch["_rand"]` (keys "noise", "t", "mae_noise") to reproduce a run.
 
-The few-shot ridge probe that consumes `pre_logits` (evaluators/fewshot_lsr.py) and the latent-diffusion VAE
-(`vae_encode` / `vae_decode`) are not part of this path: with latents, pass the encoded batch.
+The few-shot ridge probe that consumes `pre_logits` (evaluators/fewshot_lsr.py) lives in fewshot.py.  The
+latent-diffusion VAE (`vae_encode` / `vae_decode`) is not part of this path: with latents, pass the encoded batch.
 """
 from __future__ import annotations
 
