@@ -160,9 +160,7 @@ fs_matmul_kernel(const float* __restrict__ A, long long a_rs, long long a_cs, co
 
 // -----------------------------------------------------------------------------------------
 // Ridge solve: (G + l2 I) Z = R for symmetric positive semi-definite G [n, n] (fp32 in) and R [n, c] (fp32 in, Z out).
-// fp64 work copy; one CTA factorises (right-looking Cholesky, column scale + trailing rank-1 update per step; n <= ~1k
-// keeps the matrix L2-resident and the whole factorisation at a few ms), then the two triangular solves run one
-// right-hand side per thread (coalesced across threads, rows of L broadcast).
+// fp64 work copy (L2-resident for n <= ~1k); blocked Cholesky factorisation, then forward / backward substitution.
 // -----------------------------------------------------------------------------------------
 __global__ void fs_load_system_kernel(const float* __restrict__ G, float l2, int n, double* __restrict__ L) {
   const long long total = static_cast<long long>(n) * n;
@@ -174,71 +172,132 @@ __global__ void fs_load_system_kernel(const float* __restrict__ G, float l2, int
     L[i] = v + (r == c ? static_cast<double>(l2) : 0.0);
   }
 }
-__global__ void __launch_bounds__(1024) fs_cholesky_kernel(double* __restrict__ L, int n, int* __restrict__ status) {
-  __shared__ double col[2048];           // column j below the diagonal, scaled (n <= 2048)
-  __shared__ double diag;
-  for (int j = 0; j < n; ++j) {
-    if (threadIdx.x == 0) {
-      const double d = L[static_cast<long long>(j) * n + j];
-      if (!(d > 0.0)) { *status = j + 1; diag = 1.0; } else diag = sqrt(d);
+// Blocked right-looking Cholesky, NB = 32, three kernels per block column (the launches are the grid-wide barriers):
+//   diag  : one CTA factorises the 32 x 32 diagonal block in shared memory;
+//   panel : rows below it, X = A L_kk^-T, one row per thread out of a padded shared tile;
+//   update: every lower-triangular 32 x 32 tile pair of the trailing matrix, C -= P_i P_j^T (K = 32 from shared memory).
+// A last pass mirrors L into the upper triangle so that the back substitution reads rows.
+constexpr int FS_NB = 32;
+__global__ void __launch_bounds__(1024) fs_chol_diag_kernel(double* __restrict__ L, int n, int kb, int* __restrict__ status) {
+  __shared__ double a[FS_NB][FS_NB + 1];
+  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+  const int nb = min(FS_NB, n - kb);
+  a[r][c] = (r < nb && c < nb) ? L[static_cast<long long>(kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
+  __syncthreads();
+  for (int j = 0; j < nb; ++j) {
+    if (r == j && c == j) {
+      const double d = a[j][j];
+      if (!(d > 0.0)) { *status = kb + j + 1; a[j][j] = 1.0; } else a[j][j] = sqrt(d);
     }
     __syncthreads();
-    const double dj = diag;
-    for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
-      const double v = (i == j) ? dj : L[static_cast<long long>(i) * n + j] / dj;
-      L[static_cast<long long>(i) * n + j] = v;
-      L[static_cast<long long>(j) * n + i] = v;      // L^T in the upper triangle: the back substitution reads rows
-      col[i] = v;
-    }
+    if (c == j && r > j) a[r][j] /= a[j][j];
     __syncthreads();
-    // trailing update of the lower triangle: L[i][k] -= col[i] * col[k], j < k <= i < n; one warp per row, lanes along k
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int i = j + 1 + warp; i < n; i += nwarps) {
-      const double ci = col[i];
-      double* Li = L + static_cast<long long>(i) * n;
-      for (int k = j + 1 + lane; k <= i; k += 32) Li[k] -= ci * col[k];
-    }
+    if (c > j && r >= c) a[r][c] -= a[r][j] * a[c][j];
     __syncthreads();
+  }
+  if (r < nb && c <= r) L[static_cast<long long>(kb + r) * n + kb + c] = a[r][c];
+}
+__global__ void __launch_bounds__(128) fs_chol_panel_kernel(double* __restrict__ L, int n, int kb) {
+  __shared__ double lkk[FS_NB][FS_NB + 1];
+  __shared__ double rows[128][FS_NB + 1];
+  const int nb = min(FS_NB, n - kb);
+  const int row0 = kb + nb + blockIdx.x * 128;
+  for (int e = threadIdx.x; e < FS_NB * FS_NB; e += 128) {
+    const int r = e >> 5, c = e & 31;
+    lkk[r][c] = (r < nb && c <= r) ? L[static_cast<long long>(kb + r) * n + kb + c] : (r == c ? 1.0 : 0.0);
+  }
+  for (int e = threadIdx.x; e < 128 * FS_NB; e += 128) {
+    const int r = e >> 5, c = e & 31;
+    rows[r][c] = (row0 + r < n && c < nb) ? L[static_cast<long long>(row0 + r) * n + kb + c] : 0.0;
+  }
+  __syncthreads();
+  double* x = rows[threadIdx.x];
+  for (int c = 0; c < nb; ++c) {
+    double s = x[c];
+    for (int m = 0; m < c; ++m) s -= x[m] * lkk[c][m];
+    x[c] = s / lkk[c][c];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 128 * FS_NB; e += 128) {
+    const int r = e >> 5, c = e & 31;
+    if (row0 + r < n && c < nb) L[static_cast<long long>(row0 + r) * n + kb + c] = rows[r][c];
+  }
+}
+__global__ void __launch_bounds__(1024) fs_chol_update_kernel(double* __restrict__ L, int n, int kb) {
+  if (blockIdx.x > blockIdx.y) return;             // lower-triangular tile pairs only (x = column block, y = row block)
+  __shared__ double pa[FS_NB][FS_NB + 1], pb[FS_NB][FS_NB + 1];
+  const int r = threadIdx.x >> 5, c = threadIdx.x & 31;
+  const int base = kb + FS_NB;                      // only called while a full block column precedes the trailing matrix
+  const int gi = base + blockIdx.y * FS_NB + r, gj = base + blockIdx.x * FS_NB + r;
+  pa[r][c] = gi < n ? L[static_cast<long long>(gi) * n + kb + c] : 0.0;
+  pb[r][c] = gj < n ? L[static_cast<long long>(gj) * n + kb + c] : 0.0;
+  __syncthreads();
+  const int oi = base + blockIdx.y * FS_NB + r, oj = base + blockIdx.x * FS_NB + c;
+  if (oi >= n || oj > oi) return;
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < FS_NB; ++k) s += pa[r][k] * pb[c][k];
+  L[static_cast<long long>(oi) * n + oj] -= s;
+}
+__global__ void fs_mirror_kernel(double* __restrict__ L, int n) {
+  const long long total = static_cast<long long>(n) * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / n), c = static_cast<int>(i - static_cast<long long>(r) * n);
+    if (c > r) L[i] = L[static_cast<long long>(c) * n + r];
   }
 }
 // Forward then backward substitution.  A CTA (4 warps) owns `cols` right-hand sides (32, 16 or 8: whatever keeps the
 // fp64 solution block W[n][cols] in shared memory); the dot product of row i is split over 4 * 32 / cols thread groups
 // (k strided), reduced by shuffles inside a warp and through shared memory across warps.  Rows of L (and of L^T, kept
-// in the upper triangle by the factorisation) are read contiguously and broadcast.
+// in the upper triangle by the factorisation) are staged four at a time into shared memory with coalesced loads, so the
+// L2 latency is paid once per four rows instead of once per element.
+constexpr int FS_RING = 4;
 __global__ void __launch_bounds__(128)
 fs_trisolve_kernel(const double* __restrict__ L, int n, int c, int cols, const float* __restrict__ R, float* __restrict__ Z) {
   extern __shared__ double fs_sm[];
-  double* W = fs_sm;                       // [n][cols]
-  double* part = fs_sm + static_cast<size_t>(n) * cols;   // [4][32]
+  double* W = fs_sm;                                        // [n][cols]
+  double* ring = W + static_cast<size_t>(n) * cols;         // [FS_RING][n]
+  double* part = ring + static_cast<size_t>(FS_RING) * n;   // [4][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = lane % cols, sub = lane / cols, per_warp = 32 / cols;
   const int kg = warp * per_warp + sub, KG = 4 * per_warp;
   const int t = blockIdx.x * cols + col;
   const bool live = t < c;
   for (int pass = 0; pass < 2; ++pass) {
-    for (int step = 0; step < n; ++step) {
-      const int i = pass == 0 ? step : n - 1 - step;
-      const double* Li = L + static_cast<long long>(i) * n;
-      const int k_lo = pass == 0 ? 0 : i + 1, k_hi = pass == 0 ? i : n;
-      double s0 = 0.0, s1 = 0.0;
-      int k = k_lo + kg;
-      for (; k + KG < k_hi; k += 2 * KG) {
-        s0 += Li[k] * W[static_cast<size_t>(k) * cols + col];
-        s1 += Li[k + KG] * W[static_cast<size_t>(k + KG) * cols + col];
-      }
-      if (k < k_hi) s0 += Li[k] * W[static_cast<size_t>(k) * cols + col];
-      double s = s0 + s1;
-      for (int o = cols; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (sub == 0) part[warp * 32 + col] = s;
-      __syncthreads();
-      if (warp == 0 && sub == 0) {
-        const double r = pass == 0 ? (live ? static_cast<double>(R[static_cast<long long>(i) * c + t]) : 0.0)
-                                   : W[static_cast<size_t>(i) * cols + col];
-        const double w = (r - (part[col] + part[32 + col] + part[64 + col] + part[96 + col])) / Li[i];
-        W[static_cast<size_t>(i) * cols + col] = w;
-        if (pass == 1 && live) Z[static_cast<long long>(i) * c + t] = static_cast<float>(w);
+    for (int step0 = 0; step0 < n; step0 += FS_RING) {
+      const int rows_here = min(FS_RING, n - step0);
+      for (int rr = 0; rr < rows_here; ++rr) {              // stage rows (diagonal element included)
+        const int i = pass == 0 ? step0 + rr : n - 1 - (step0 + rr);
+        const double* Li = L + static_cast<long long>(i) * n;
+        const int lo = pass == 0 ? 0 : i, hi = pass == 0 ? i + 1 : n;
+        for (int k = lo + threadIdx.x; k < hi; k += 128) ring[rr * n + k] = Li[k];
       }
       __syncthreads();
+      for (int rr = 0; rr < rows_here; ++rr) {
+        const int i = pass == 0 ? step0 + rr : n - 1 - (step0 + rr);
+        const double* Li = ring + rr * n;
+        const int k_lo = pass == 0 ? 0 : i + 1, k_hi = pass == 0 ? i : n;
+        double s0 = 0.0, s1 = 0.0;
+        int k = k_lo + kg;
+        for (; k + KG < k_hi; k += 2 * KG) {
+          s0 += Li[k] * W[static_cast<size_t>(k) * cols + col];
+          s1 += Li[k + KG] * W[static_cast<size_t>(k + KG) * cols + col];
+        }
+        if (k < k_hi) s0 += Li[k] * W[static_cast<size_t>(k) * cols + col];
+        double s = s0 + s1;
+        for (int o = cols; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (sub == 0) part[warp * 32 + col] = s;
+        __syncthreads();
+        if (warp == 0 && sub == 0) {
+          const double r = pass == 0 ? (live ? static_cast<double>(R[static_cast<long long>(i) * c + t]) : 0.0)
+                                     : W[static_cast<size_t>(i) * cols + col];
+          const double w = (r - (part[col] + part[32 + col] + part[64 + col] + part[96 + col])) / Li[i];
+          W[static_cast<size_t>(i) * cols + col] = w;
+          if (pass == 1 && live) Z[static_cast<long long>(i) * c + t] = static_cast<float>(w);
+        }
+        __syncthreads();
+      }
     }
   }
 }
@@ -345,18 +404,30 @@ extern "C" size_t umd_fewshot_solve_scratch_bytes(int n, int num_rhs) {
 extern "C" int umd_fewshot_ridge_solve(const float* gram, float l2_reg, const float* rhs, int n, int num_rhs, float* z,
                                        void* scratch, size_t scratch_bytes, int* status, umd_stream_t stream) {
   UMD_REQUIRE(gram && rhs && z && scratch && status && n > 0 && num_rhs > 0, "umd_fewshot_ridge_solve: bad argument");
-  UMD_REQUIRE(n <= 2048, "umd_fewshot_ridge_solve: n = %d exceeds the single-CTA factorisation limit (2048)", n);
+  UMD_REQUIRE(n <= 2048, "umd_fewshot_ridge_solve: n = %d exceeds the shared-memory solve limit (2048)", n);
   UMD_REQUIRE(scratch_bytes >= umd_fewshot_solve_scratch_bytes(n, num_rhs), "umd_fewshot_ridge_solve: scratch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* L = static_cast<double*>(scratch);
   UMD_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
   fs_load_system_kernel<<<grid_for(static_cast<long long>(n) * n, 256), 256, 0, st>>>(gram, l2_reg, n, L);
   FS_LAUNCH_CHECK();
-  fs_cholesky_kernel<<<1, 1024, 0, st>>>(L, n, status);
+  for (int kb = 0; kb < n; kb += FS_NB) {
+    fs_chol_diag_kernel<<<1, 1024, 0, st>>>(L, n, kb, status);
+    FS_LAUNCH_CHECK();
+    const int below = n - kb - FS_NB;
+    if (below <= 0) break;
+    fs_chol_panel_kernel<<<static_cast<int>(ceil_div_ll(below, 128)), 128, 0, st>>>(L, n, kb);
+    FS_LAUNCH_CHECK();
+    const int nblk = static_cast<int>(ceil_div_ll(below, FS_NB));
+    fs_chol_update_kernel<<<dim3(nblk, nblk), 1024, 0, st>>>(L, n, kb);
+    FS_LAUNCH_CHECK();
+  }
+  fs_mirror_kernel<<<grid_for(static_cast<long long>(n) * n, 256), 256, 0, st>>>(L, n);
   FS_LAUNCH_CHECK();
   int cols = 32;
-  while (cols > 8 && (static_cast<size_t>(n) * cols + 128) * sizeof(double) > 200 * 1024) cols >>= 1;
-  const size_t smem = (static_cast<size_t>(n) * cols + 128) * sizeof(double);
+  auto smem_for = [&](int cc) { return (static_cast<size_t>(n) * (cc + FS_RING) + 128) * sizeof(double); };
+  while (cols > 8 && smem_for(cols) > 227 * 1024) cols >>= 1;
+  const size_t smem = smem_for(cols);
   static bool attr_set = false;
   if (!attr_set) {
     UMD_CHECK_CUDA(cudaFuncSetAttribute(fs_trisolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
