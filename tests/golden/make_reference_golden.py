@@ -11,7 +11,8 @@ same draws can be given to the oracle and to the CUDA path.  Parameter gradients
 (central, fp64) along seeded parameter directions; the oracle's autograd gradient must reproduce those slopes.
 
 Runs only in the build container (it needs /root/reference):
-  python tests/golden/make_reference_golden.py
+  python tests/golden/make_reference_golden.py            # reference_golden.pt (step cases + diffusion vectors)
+  python tests/golden/make_reference_golden.py sampler    # reference_sampler_golden.pt (create_apply_fn + DDIM loop)
 """
 import ast
 import hashlib
@@ -39,7 +40,11 @@ CASES = {
                dict(mask_ratio=0.0, mask_ratio_no_noise=0.75, no_noise_prob=0.0, use_labels=True), 4, 4),
     "umd_lbl_s4": (dict(variant="S/4", adaln=True, num_classes=10, depth=1, dec_depth=1),
                    dict(mask_ratio=0.375, mask_ratio_no_noise=0.75, no_noise_prob=0.5, use_labels=True), 4, 2),
+    # Latent-UMD recipe (configs/ae_i1k.py:45-51): 32x32x4 latents, patch 2, linear beta schedule
+    "latent_s2": (dict(variant="S/2", adaln=True, depth=1, dec_depth=1, img_size=32, channels=4),
+                  dict(mask_ratio=0.375, mask_ratio_no_noise=0.75, no_noise_prob=0.5, use_labels=False), 4, 2),
 }
+SCHEDULE = {"latent_s2": "linear"}     # beta schedule per case (default cosine)
 PARAM_SEED, BATCH_SEED, DIR_SEED = 0, 100, 4242
 FD_STEP = 1e-3
 GROUP_DIRECTIONS = 3   # whole-tree directions; plus one direction per top-level parameter group
@@ -58,9 +63,12 @@ def load_reference():
   assert ae.__file__.startswith(REF) and gd.__file__.startswith(REF)
   path = os.path.join(REF, "big_vision", "trainers", "train_ae.py")
   tree = ast.parse(open(path).read(), filename=path)
-  node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "loss_fn")
-  code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
-  return ae, gd, code, (node.lineno, node.end_lineno)
+  def lift(fn_name):
+    node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == fn_name)
+    return compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), (node.lineno, node.end_lineno)
+  code, lines = lift("loss_fn")
+  load_reference.lift = lift
+  return ae, gd, code, lines
 
 
 class Config(dict):
@@ -124,7 +132,7 @@ def build_case(name, ae, gdm, loss_code):
                              device="cpu")
   params = tree64(params_t)
   model = ae.Model(**mkw)                                   # the reference's factory (ae.py:220-222)
-  gd = gdm.create_gaussian_diffusion("cosine", 1000)        # gaussian_diffusion.py:32-66
+  gd = gdm.create_gaussian_diffusion(SCHEDULE.get(name, "cosine"), 1000)        # gaussian_diffusion.py:32-66
   n_clean = B - n_noise
   assert n_clean == int(B * tkw["no_noise_prob"])
   images = jnp.asarray(np64(batch["image"]))
@@ -134,6 +142,8 @@ def build_case(name, ae, gdm, loss_code):
   x_t = gdm.q_sample(gd=gd, x_start=x0_noise, t=t, noise=noise)         # gaussian_diffusion.py:84-98
   labels = jnp.asarray(batch["label"][:n_noise].numpy().astype(np.int32)) if tkw["use_labels"] else None
   has_lbl = mkw.get("num_classes") is not None
+  img_size, channels = mkw.get("img_size", 64), mkw.get("channels", 3)
+  patch = int(mkw["variant"].split("/")[1])
 
   def keys():
     drop = rand.get("label_drop_noise")
@@ -145,7 +155,7 @@ def build_case(name, ae, gdm, loss_code):
         cfg_rng_noise=jax.Key({"bernoulli": np64(drop.double()) if drop is not None else np.zeros((n_noise,))}))
 
   def reference_loss(p):
-    env = dict(jnp=jnp, model=model, config=Config(diffusion_space=(64, 64, 3), **tkw), B=B, n_noise=n_noise,
+    env = dict(jnp=jnp, model=model, config=Config(diffusion_space=(img_size, img_size, channels), **tkw), B=B, n_noise=n_noise,
                n_no_noise=n_clean, x_0_noise=x0_noise, x_0_no_noise=x0_clean, x_t_noise=x_t, batched_t=t,
                labels_t=labels, noise=noise, **keys())
     exec(loss_code, env)                                     # defines the reference's loss_fn in env
@@ -160,12 +170,12 @@ def build_case(name, ae, gdm, loss_code):
     pred, o = model.apply({"params": params}, x0_clean, t=jnp.zeros((n_clean, 1), dtype=jnp.int32), train=True,
                           mask=tkw["mask_ratio_no_noise"],
                           rngs={"dropout": k["rng_model"], "cfg": k["cfg_rng"], "mae_noise": k["mae_noise_rng"]})
-    out["clean"] = pack(pred, o)
+    out["clean"] = pack(pred, o, patch)
   if n_noise > 0:
     pred, o = model.apply({"params": params}, x_t, t=t + 1, y=labels, train=True, mask=tkw["mask_ratio"],
                           rngs={"dropout": k["rng_model_noise"], "cfg": k["cfg_rng_noise"],
                                 "mae_noise": k["mae_noise_rng_noise"]})
-    out["noise"] = pack(pred, o)
+    out["noise"] = pack(pred, o, patch)
   slopes = []
   for grp, d in directions(params_t):
     lp, lm = reference_loss(shifted(params, d, FD_STEP)), reference_loss(shifted(params, d, -FD_STEP))
@@ -182,14 +192,14 @@ def build_case(name, ae, gdm, loss_code):
   return out
 
 
-def pack(pred, o):
+def pack(pred, o, patch=4):
   pred = np.asarray(pred)
   d = {"pred0": torch.from_numpy(pred[0]).float(),                                  # sample 0 in full
        "pred_sample_means": torch.from_numpy(pred.mean(axis=(1, 2))).double(),      # [n, 2C]
        "pred_abs_mean": float(np.abs(pred).mean()),
        "pre_logits": torch.from_numpy(np.asarray(o["pre_logits"])).double()}
   if o["mask"] is not None:
-    m = np.asarray(o["mask"])[:, ::4, ::4, 0]                                       # one value per 4x4 patch
+    m = np.asarray(o["mask"])[:, ::patch, ::patch, 0]                               # one value per patch
     assert set(np.unique(m)) <= {0.0, 1.0}
     d["patch_mask"] = torch.from_numpy(m.reshape(m.shape[0], -1).astype(np.uint8))
   return d
@@ -242,8 +252,47 @@ def diffusion_vectors(gdm):
   return out
 
 
+SAMPLER = dict(case="dit_s4", n=2, steps=4, eta=0.3, ys=(3, 7), noise_seed=21,
+               variants=((1.5, True), (2.0, False), (None, True)))   # (cfg_scale, eps_pred)
+
+
+def sampler_vectors(ae, gdm):
+  """The whole sampler as the reference wires it: `create_apply_fn` (train_ae.py:472-483, lifted like loss_fn: the model
+  at t + 1 on `ema_params`, eps head or x0 head converted) under `ddim_sample_loop` (gaussian_diffusion.py:213-280) with
+  classifier-free guidance, on the dit_s4 parameters."""
+  import jax
+  import jax.numpy as jnp
+  code, lines = load_reference.lift("create_apply_fn")
+  mkw = CASES[SAMPLER["case"]][0]
+  engine_model, _ = U.make_models(**mkw)
+  params = tree64(U.cpu_tree(U.perturb_init(engine_model, PARAM_SEED, "cpu")))
+  model = ae.Model(**mkw)
+  gd = gdm.create_gaussian_diffusion("cosine", 1000)
+  env = dict(model=model, config=Config(diffusion_space=(64, 64, 3)), _predict_eps_from_xstart=gdm._predict_eps_from_xstart)
+  exec(code, env)
+  n, steps = SAMPLER["n"], SAMPLER["steps"]
+  g = torch.Generator().manual_seed(SAMPLER["noise_seed"])
+  noises = [torch.randn(n, 64, 64, 3, generator=g) for _ in range(steps + 2)]
+  ys = jnp.asarray(np.array(SAMPLER["ys"], dtype=np.int32))
+  out = {"lines": lines, "noise_digest": digest(torch.stack(noises)), "samples": []}
+  for cfg_scale, eps_pred in SAMPLER["variants"]:
+    apply_fn = env["create_apply_fn"]({"ema_params": params, "gd": gd}, eps_pred=eps_pred)
+    ret, _ = gdm.ddim_sample_loop(gd, apply_fn, jax.Key({"normal": [np64(z) for z in noises]}), np.zeros((n, 64, 64, 3)),
+                                  ys=ys if cfg_scale is not None else None, sampling_steps=steps, cfg_scale=cfg_scale,
+                                  eta=SAMPLER["eta"])
+    out["samples"].append(torch.from_numpy(np.asarray(ret["sample"])).float())
+    print("sampler", cfg_scale, eps_pred, float(np.abs(np.asarray(ret["sample"])).mean()))
+  return out
+
+
 def main():
   ae, gdm, loss_code, loss_lines = load_reference()
+  if sys.argv[1:] == ["sampler"]:
+    path = os.path.join(HERE, "reference_sampler_golden.pt")
+    torch.save({"provenance": "create_apply_fn + ddim_sample_loop of the reference executed over tests/golden/refshim",
+                "sampler": sampler_vectors(ae, gdm)}, path)
+    print(path, os.path.getsize(path), "bytes")
+    return
   gold = {"provenance": "reference source executed over tests/golden/refshim (numpy fp64); loss_fn = train_ae.py:%d-%d"
                         % loss_lines,
           "fd_step": FD_STEP, "cases": {}, "diffusion": diffusion_vectors(gdm)}

@@ -29,8 +29,8 @@ def rebuild(name):
   return model, ocfg, tkw, params, batch, rand, n_noise, want
 
 
-def oracle_loss(params64, ocfg, tkw, batch, rand, n_noise):
-  gd = O.gaussian_diffusion_tables("cosine", 1000)
+def oracle_loss(params64, ocfg, tkw, batch, rand, n_noise, schedule="cosine"):
+  gd = O.gaussian_diffusion_tables(schedule, 1000)
   img = batch["image"].to(F64)
   x0n, x0c = img[:n_noise], img[n_noise:]
   x_t = O.q_sample(gd, x0n, rand["t"], rand["noise"].to(F64))
@@ -43,7 +43,7 @@ def to64(tree, grad=False):
   return {k: (to64(v, grad) if isinstance(v, dict) else v.double().clone().requires_grad_(grad)) for k, v in tree.items()}
 
 
-def check_branch(aux, br, want, C=3):
+def check_branch(aux, br, want, patch=4):
   pred = aux[f"pred_{br}"].detach()
   out = aux[f"out_{br}"]
   assert U.rel_l2(pred[0], want["pred0"]) <= 1e-6            # the fixture stores sample 0 as float32
@@ -51,7 +51,7 @@ def check_branch(aux, br, want, C=3):
   assert abs(float(pred.abs().mean()) - want["pred_abs_mean"]) <= 1e-11
   assert torch.allclose(out["pre_logits"].detach(), want["pre_logits"], rtol=0, atol=1e-10)
   if "patch_mask" in want:
-    seq = out["mask"][:, ::4, ::4, 0].reshape(pred.shape[0], -1)
+    seq = out["mask"][:, ::patch, ::patch, 0].reshape(pred.shape[0], -1)
     assert torch.equal(seq.to(torch.uint8), want["patch_mask"])           # bit-exact, ties included
     assert torch.equal((out["ids_restore"] >= (seq == 0).sum(1, keepdim=True)).to(torch.uint8), want["patch_mask"])
   else:
@@ -61,12 +61,12 @@ def check_branch(aux, br, want, C=3):
 @pytest.mark.parametrize("name", sorted(RG.CASES))
 def test_forward_and_loss_match_reference_source(name):
   model, ocfg, tkw, params, batch, rand, n_noise, want = rebuild(name)
-  loss, aux, x_t = oracle_loss(to64(params), ocfg, tkw, batch, rand, n_noise)
+  loss, aux, x_t = oracle_loss(to64(params), ocfg, tkw, batch, rand, n_noise, RG.SCHEDULE.get(name, "cosine"))
   assert U.rel_l2(x_t, want["x_t"]) <= 1e-6
   assert abs(float(loss) - want["loss"]) <= 1e-11 * abs(want["loss"]) + 1e-12, (float(loss), want["loss"])
   for br in ("noise", "clean"):
     if br in want:
-      check_branch(aux, br, want[br])
+      check_branch(aux, br, want[br], ocfg["patch_size"][0])
     else:
       assert f"pred_{br}" not in aux
 
@@ -77,7 +77,7 @@ def test_autograd_gradient_reproduces_reference_loss_slopes(name):
   directions d over the whole tree and over each top-level parameter group."""
   model, ocfg, tkw, params, batch, rand, n_noise, want = rebuild(name)
   p64 = to64(params, grad=True)
-  loss, _, _ = oracle_loss(p64, ocfg, tkw, batch, rand, n_noise)
+  loss, _, _ = oracle_loss(p64, ocfg, tkw, batch, rand, n_noise, RG.SCHEDULE.get(name, "cosine"))
   loss.backward()
   grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in RG.flatten(p64).items()}
   gnorm = float(torch.sqrt(sum((g ** 2).sum() for g in grads.values())))
@@ -130,3 +130,22 @@ def test_q_sample_and_ddim_match_reference_source():
     if key.startswith("timesteps_"):
       _, n, s = key.split("_")
       assert O.ddim_timesteps(int(n), int(s)) == v.tolist(), key
+
+
+def test_sampler_matches_reference_source():
+  """create_apply_fn (train_ae.py:472-483) under ddim_sample_loop with classifier-free guidance, both heads."""
+  S = RG.SAMPLER
+  gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sampler_golden.pt"))["sampler"]
+  mkw = RG.CASES[S["case"]][0]
+  model, ocfg = U.make_models(**mkw)
+  params = to64(U.cpu_tree(U.perturb_init(model, RG.PARAM_SEED, "cpu")))
+  g = torch.Generator().manual_seed(S["noise_seed"])
+  noises = [torch.randn(S["n"], 64, 64, 3, generator=g) for _ in range(S["steps"] + 2)]
+  assert RG.digest(torch.stack(noises)) == gold["noise_digest"]
+  gd = O.gaussian_diffusion_tables("cosine", 1000)
+  ys = torch.tensor(S["ys"])
+  for (cfg_scale, eps_pred), want in zip(S["variants"], gold["samples"]):
+    apply_fn = O.make_apply_fn(params, ocfg, gd, eps_pred=eps_pred, dtype=F64)
+    got = O.ddim_sample_loop(gd, apply_fn, [z.double() for z in noises], ys=ys if cfg_scale is not None else None,
+                             sampling_steps=S["steps"], cfg_scale=cfg_scale, eta=S["eta"])
+    assert U.rel_l2(got, want) <= 1e-6, (cfg_scale, eps_pred, U.rel_l2(got, want))

@@ -27,7 +27,7 @@ def rebuild(name):
   return model, tkw, params, batch, rand, n_noise, want
 
 
-def check_branch(pred, out, want):
+def check_branch(pred, out, want, patch=4):
   pred = pred.float().cpu()
   assert torch.isfinite(pred).all()
   r = U.rel_l2(pred[0], want["pred0"])
@@ -36,11 +36,11 @@ def check_branch(pred, out, want):
   assert abs(float(pred.abs().mean()) - want["pred_abs_mean"]) <= 1e-2 * want["pred_abs_mean"]
   assert U.rel_l2(out["pre_logits"].cpu(), want["pre_logits"]) <= U.TOL_PRED_REL_L2
   if "patch_mask" in want:
-    seq = out["mask"][:, ::4, ::4, 0].reshape(pred.shape[0], -1).cpu()
+    seq = out["mask"][:, ::patch, ::patch, 0].reshape(pred.shape[0], -1).cpu()
     assert torch.equal(seq.to(torch.uint8), want["patch_mask"]), "token mask must match the reference bit-exactly"
     # every pixel of a patch carries the patch's value (ae.py:30-36)
     m = out["mask"].cpu()
-    assert torch.equal(m, m[:, ::4, ::4].repeat_interleave(4, 1).repeat_interleave(4, 2))
+    assert torch.equal(m, m[:, ::patch, ::patch].repeat_interleave(patch, 1).repeat_interleave(patch, 2))
   else:
     assert out["mask"] is None
 
@@ -51,7 +51,8 @@ def test_training_forward_matches_reference_source(name):
   from small_vision_b200.diffusion import create_gaussian_diffusion, q_sample, to_device
   model, tkw, params, batch, rand, n_noise, want = rebuild(name)
   img = batch["image"].to(DEV)
-  gd = to_device(create_gaussian_diffusion("cosine", 1000), DEV)
+  gd = to_device(create_gaussian_diffusion(RG.SCHEDULE.get(name, "cosine"), 1000), DEV)
+  patch = model.cfg.patch
   x_t = q_sample(gd=gd, x_start=img[:n_noise].contiguous(), t=rand["t"].to(DEV), noise=rand["noise"].to(DEV))
   assert U.rel_l2(x_t.cpu(), want["x_t"]) <= 1e-5
   if "clean" in want:
@@ -59,7 +60,7 @@ def test_training_forward_matches_reference_source(name):
     pred, out = model.apply({"params": params}, img[n_noise:].contiguous(),
                             t=torch.zeros(nc, 1, dtype=torch.int32, device=DEV), train=True,
                             mask=tkw["mask_ratio_no_noise"], rngs={"mae_noise": rand["mask_noise_clean"].to(DEV)})
-    check_branch(pred, out, want["clean"])
+    check_branch(pred, out, want["clean"], patch)
   if "noise" in want:
     rngs = {"mae_noise": rand["mask_noise_noise"].to(DEV)}
     if "label_drop_noise" in rand:
@@ -67,7 +68,7 @@ def test_training_forward_matches_reference_source(name):
     y = batch["label"][:n_noise].to(DEV) if tkw["use_labels"] else None
     pred, out = model.apply({"params": params}, x_t, t=rand["t"].to(DEV) + 1, y=y, train=True, mask=tkw["mask_ratio"],
                             rngs=rngs)
-    check_branch(pred, out, want["noise"])
+    check_branch(pred, out, want["noise"], patch)
 
 
 @pytest.mark.parametrize("name", sorted(RG.CASES))
@@ -79,7 +80,9 @@ def test_update_fn_loss_and_gradient_slopes_match_reference_source(name):
   from small_vision_b200.train import create_train_state, make_update_fn
   model, tkw, params, batch, rand, n_noise, want = rebuild(name)
   B = batch["image"].shape[0]
-  tcfg = TrainConfig(batch_size=B, total_steps=1000, warmup_steps=0, peak_lr=2e-3, **tkw)
+  mkw = RG.CASES[name][0]
+  tcfg = TrainConfig(batch_size=B, total_steps=1000, warmup_steps=0, peak_lr=2e-3, beta_schedule=RG.SCHEDULE.get(name, "cosine"),
+                     diffusion_space=(mkw.get("img_size", 64), mkw.get("img_size", 64), mkw.get("channels", 3)), **tkw)
   state = create_train_state(model, tcfg, seed=0, device=DEV, params=params)
   dirs = RG.directions(U.cpu_tree(params))          # before the step: update_fn rewrites the arena in place
   gb = U.to_dev(batch, DEV)
@@ -121,3 +124,27 @@ def test_ddim_step_kernel_matches_reference_source():
     # row 3 sits at t = 999 where sqrt(1/abar - 1) ~ 2e4 amplifies fp32 round-off of x_t and eps
     assert U.rel_l2(r["pred_xstart"].cpu(), s["pred_xstart"].float()) <= 1e-4, s
     assert U.rel_l2(r["sample"].cpu(), s["sample"].float()) <= 1e-4, s
+
+
+def test_sampler_matches_reference_source():
+  """diffusion.create_apply_fn + ddim_sample_loop (forward kernels on the doubled batch + umd_ddim_step) against the
+  reference's create_apply_fn (train_ae.py:472-483) under its ddim_sample_loop, executed over the jax stand-in."""
+  from small_vision_b200 import diffusion as Dm
+  S = RG.SAMPLER
+  gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sampler_golden.pt"))["sampler"]
+  mkw = RG.CASES[S["case"]][0]
+  model, _ = U.make_models(**mkw)
+  params = U.perturb_init(model, RG.PARAM_SEED, DEV)
+  g = torch.Generator().manual_seed(S["noise_seed"])
+  noises = [torch.randn(S["n"], 64, 64, 3, generator=g) for _ in range(S["steps"] + 2)]
+  assert RG.digest(torch.stack(noises)) == gold["noise_digest"]
+  gd = Dm.to_device(Dm.create_gaussian_diffusion("cosine", 1000), DEV)
+  ys = torch.tensor(S["ys"]).to(DEV)
+  for (cfg_scale, eps_pred), want in zip(S["variants"], gold["samples"]):
+    apply_fn = Dm.create_apply_fn(model, params, eps_pred=eps_pred)
+    got, _ = Dm.ddim_sample_loop(gd, apply_fn, 0, torch.zeros(S["n"], 64, 64, 3), ys=ys if cfg_scale is not None else None,
+                                 sampling_steps=S["steps"], cfg_scale=cfg_scale, eta=S["eta"], noises=noises)
+    a = got["sample"].float().cpu()
+    assert torch.isfinite(a).all()
+    r = U.rel_l2(a, want)
+    assert r <= U.TOL_PRED_REL_L2, (cfg_scale, eps_pred, r)
