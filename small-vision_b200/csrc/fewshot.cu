@@ -383,7 +383,7 @@ extern "C" int umd_fewshot_matmul(const float* A, long long a_row_stride, long l
   int splits = 1;
   const int tiles = gx * gy, sms = sm_count();
   if (tiles < 2 * sms && K > 4 * FS_TK * 8) {
-    splits = static_cast<int>(ceil_div_ll(2ll * sms, tiles));
+    splits = (2 * sms) / tiles;   // one resident wave (2 CTAs per SM at 116 registers): 343 CTAs on 296 slots cost a 16 %-full second wave
     const int max_splits = K / (FS_TK * 8);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
