@@ -242,7 +242,7 @@ int umd_fewshot_stats(const float* x, int n, int d, float* mean, float* std_plus
 /* fewshot_lsr.py:48-51 (support) and :99-100 (query): out[n, d + 1] = [(x - mean) / std | bias_constant]. */
 int umd_fewshot_whiten(const float* x, const float* mean, const float* std_plus_eps, int n, int d, float bias_constant,
                        float* out, umd_stream_t stream);
-/* fewshot_lsr.py:54,82  rhs[dim, C] = X^T (2 onehot(y) - 1) from per-class row sums; sums_scratch: (C + 1) * dim floats. */
+/* fewshot_lsr.py:54,82  rhs[dim, C] = X^T (2 onehot(y) - 1) from per-class row sums; sums_scratch: (C + 2) * dim floats. */
 int umd_fewshot_xty(const float* xw, const int* y, int n, int dim, int num_classes, float* sums_scratch, float* rhs,
                     umd_stream_t stream);
 /* fewshot_lsr.py:54  out[n, C] = 2 onehot(y) - 1 (needed as the right-hand side when n < dim, :86-88). */

@@ -63,17 +63,23 @@ __global__ void fs_whiten_kernel(const float* __restrict__ x, const float* __res
 }
 
 // rhs[dim, c] = X^T Y with Y = 2 onehot(y) - 1 (fewshot_lsr.py:54): 2 * (sum of the rows of class c) - (sum of all rows).
-// Pass 1 scatters rows into class sums (fp32 atomics: every class receives `shots` rows), pass 2 finishes.
+// Pass 1 scatters rows into class sums (fp32 atomics: every class receives `shots` rows, so contention is low), pass 2
+// adds the class sums up to the total row (one thread per feature, coalesced), pass 3 finishes.  Rows whose label is
+// outside [0, c) only count towards the total (their one-hot row is all zero), like jax.nn.one_hot.
 __global__ void fs_class_sums_kernel(const float* __restrict__ xw, const int* __restrict__ y, int n, int dim, int c,
-                                     float* __restrict__ sums /*[c + 1, dim], zeroed; row c = total*/) {
+                                     float* __restrict__ sums /*[c + 2, dim], zeroed; row c = total, row c + 1 = unlabelled*/) {
   const int r = blockIdx.x;
-  const int cls = y[r];
+  int cls = y[r];
+  if (cls < 0 || cls >= c) cls = c + 1;
   const float* row = xw + static_cast<long long>(r) * dim;
-  for (int k = threadIdx.x; k < dim; k += blockDim.x) {
-    const float v = row[k];
-    if (cls >= 0 && cls < c) atomicAdd(&sums[static_cast<long long>(cls) * dim + k], v);
-    atomicAdd(&sums[static_cast<long long>(c) * dim + k], v);
-  }
+  for (int k = threadIdx.x; k < dim; k += blockDim.x) atomicAdd(&sums[static_cast<long long>(cls) * dim + k], row[k]);
+}
+__global__ void fs_total_row_kernel(float* __restrict__ sums, int dim, int c) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= dim) return;
+  float t = sums[static_cast<long long>(c + 1) * dim + k];
+  for (int cls = 0; cls < c; ++cls) t += sums[static_cast<long long>(cls) * dim + k];
+  sums[static_cast<long long>(c) * dim + k] = t;
 }
 __global__ void fs_rhs_from_sums_kernel(const float* __restrict__ sums, int dim, int c, float* __restrict__ rhs /*[dim, c]*/) {
   const long long total = static_cast<long long>(dim) * c;
@@ -358,8 +364,10 @@ extern "C" int umd_fewshot_xty(const float* xw, const int* y, int n, int dim, in
                                float* rhs, umd_stream_t stream) {
   UMD_REQUIRE(xw && y && sums_scratch && rhs && n > 0 && dim > 0 && num_classes > 0, "umd_fewshot_xty: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  UMD_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, sizeof(float) * (num_classes + 1ll) * dim, st));
+  UMD_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, sizeof(float) * (num_classes + 2ll) * dim, st));
   fs_class_sums_kernel<<<n, 256, 0, st>>>(xw, y, n, dim, num_classes, sums_scratch);
+  FS_LAUNCH_CHECK();
+  fs_total_row_kernel<<<static_cast<int>(ceil_div_ll(dim, 128)), 128, 0, st>>>(sums_scratch, dim, num_classes);
   FS_LAUNCH_CHECK();
   fs_rhs_from_sums_kernel<<<grid_for(static_cast<long long>(dim) * num_classes, 256), 256, 0, st>>>(sums_scratch, dim,
                                                                                                     num_classes, rhs);

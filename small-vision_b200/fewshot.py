@@ -74,7 +74,7 @@ def _precompute_cache(x, y, num_classes):
   cache = {"mean": mean, "std": std, "num_classes": int(num_classes)}
   if n >= dim:   # fewshot_lsr.py:80-83
     cache["gram"] = matmul(xw, xw, trans_a=True)
-    sums = torch.empty((num_classes + 1) * dim, dtype=torch.float32, device=x.device)
+    sums = torch.empty((num_classes + 2) * dim, dtype=torch.float32, device=x.device)
     rhs = torch.empty(dim, num_classes, dtype=torch.float32, device=x.device)
     lib.check(L.umd_fewshot_xty(lib.ptr(xw), lib.ptr(y), C.c_int(n), C.c_int(dim), C.c_int(num_classes), lib.ptr(sums),
                                 lib.ptr(rhs), lib.current_stream()), "umd_fewshot_xty")
