@@ -12,7 +12,7 @@ same draws can be given to the oracle and to the CUDA path.  Parameter gradients
 
 Runs only in the build container (it needs /root/reference):
   python tests/golden/make_reference_golden.py            # reference_golden.pt (step cases + diffusion vectors)
-  python tests/golden/make_reference_golden.py sampler    # reference_sampler_golden.pt (create_apply_fn + DDIM loop)
+  python tests/golden/make_reference_golden.py sampler    # reference_sampler_golden.pt (create_apply_fn + DDIM loop, evaluator fns)
 """
 import ast
 import hashlib
@@ -285,12 +285,62 @@ def sampler_vectors(ae, gdm):
   return out
 
 
+EVAL = dict(model=dict(variant="S/4", adaln=True, depth=2, dec_depth=1), param_seed=5, data_seed=9, n=4, t_noised=50,
+            mask_ratio_no_noise=0.75)
+
+
+def eval_inputs(num_patches=256):
+  """The inputs of tests/test_model_gpu.py::test_evaluator_predict_functions_match_oracle (same generator order)."""
+  g = torch.Generator().manual_seed(EVAL["data_seed"])
+  n = EVAL["n"]
+  image = torch.rand(n, 64, 64, 3, generator=g) * 2 - 1
+  noise = torch.randn(n, 64, 64, 3, generator=g)
+  t = torch.randint(0, 1000, (n, 1), generator=g, dtype=torch.int32)
+  mn = torch.rand(n, num_patches, generator=g)
+  return image, noise, t, mn
+
+
+def evaluator_vectors(ae, gdm):
+  """The evaluator closures of train_ae.py:384-470 (predict_fn, create_noised_pred_fn, eval_patch_fn, eval_loss_fn), lifted
+  by ast and run on supplied draws."""
+  import jax
+  import jax.numpy as jnp
+  engine_model, _ = U.make_models(**EVAL["model"])
+  params = tree64(U.cpu_tree(U.perturb_init(engine_model, EVAL["param_seed"], "cpu")))
+  model = ae.Model(**EVAL["model"])
+  gd = gdm.create_gaussian_diffusion("cosine", 1000)
+  image, noise, t, mn = eval_inputs()
+  key = jax.Key({"normal": np64(noise), "randint": t.numpy().astype(np.int32), "uniform": np64(mn)})
+  state = {"params": params, "gd": gd, "rng": key}
+  batch = {"image": jnp.asarray(np64(image))}
+  env = dict(jax=jax, jnp=jnp, model=model, q_sample=gdm.q_sample, _predict_xstart_from_eps=gdm._predict_xstart_from_eps,
+             config=Config(diffusion_space=(64, 64, 3), mask_ratio_no_noise=EVAL["mask_ratio_no_noise"]))
+  lines = {}
+  for fn in ("predict_fn", "create_noised_pred_fn", "eval_patch_fn", "eval_loss_fn"):
+    code, lines[fn] = load_reference.lift(fn)      # ast.walk is breadth-first: the outer predict_fn (:384) comes first
+    exec(code, env)
+  T = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float64))
+  out = {"lines": lines, "input_digest": digest(image) + digest(noise) + digest(mn)}
+  _, o = env["predict_fn"](state, batch)
+  out["predict_pre_logits"] = T(o["pre_logits"])
+  _, o = env["create_noised_pred_fn"](EVAL["t_noised"])(state, batch)
+  out["noised_pre_logits"] = T(o["pre_logits"])
+  px0, mask = env["eval_patch_fn"](state, batch)
+  out["patch_pred_x0"] = T(px0).float()[:2].clone()                     # first two samples (fixture size)
+  out["patch_mask"] = torch.from_numpy(np.asarray(mask)[:, ::4, ::4, 0].reshape(EVAL["n"], -1).astype(np.uint8))
+  loss, x_t, pred_x0, pred_x0_eps = env["eval_loss_fn"](state, batch)
+  out["loss"] = float(loss)
+  out["x_t"], out["pred_x0"], out["pred_x0_eps"] = T(x_t).float()[:2].clone(), T(pred_x0).float()[:2].clone(), T(pred_x0_eps).float()[:2].clone()
+  print("evaluators: loss", out["loss"], "lines", lines)
+  return out
+
+
 def main():
   ae, gdm, loss_code, loss_lines = load_reference()
   if sys.argv[1:] == ["sampler"]:
     path = os.path.join(HERE, "reference_sampler_golden.pt")
     torch.save({"provenance": "create_apply_fn + ddim_sample_loop of the reference executed over tests/golden/refshim",
-                "sampler": sampler_vectors(ae, gdm)}, path)
+                "sampler": sampler_vectors(ae, gdm), "evaluators": evaluator_vectors(ae, gdm)}, path)
     print(path, os.path.getsize(path), "bytes")
     return
   gold = {"provenance": "reference source executed over tests/golden/refshim (numpy fp64); loss_fn = train_ae.py:%d-%d"

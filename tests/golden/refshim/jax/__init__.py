@@ -38,6 +38,7 @@ random = _types.SimpleNamespace(
     uniform=lambda key, shape: key.take("uniform", shape),
     normal=lambda key, shape: key.take("normal", shape),
     bernoulli=lambda key, p, shape: key.take("bernoulli", shape).astype(bool),
+    randint=lambda key, shape, dtype=None, minval=0, maxval=None: key.take("randint", shape),
 )
 
 

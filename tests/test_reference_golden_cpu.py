@@ -149,3 +149,32 @@ def test_sampler_matches_reference_source():
     got = O.ddim_sample_loop(gd, apply_fn, [z.double() for z in noises], ys=ys if cfg_scale is not None else None,
                              sampling_steps=S["steps"], cfg_scale=cfg_scale, eta=S["eta"])
     assert U.rel_l2(got, want) <= 1e-6, (cfg_scale, eps_pred, U.rel_l2(got, want))
+
+
+def test_evaluator_functions_match_reference_source():
+  """predict_fn / create_noised_pred_fn / eval_patch_fn / eval_loss_fn (train_ae.py:384-470, lifted by ast) against the
+  oracle compositions that tests/test_model_gpu.py::test_evaluator_predict_functions_match_oracle holds the engine to."""
+  E = RG.EVAL
+  gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sampler_golden.pt"))["evaluators"]
+  model, ocfg = U.make_models(**E["model"])
+  params = to64(U.cpu_tree(U.perturb_init(model, E["param_seed"], "cpu")))
+  image, noise, t, mn = RG.eval_inputs()
+  assert RG.digest(image) + RG.digest(noise) + RG.digest(mn) == gold["input_digest"]
+  image, noise = image.double(), noise.double()
+  gd = O.gaussian_diffusion_tables("cosine", 1000)
+  n, C = E["n"], 3
+  z = torch.zeros(n, 1, dtype=torch.int32)
+  _, o = O.model_apply(params, ocfg, image, t=z, dtype=F64)
+  assert torch.allclose(o["pre_logits"], gold["predict_pre_logits"], rtol=0, atol=1e-10)
+  t50 = torch.full((n, 1), E["t_noised"], dtype=torch.int32)
+  _, o = O.model_apply(params, ocfg, O.q_sample(gd, image, t50, noise), t=t50 + 1, dtype=F64)
+  assert torch.allclose(o["pre_logits"], gold["noised_pre_logits"], rtol=0, atol=1e-10)
+  pred, o = O.model_apply(params, ocfg, image, t=z, mask=E["mask_ratio_no_noise"], mask_noise=mn, dtype=F64)
+  assert torch.equal(o["mask"][:, ::4, ::4, 0].reshape(n, -1).to(torch.uint8), gold["patch_mask"])
+  assert U.rel_l2(pred[:2, ..., :C], gold["patch_pred_x0"]) <= 1e-6
+  x_t = O.q_sample(gd, image, t, noise)
+  pred, _ = O.model_apply(params, ocfg, x_t, t=t + 1, dtype=F64)
+  loss = (torch.mean((pred[..., C:] - noise) ** 2) + torch.mean((pred[..., :C] - image) ** 2)) / 2
+  assert abs(float(loss) - gold["loss"]) <= 1e-11
+  assert U.rel_l2(x_t[:2], gold["x_t"]) <= 1e-6 and U.rel_l2(pred[:2, ..., :C], gold["pred_x0"]) <= 1e-6
+  assert U.rel_l2(O.predict_xstart_from_eps(gd, x_t, t, pred[..., C:])[:2], gold["pred_x0_eps"]) <= 1e-6

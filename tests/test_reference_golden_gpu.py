@@ -148,3 +148,29 @@ def test_sampler_matches_reference_source():
     assert torch.isfinite(a).all()
     r = U.rel_l2(a, want)
     assert r <= U.TOL_PRED_REL_L2, (cfg_scale, eps_pred, r)
+
+
+def test_evaluator_functions_match_reference_source():
+  """small-vision_b200/evaluators.py against the reference's evaluator closures (train_ae.py:384-470) run over the stand-in."""
+  from small_vision_b200 import evaluators as E
+  from small_vision_b200.diffusion import create_gaussian_diffusion, to_device
+  cfgE = RG.EVAL
+  gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sampler_golden.pt"))["evaluators"]
+  model, _ = U.make_models(**cfgE["model"])
+  params = U.perturb_init(model, cfgE["param_seed"], DEV)
+  image, noise, t, mn = RG.eval_inputs(model.cfg.num_patches)
+  assert RG.digest(image) + RG.digest(noise) + RG.digest(mn) == gold["input_digest"]
+  state = {"params": params, "gd": to_device(create_gaussian_diffusion("cosine", 1000), DEV), "rng": 0}
+  batch = {"image": image.to(DEV), "_rand": {"noise": noise.to(DEV), "t": t.to(DEV), "mae_noise": mn.to(DEV)}}
+  _, out = E.make_predict_fn(model)(state, batch)
+  assert U.rel_l2(out["pre_logits"].cpu(), gold["predict_pre_logits"]) <= U.TOL_PRED_REL_L2
+  _, out = E.create_noised_pred_fn(model, cfgE["t_noised"])(state, batch)
+  assert U.rel_l2(out["pre_logits"].cpu(), gold["noised_pre_logits"]) <= U.TOL_PRED_REL_L2
+  px0, mask = E.make_eval_patch_fn(model, cfgE["mask_ratio_no_noise"])(state, batch)
+  assert torch.equal(mask[:, ::4, ::4, 0].reshape(cfgE["n"], -1).cpu().to(torch.uint8), gold["patch_mask"])
+  assert U.rel_l2(px0[:2].cpu(), gold["patch_pred_x0"]) <= U.TOL_PRED_REL_L2
+  loss, x_t, pred_x0, pred_x0_eps = E.make_eval_loss_fn(model)(state, batch)
+  assert abs(float(loss) - gold["loss"]) <= U.TOL_LOSS_REL * abs(gold["loss"])
+  assert U.rel_l2(x_t[:2].cpu(), gold["x_t"]) <= 1e-5
+  assert U.rel_l2(pred_x0[:2].cpu(), gold["pred_x0"]) <= U.TOL_PRED_REL_L2
+  assert U.rel_l2(pred_x0_eps[:2].cpu(), gold["pred_x0_eps"]) <= U.TOL_PRED_REL_L2
