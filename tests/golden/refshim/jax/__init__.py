@@ -4,6 +4,7 @@ import types as _types
 import numpy as _np
 
 from . import numpy  # noqa: F401  (jax.numpy)
+from . import sharding  # noqa: F401  (jax.sharding)
 from .numpy import JArr as _JArr
 
 
@@ -72,6 +73,13 @@ def _one_hot(y, num_classes):
 
 
 nn = _types.SimpleNamespace(initializers=_Init(), one_hot=_one_hot)
+
+
+def tree_map(fn, tree):
+  """jax.tree_map over nested dicts (the only containers in the parameter tree)."""
+  if isinstance(tree, dict):
+    return {k: tree_map(fn, v) for k, v in tree.items()}
+  return fn(tree)
 
 
 def jit(fn=None, **_kw):

@@ -1,13 +1,18 @@
-"""Names imported by fewshot_lsr.py at module level; unused by the functions the fixture runs."""
+"""jax.sharding names used by big_vision/sharding.py (executed by make_sharding_golden.py) and imported at module level
+by fewshot_lsr.py: plain value objects."""
+
+
+class PartitionSpec(tuple):
+  def __new__(cls, *parts):
+    return super().__new__(cls, parts)
 
 
 class NamedSharding:
-  pass
-
-
-class PartitionSpec:
-  pass
+  def __init__(self, mesh, spec):
+    self.mesh, self.spec = mesh, spec
 
 
 class Mesh:
-  pass
+  def __init__(self, devices, axis_names):
+    import numpy as np
+    self.devices, self.axis_names = np.asarray(devices), tuple(axis_names)
