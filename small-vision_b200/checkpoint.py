@@ -30,20 +30,20 @@ def _to_numpy(v):
   return np.asarray(v)
 
 
-def traverse_with_names(tree):
-  """utils.py:650-673: yields (name, leaf) with names like "Encoder/encoderblock/MlpBlock_0/Dense_0/kernel"."""
+def traverse_with_names(tree, prefix=()):
+  """Leaf names as the reference's `_traverse_with_names` builds them (utils.py:650-673): path components joined by
+  '/', mapping keys visited in sorted order, sequence items by index, `None` sub-trees skipped."""
   if tree is None:
     return
   if isinstance(tree, Mapping):
-    for key in sorted(tree.keys()):
-      for path, v in traverse_with_names(tree[key]):
-        yield (str(key) + "/" + path).rstrip("/"), v
+    children = [(str(k), tree[k]) for k in sorted(tree.keys())]
   elif isinstance(tree, (list, tuple)):
-    for idx in range(len(tree)):
-      for path, v in traverse_with_names(tree[idx]):
-        yield (str(idx) + "/" + path).rstrip("/"), v
+    children = [(str(i), v) for i, v in enumerate(tree)]
   else:
-    yield "", tree
+    yield "/".join(prefix), tree
+    return
+  for name, child in children:
+    yield from traverse_with_names(child, prefix + (name,))
 
 
 def tree_flatten_with_names(tree):
@@ -52,18 +52,16 @@ def tree_flatten_with_names(tree):
 
 
 def recover_tree(keys, values):
-  """utils.py:857-884."""
+  """Inverse of the flat naming (utils.py:857-884): nested dicts from '/'-separated names."""
   tree = {}
-  sub_trees = collections.defaultdict(list)
-  for k, v in zip(keys, values):
-    if "/" not in k:
-      tree[k] = v
-    else:
-      k_left, k_right = k.split("/", 1)
-      sub_trees[k_left].append((k_right, v))
-  for k, kv_pairs in sub_trees.items():
-    k_subtree, v_subtree = zip(*kv_pairs)
-    tree[k] = recover_tree(k_subtree, v_subtree)
+  for name, value in zip(keys, values):
+    *parents, leaf = name.split("/")
+    node = tree
+    for part in parents:
+      node = node.setdefault(part, {})
+      if not isinstance(node, dict):
+        raise ValueError(f"checkpoint name '{name}' descends through the leaf '{part}'")
+    node[leaf] = value
   return tree
 
 

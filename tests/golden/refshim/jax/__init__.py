@@ -82,6 +82,41 @@ def tree_map(fn, tree):
   return fn(tree)
 
 
+class _TreeDef:
+  def __init__(self, skeleton):
+    self.skeleton = skeleton
+
+  def unflatten(self, leaves):
+    it = iter(leaves)
+
+    def build(node):
+      if isinstance(node, dict):
+        return {k: build(node[k]) for k in sorted(node)}
+      if isinstance(node, (list, tuple)):
+        return type(node)(build(v) for v in node)
+      return next(it)
+    return build(self.skeleton)
+
+
+def _tree_flatten(tree):
+  """jax.tree_util.tree_flatten for dicts (keys in sorted order), lists and tuples; None is an empty sub-tree."""
+  leaves = []
+
+  def walk(node):
+    if node is None:
+      return None
+    if isinstance(node, dict):
+      return {k: walk(node[k]) for k in sorted(node)}
+    if isinstance(node, (list, tuple)):
+      return type(node)(walk(v) for v in node)
+    leaves.append(node)
+    return 0
+  return leaves, _TreeDef(walk(tree))
+
+
+tree_util = _types.SimpleNamespace(tree_flatten=_tree_flatten, tree_map=tree_map)
+
+
 def jit(fn=None, **_kw):
   """jax.jit as a pass-through (also when used through functools.partial(jax.jit, static_argnums=...))."""
   return fn if fn is not None else (lambda f: f)
