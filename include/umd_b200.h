@@ -268,12 +268,13 @@ int umd_fewshot_accuracy(const float* scores, const int* labels, int n, int num_
  * crop window (pp/ops_image.py:197-242; boxes[n] = {y0, x0, h, w}, null = whole image) -> bilinear resize to out_h x out_w
  * with half-pixel centres, clipped and truncated back to uint8 (pp/ops_image.py:75-85) -> horizontal flip where
  * flips[n] != 0 (:306-314) -> value_range (pp/ops_general.py:51-60).  images [n, src_h, src_w, C] uint8;
- * out [n, out_h, out_w, C] fp32; resized_u8 (optional) receives the intermediate uint8 image.  The crop boxes and flip
+ * out [n, out_h, out_w, C] fp32; resized_u8 (optional) receives the intermediate uint8 image.  vmin / vmax are doubles because
+ * the reference forms (vmax - vmin) from Python scalars before rounding to float32.  The crop boxes and flip
  * flags are inputs (the reference draws them with tf.image.sample_distorted_bounding_box / random_flip_left_right).
  * ------------------------------------------------------------------------------------------ */
 int umd_augment_u8(const unsigned char* images, int n, int src_h, int src_w, int channels, const int* boxes_or_null,
-                   const unsigned char* flips_or_null, int out_h, int out_w, float in_min, float in_max, float vmin,
-                   float vmax, int clip_values, float* out, unsigned char* resized_u8_or_null, umd_stream_t stream);
+                   const unsigned char* flips_or_null, int out_h, int out_w, float in_min, float in_max, double vmin,
+                   double vmax, int clip_values, float* out, unsigned char* resized_u8_or_null, umd_stream_t stream);
 
 #ifdef __cplusplus
 }

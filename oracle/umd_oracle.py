@@ -642,7 +642,7 @@ def preprocess_train(images_u8, boxes=None, flips=None, size=None, vmin=-1.0, vm
       q = q[:, ::-1]
     mid[i] = q
     f = (q.astype(f32) - f32(in_min)) / (f32(in_max) - f32(in_min))
-    f = f32(vmin) + f * (f32(vmax) - f32(vmin))
+    f = f32(vmin) + f * f32(float(vmax) - float(vmin))      # Python-scalar difference, rounded once (ops_general.py:57)
     if clip_values:
       f = np.clip(f, f32(vmin), f32(vmax))
     out[i] = f

@@ -462,7 +462,8 @@ extern "C" int umd_fewshot_accuracy(const float* scores, const int* labels, int 
 //   decode_jpeg_and_inception_crop(size)|flip_lr|value_range(-1, 1)        (configs/ae_i1k.py:64-69)
 // that follows JPEG decoding — crop window -> tf.image.resize(bilinear, antialias=False) -> clip + cast back to uint8
 // (pp/ops_image.py:75-85) -> horizontal flip (:306-314) -> (x - in_min) / (in_max - in_min) * (vmax - vmin) + vmin
-// (pp/ops_general.py:51-60) — fused into one pass: one thread per output value, uint8 in, fp32 out.
+// (pp/ops_general.py:51-60; vmin / vmax are Python scalars there, so their difference is formed in double precision and
+// rounded once: hence the double arguments) — fused into one pass: one thread per output value, uint8 in, fp32 out.
 // The arithmetic follows TensorFlow's half-pixel-centre bilinear kernel operation by operation with non-contracting
 // intrinsics, so the intermediate uint8 image (a truncating cast) and the fp32 result are bit-identical to an IEEE
 // single-precision evaluation in the same order.  HBM-bound: <= 1 B read + 4 B written per output value.
@@ -470,7 +471,7 @@ extern "C" int umd_fewshot_accuracy(const float* scores, const int* labels, int 
 namespace umd {
 __global__ void augment_kernel(const unsigned char* __restrict__ src, int Hs, int Ws, int C, const int* __restrict__ boxes,
                                const unsigned char* __restrict__ flips, int Sh, int Sw, float in_min, float in_max, float vmin,
-                               float vmax, int clip_values, float* __restrict__ out, unsigned char* __restrict__ out_u8,
+                               float vmax, float span, int clip_values, float* __restrict__ out, unsigned char* __restrict__ out_u8,
                                long long total) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -500,7 +501,7 @@ __global__ void augment_kernel(const unsigned char* __restrict__ src, int Hs, in
     const unsigned char q = static_cast<unsigned char>(v);         // truncation, like tf.cast(float -> uint8)
     if (out_u8) out_u8[i] = q;
     float f = __fdiv_rn(__fsub_rn(static_cast<float>(q), in_min), __fsub_rn(in_max, in_min));
-    f = __fadd_rn(vmin, __fmul_rn(f, __fsub_rn(vmax, vmin)));
+    f = __fadd_rn(vmin, __fmul_rn(f, span));
     if (clip_values) f = fminf(fmaxf(f, vmin), vmax);
     out[i] = f;
   }
@@ -508,15 +509,15 @@ __global__ void augment_kernel(const unsigned char* __restrict__ src, int Hs, in
 }  // namespace umd
 
 extern "C" int umd_augment_u8(const unsigned char* images, int n, int src_h, int src_w, int channels, const int* boxes_or_null,
-                              const unsigned char* flips_or_null, int out_h, int out_w, float in_min, float in_max, float vmin,
-                              float vmax, int clip_values, float* out, unsigned char* resized_u8_or_null, umd_stream_t stream) {
+                              const unsigned char* flips_or_null, int out_h, int out_w, float in_min, float in_max, double vmin,
+                              double vmax, int clip_values, float* out, unsigned char* resized_u8_or_null, umd_stream_t stream) {
   UMD_REQUIRE(images && out && n >= 0 && src_h > 0 && src_w > 0 && channels > 0 && out_h > 0 && out_w > 0, "umd_augment_u8: bad argument");
   UMD_REQUIRE(in_max != in_min, "umd_augment_u8: in_max == in_min");
   if (n == 0) return UMD_OK;
   const long long total = static_cast<long long>(n) * out_h * out_w * channels;
   augment_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      images, src_h, src_w, channels, boxes_or_null, flips_or_null, out_h, out_w, in_min, in_max, vmin, vmax, clip_values, out,
-      resized_u8_or_null, total);
+      images, src_h, src_w, channels, boxes_or_null, flips_or_null, out_h, out_w, in_min, in_max, static_cast<float>(vmin),
+      static_cast<float>(vmax), static_cast<float>(vmax - vmin), clip_values, out, resized_u8_or_null, total);
   FS_LAUNCH_CHECK();
   return UMD_OK;
 }

@@ -42,8 +42,8 @@ def augment(images, *, boxes=None, flips=None, size=None, vmin=-1.0, vmax=1.0, i
   out = torch.empty(n, oh, ow, Cc, dtype=torch.float32, device=images.device)
   u8 = torch.empty(n, oh, ow, Cc, dtype=torch.uint8, device=images.device) if return_uint8 else None
   lib.check(lib.load().umd_augment_u8(lib.ptr(images), C.c_int(n), C.c_int(Hs), C.c_int(Ws), C.c_int(Cc), lib.ptr(b),
-                                      lib.ptr(f), C.c_int(oh), C.c_int(ow), C.c_float(in_min), C.c_float(in_max), C.c_float(vmin),
-                                      C.c_float(vmax), C.c_int(int(clip_values)), lib.ptr(out), lib.ptr(u8),
+                                      lib.ptr(f), C.c_int(oh), C.c_int(ow), C.c_float(in_min), C.c_float(in_max), C.c_double(vmin),
+                                      C.c_double(vmax), C.c_int(int(clip_values)), lib.ptr(out), lib.ptr(u8),
                                       lib.current_stream()), "umd_augment_u8")
   return (out, u8) if return_uint8 else out
 

@@ -51,3 +51,16 @@ def test_matches_torch_bilinear_up_to_the_truncation_boundary():
     # truncation: got == floor(ref) except where ref sits within float32 round-off of an integer
     assert np.all((got <= ref + 1e-3) & (got >= ref - 1 - 1e-3))
     assert np.mean(got == np.floor(ref)) > 0.999
+
+
+def test_value_range_matches_reference_source():
+  """oracle value-range stage == the reference's own get_value_range (pp/ops_general.py:30-62) run over a numpy stand-in
+  for its five tf names (tests/golden/make_pp_golden.py), bit for bit, on every uint8 value."""
+  import os
+  from tests.golden import make_pp_golden as PG
+  gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pp_golden.npz"))
+  x = PG.all_bytes()
+  for i, (vmin, vmax, in_min, in_max, clip) in enumerate(PG.SETTINGS):
+    out, mid = O.preprocess_train(x, vmin=vmin, vmax=vmax, in_min=in_min, in_max=in_max, clip_values=clip)
+    assert np.array_equal(mid, x)
+    assert np.array_equal(out, gold[f"case{i}"]), PG.SETTINGS[i]
