@@ -111,7 +111,7 @@ class TrainConfig:
     c = dataclasses.replace(self)
     steps_per_epoch = c.ntrain_img / c.batch_size
     if c.total_steps is None:
-      c.total_steps = int(c.total_epochs * steps_per_epoch)
+      c.total_steps = max(round(c.total_epochs * steps_per_epoch), 1)   # utils.steps rounds to nearest (utils.py:1059-1061)
     if c.warmup_steps is None:
       warmup_epochs = int(0.05 * c.total_epochs)           # ae_i1k.py:93
       c.warmup_steps = warmup_epochs * c.ntrain_img // c.batch_size   # train_ae.py:137

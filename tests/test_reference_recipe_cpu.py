@@ -1,0 +1,63 @@
+"""small-vision_b200/config.py and the parameter layout against tests/golden/reference_recipe_golden.json: the recipes
+of the BASELINE.json configurations as the reference's own `configs/ae_i1k.py`, `utils.steps` and the optimiser wiring of
+train_ae.py:124-151 resolve them (executed over stand-ins, tests/golden/make_recipe_golden.py): step counts, learning-rate
+schedule arguments, AdamW hyper-parameters, the weight-decay mask per leaf, model kwargs, masking / branch settings."""
+import json
+import os
+
+import pytest
+
+from small_vision_b200.config import TrainConfig
+from small_vision_b200.model import Model
+from tests.golden import make_recipe_golden as RG
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_recipe_golden.json")))
+
+
+def _train_config(r):
+  t, sched = r["train"], r["diff_schedule"]
+  return TrainConfig(batch_size=r["batch_size"], no_noise_prob=t["no_noise_prob"], mask_ratio=t["mask_ratio"],
+                     mask_ratio_no_noise=t["mask_ratio_no_noise"], use_labels=bool(t["use_labels"]),
+                     beta_schedule=sched["beta_schedule"], timesteps=sched["timesteps"],
+                     diffusion_space=tuple(r["diffusion_space"]), total_epochs=r["total_epochs"], ntrain_img=GOLD["ntrain_img"],
+                     ema_decay=t["ema_decay"])
+
+
+@pytest.mark.parametrize("name", sorted(RG.RECIPES))
+def test_schedule_and_optimiser_hyperparameters_match_reference_source(name):
+  r = GOLD["recipes"][name]
+  c = _train_config(r).resolved()           # peak_lr, wd, betas, clip_norm, mu_dtype stay at TrainConfig's defaults
+  s = r["schedule"]
+  assert c.total_steps == r["total_steps"] == s["decay_steps"]           # utils.steps rounds (utils.py:1059-1061)
+  assert c.warmup_steps == s["warmup_steps"]
+  assert c.scaled_peak_lr == pytest.approx(s["peak_value"], rel=1e-12) and s["init_value"] == 0.0
+  a = r["adamw"]
+  assert (c.wd, c.betas[0], c.betas[1], c.mu_dtype) == (a["weight_decay"], a["b1"], a["b2"], a["mu_dtype"])
+  assert c.clip_norm == r["clip_norm"] and r["chain"] == ["clip", "adamw"] and r["adamw_learning_rate_is_schedule"]
+
+
+@pytest.mark.parametrize("name", sorted(RG.RECIPES))
+def test_model_kwargs_and_decay_mask_match_reference_source(name):
+  r = GOLD["recipes"][name]
+  model = Model(**r["model"])                # the reference's own config.model dict, unchanged
+  cfg = model.cfg
+  assert cfg.img_size == r["diffusion_space"][0] and cfg.channels == r["diffusion_space"][2]
+  assert cfg.num_classes == r["train"]["num_classes"]
+  got = {"/".join(lf.path): model.layout.decay(lf) for lf in model.layout.leaves}
+  assert got == r["decay_mask"]
+  assert any(got.values()) and not all(got.values())
+
+
+def test_defaults_are_the_reference_defaults():
+  r = GOLD["recipes"]["default"]
+  d = TrainConfig()
+  t = r["train"]
+  assert (d.batch_size, d.no_noise_prob, d.mask_ratio, d.mask_ratio_no_noise, d.use_labels) == \
+      (r["batch_size"], t["no_noise_prob"], t["mask_ratio"], t["mask_ratio_no_noise"], bool(t["use_labels"]))
+  assert d.total_epochs == r["total_epochs"] and tuple(d.diffusion_space) == tuple(r["diffusion_space"])
+  assert d.peak_lr * d.batch_size / 256 == pytest.approx(r["schedule"]["peak_value"], rel=1e-12)
+  # label fine-tuning sets the EMA rate from the batch size (configs/ae_i1k.py:31-33)
+  assert GOLD["recipes"]["dit_b4_labels"]["train"]["ema_decay"] == pytest.approx(1e-4 * 256 / 256)
+  # the few-shot probe and sampler settings the §8f components default to
+  assert r["fewshot"]["l2_reg"] == 1024 and r["fewshot"]["representation_layer"] == "pre_logits"
+  assert r["diff_schedule"]["sampling_timesteps"] == 125 and r["diff_schedule"]["eta"] == 1.0
