@@ -20,6 +20,9 @@ repository ships no golden vectors or tests for this path (SURVEY.md F2, F5, §8
     library layers the stand-in itself restates (Dense, LayerNorm eps 1e-6, dot-product
     attention, Conv / ConvTranspose orientation, gelu-tanh, silu); those are checked
     against torch's independent implementations in tests/test_oracle_invariants.py.
+  * Few-shot probe, sharding declarations, checkpoint naming, value_range and the recipe
+    wiring (step counts, schedule / AdamW arguments, decay mask) are pinned the same way
+    (tests/golden/refshim/README.md lists every fixture and the reference code behind it).
   * Optimiser (optax 0.2.x: clip_by_global_norm, adamw with bf16 mu, masked decay,
     warmup_cosine_decay_schedule; train_ae.py:135-151): restated from optax's published
     semantics and checked against torch.optim.AdamW and closed forms —
