@@ -52,6 +52,30 @@ def unflatten_dict(flat):
   return out
 
 
+def init_log(model, engine_model, mkw):
+  """One forward pass of the reference model over zero parameters of the engine layout's shapes (the stand-in asserts
+  every shape the reference asks for) while the stand-in records which initialiser the reference hands to each leaf
+  (None = the Flax layer's default)."""
+  import numpy as np
+  import jax
+  import jax.numpy as jnp
+  import flax.linen as nn
+  tree = {}
+  for lf in engine_model.layout.leaves:
+    d = tree
+    for k in lf.path[:-1]:
+      d = d.setdefault(k, {})
+    d[lf.path[-1]] = np.zeros(lf.shape)
+  nn.INIT_LOG.clear()
+  S, C = mkw["img_size"], mkw["channels"]
+  L = engine_model.cfg.num_patches
+  y = jnp.asarray(np.zeros((1,), np.int32)) if mkw.get("num_classes") else None
+  model.apply({"params": tree}, jnp.asarray(np.zeros((1, S, S, C))), t=jnp.asarray(np.ones((1, 1), np.int32)), y=y, mask=0.375,
+              rngs={"mae_noise": jax.Key({"uniform": np.linspace(0, 1, L)[None]})})
+  assert set(nn.INIT_LOG) == {lf.path for lf in engine_model.layout.leaves}, set(nn.INIT_LOG) ^ {lf.path for lf in engine_model.layout.leaves}
+  return {"/".join(k): {"layer": layer, "init": init} for k, (layer, init) in sorted(nn.INIT_LOG.items())}
+
+
 def main():
   sys.path.insert(0, os.path.join(HERE, "refshim"))
   sys.path.insert(0, REF)
@@ -102,6 +126,7 @@ def main():
         d = d.setdefault(k, {})
       d[lf.path[-1]] = 0
     mask = flatten_dict(calls["adamw"]["mask"](tree))
+    inits = init_log(model, em, mkw)
     gold["recipes"][name] = {
         "arg": arg, "model": {k: (list(v) if isinstance(v, tuple) else v) for k, v in mkw.items()},
         "batch_size": batch_size, "total_epochs": config.total_epochs, "total_steps": total_steps,
@@ -115,6 +140,7 @@ def main():
         "diff_schedule": config.diff_schedule.to_dict(),
         "fewshot": {k: config.evals.fewshot.get(k) for k in ("shots", "l2_reg", "num_seeds", "representation_layer", "pred")},
         "input_pp": config.input.pp,
+        "init": inits,
     }
     r = gold["recipes"][name]
     print(name, "steps", total_steps, "schedule", r["schedule"], "adamw", r["adamw"])

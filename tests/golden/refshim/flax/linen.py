@@ -10,6 +10,7 @@ import jax as _jax
 from jax.numpy import JArr as _JArr
 
 _stack = []          # modules whose setup/__call__ is executing (innermost last): parents of new sub-modules
+INIT_LOG = {}        # leaf path -> (module class, initialiser descriptor or None = the layer's Flax default); see Module.param
 broadcast = object()
 initializers = _jax.nn.initializers
 
@@ -118,7 +119,16 @@ class Module:
     assert self.parent is not None and self.name is not None, f"unbound module {type(self).__name__}"
     return self.parent._params()[self.name]
 
+  def _path(self):
+    parts, m = [], self
+    while m is not None and m.parent is not None:
+      parts.append(m.name)
+      m = m.parent
+    return tuple(reversed(parts))
+
   def param(self, name, _init, shape, *_a):
+    path = tuple(p for p in self._path() if not p.startswith("layer")) + (name,)     # scan steps share one stacked leaf
+    INIT_LOG[path] = (type(self).__name__, _init.describe() if hasattr(_init, "describe") else None)
     v = _np.asarray(self._params()[name], dtype=_np.float64)
     assert tuple(v.shape) == tuple(int(s) for s in shape), (self.name, name, v.shape, shape)
     return v.view(_JArr)
@@ -185,10 +195,10 @@ class Dense(Module):
 
   def __call__(self, x):
     x = _np.asarray(x, dtype=_np.float64)
-    k = self.param("kernel", None, (x.shape[-1], self.features))
+    k = self.param("kernel", self.kernel_init, (x.shape[-1], self.features))
     y = x @ _np.asarray(k)
     if self.use_bias:
-      y = y + _np.asarray(self.param("bias", None, (self.features,)))
+      y = y + _np.asarray(self.param("bias", self.bias_init, (self.features,)))
     return _w(y)
 
 
@@ -209,9 +219,10 @@ class _Proj(Module):
   """DenseGeneral as used inside MultiHeadDotProductAttention."""
   shape_in: tuple = ()
   shape_out: tuple = ()
+  kernel_init: object = None
 
   def __call__(self, x):
-    k = _np.asarray(self.param("kernel", None, tuple(self.shape_in) + tuple(self.shape_out)))
+    k = _np.asarray(self.param("kernel", self.kernel_init, tuple(self.shape_in) + tuple(self.shape_out)))
     b = _np.asarray(self.param("bias", None, tuple(self.shape_out)))
     ni = len(self.shape_in)
     return _np.tensordot(x, k, axes=(list(range(x.ndim - ni, x.ndim)), list(range(ni)))) + b
@@ -230,9 +241,9 @@ class MultiHeadDotProductAttention(Module):
     h = self.num_heads
     assert d % h == 0
     hd = d // h
-    q = _Proj((d,), (h, hd), name="query")(xq)      # [b, s, h, hd]
-    k = _Proj((d,), (h, hd), name="key")(xkv)
-    v = _Proj((d,), (h, hd), name="value")(xkv)
+    q = _Proj((d,), (h, hd), self.kernel_init, name="query")(xq)      # [b, s, h, hd]
+    k = _Proj((d,), (h, hd), self.kernel_init, name="key")(xkv)
+    v = _Proj((d,), (h, hd), self.kernel_init, name="value")(xkv)
     out = _np.empty_like(q)
     for b in range(q.shape[0]):
       for j in range(h):
@@ -241,7 +252,7 @@ class MultiHeadDotProductAttention(Module):
         w = _np.exp(logits)
         w = w / w.sum(-1, keepdims=True)
         out[b, :, j] = w @ v[b, :, j]
-    return _w(_Proj((h, hd), (d,), name="out")(out))
+    return _w(_Proj((h, hd), (d,), self.kernel_init, name="out")(out))
 
 
 class Dropout(Module):
@@ -265,7 +276,7 @@ class Conv(Module):
     kh, kw = self.kernel_size
     assert tuple(self.strides) == (kh, kw) and self.padding == "VALID"
     n, H, W, c = x.shape
-    k = _np.asarray(self.param("kernel", None, (kh, kw, c, self.features)))
+    k = _np.asarray(self.param("kernel", self.kernel_init, (kh, kw, c, self.features)))
     b = _np.asarray(self.param("bias", None, (self.features,)))
     out = _np.zeros((n, H // kh, W // kw, self.features))
     for a in range(kh):                 # cross-correlation: out[i, j] = sum_ab x[i*kh + a, j*kw + b] K[a, b]
@@ -290,7 +301,7 @@ class ConvTranspose(Module):
     sh, sw = self.strides
     assert self.padding == "VALID"
     n, h, w, c = x.shape
-    k = _np.asarray(self.param("kernel", None, (kh, kw, c, self.features)))
+    k = _np.asarray(self.param("kernel", self.kernel_init, (kh, kw, c, self.features)))
     b = _np.asarray(self.param("bias", None, (self.features,)))
     Hd, Wd = (h - 1) * sh + 1, (w - 1) * sw + 1
     xd = _np.zeros((n, Hd + 2 * (kh - 1), Wd + 2 * (kw - 1), c))

@@ -60,11 +60,25 @@ lax = _types.SimpleNamespace(scan=_scan)
 checkpoint_policies = _types.SimpleNamespace(nothing_saveable=None)
 
 
-class _Init:
-  """Initialisers are never evaluated: parameters are supplied to `apply`."""
+class InitDesc:
+  """An initialiser as the reference names it: `nn.initializers.zeros` (uncalled) or `nn.initializers.normal(stddev=..)`
+  (called).  Never evaluated — parameters are supplied to `apply` — but recorded per leaf by flax.linen.Module.param."""
 
+  def __init__(self, name, args=(), kwargs=None):
+    self.name, self.args, self.kwargs = name, tuple(args), dict(kwargs or {})
+
+  def __call__(self, *args, **kwargs):
+    return InitDesc(self.name, args, kwargs)
+
+  def describe(self):
+    num = lambda v: isinstance(v, (int, float)) or (hasattr(v, "dtype") and getattr(v, "ndim", 1) == 0)
+    return {"name": self.name, "args": [float(a) for a in self.args if num(a)],
+            "kwargs": {k: float(v) for k, v in self.kwargs.items() if num(v)}}
+
+
+class _Init:
   def __getattr__(self, name):
-    return lambda *a, **k: ("init", name)
+    return InitDesc(name)
 
 
 def _one_hot(y, num_classes):

@@ -61,3 +61,46 @@ def test_defaults_are_the_reference_defaults():
   # the few-shot probe and sampler settings the §8f components default to
   assert r["fewshot"]["l2_reg"] == 1024 and r["fewshot"]["representation_layer"] == "pre_logits"
   assert r["diff_schedule"]["sampling_timesteps"] == 125 and r["diff_schedule"]["eta"] == 1.0
+
+
+@pytest.mark.parametrize("name", sorted(RG.RECIPES))
+def test_parameter_tree_and_initialisers_match_reference_source(name):
+  """The fixture's `init` table was recorded while the reference's own model ran over parameters of the engine layout's
+  shapes (the stand-in asserts every shape the reference requests and that both leaf sets coincide — at full depth for
+  B/4 and L/2).  Here: the initialiser the reference hands to each leaf (None = the Flax layer's default) against the
+  engine's `Leaf.init` used by Model.init / init_arena."""
+  import math
+  r = GOLD["recipes"][name]
+  model = Model(**r["model"])
+  assert {"/".join(lf.path) for lf in model.layout.leaves} == set(r["init"])
+  for lf in model.layout.leaves:
+    rec = r["init"]["/".join(lf.path)]
+    layer, init, leaf = rec["layer"], rec["init"], lf.path[-1]
+    shape = lf.shape[1:] if len(lf.path) > 2 and lf.path[1].startswith("Scan") else lf.shape   # stacked [depth, ...]
+    if init is None:                                                     # Flax defaults
+      if layer == "LayerNorm":
+        want = "ones" if leaf == "scale" else "zeros"
+      elif layer == "Embed":
+        want = ("normal", 1 / math.sqrt(shape[-1]))                      # variance_scaling(1, fan_in, normal, out_axis=0)
+      elif leaf == "bias":
+        want = "zeros"
+      else:
+        want = ("lecun", math.prod(shape[:-1]))                          # lecun_normal: fan_in = everything but the last axis
+    elif init["name"] == "zeros":
+      want = "zeros"
+    elif init["name"] == "normal":
+      want = ("normal", (init["args"] or [init["kwargs"]["stddev"]])[0])
+    elif init["name"] == "xavier_uniform":
+      if layer == "_Proj" and lf.path[-2] == "out":
+        want = ("xavier", shape[0] * shape[1], shape[2])                 # DenseGeneral flattens [H, Dh] -> D
+      elif layer == "_Proj":
+        want = ("xavier", shape[0], shape[1] * shape[2])
+      else:
+        want = ("xavier", shape[0], shape[1])
+    else:
+      raise AssertionError(f"unexpected initialiser {init}")
+    got = "zeros" if lf.init == "adaln" else lf.init                     # 'adaln' = zero-init unless nonzero_adaln is asked for
+    if isinstance(want, tuple):
+      assert isinstance(got, tuple) and got[0] == want[0] and got[1:] == pytest.approx(want[1:], rel=1e-12), (lf.path, got, want)
+    else:
+      assert got == want, (lf.path, got, want)
