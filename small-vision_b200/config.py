@@ -133,3 +133,61 @@ def warmup_cosine_lr(count: int, *, peak: float, warmup_steps: int, decay_steps:
   cos = 0.5 * (1.0 + math.cos(math.pi * c / span))
   alpha = (end_value / peak) if peak else 0.0
   return peak * ((1.0 - alpha) * cos + alpha)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's launcher-facing recipe: `--config big_vision/configs/ae_i1k.py:variant=B/4,batch_size=4096,...`
+# ------------------------------------------------------------------------------------------------------------------
+_ARG_SPEC = dict(variant="B/4", scan=True, fsdp=False, batch_size=1024, use_labels=False, mask_ratio=0.375, no_noise_prob=0.5,
+                 mask_ratio_no_noise=0.75, finetune=False, lr=15e-5, wd=5e-2, beta2=0.95, size=64, adaln=True, epochs=800,
+                 area_min=80, use_preprocessed_latents=False, latent_diffusion=False, wandb_mode="online", save_ckpt=True)
+
+
+def parse_arg(arg: Optional[str]) -> dict:
+  """The option string of configs/ae_i1k.py:8-11 (`name=value,flag,...`; configs/common.py:29-103): values are converted
+  with the type of their default, booleans strictly from 'true' / 'false' / '' (a bare name means True), a lone value
+  without '=' goes to the first option, unknown names raise."""
+  arg = arg or ""
+  if arg and "," not in arg and "=" not in arg:
+    arg = f"{arg}=True" if arg in _ARG_SPEC else f"{next(iter(_ARG_SPEC))}={arg}"
+  raw = {}
+  for item in arg.split(","):
+    if item:
+      name, _, val = item.partition("=")
+      raw[name] = val if "=" in item else "True"
+  out = {}
+  for name, default in _ARG_SPEC.items():
+    val = raw.pop(name, None)
+    if val is None:
+      out[name] = default
+    elif isinstance(default, bool):
+      if val.lower() not in ("true", "false", ""):
+        raise ValueError(f"{name}: expected a boolean, got '{val}'")
+      out[name] = val.lower() == "true"
+    else:
+      out[name] = type(default)(val)
+  if raw:
+    raise ValueError(f"Unhandled config args remain: {raw}")
+  return out
+
+
+def get_config(arg: Optional[str] = None) -> Tuple[dict, TrainConfig]:
+  """What configs/ae_i1k.py::get_config resolves for the training step, from the same option string: the `config.model`
+  kwargs for `Model(**kw)` (ae_i1k.py:81-89) and a TrainConfig (ae_i1k.py:12-53,91-96).  Dataset, evaluator, logging and
+  checkpoint entries of the reference config have no counterpart on this path."""
+  a = parse_arg(arg)
+  if a["latent_diffusion"]:
+    if a["size"] != 256:
+      raise AssertionError("Latent Diffusion only supports 256x256 images")     # ae_i1k.py:17
+    space = (32, 32, 4)
+  else:
+    space = (a["size"], a["size"], 3)
+  num_classes = 1000 if a["use_labels"] else None
+  model = dict(num_classes=num_classes, variant=a["variant"], scan=a["scan"], adaln=a["adaln"], channels=space[-1],
+               img_size=space[0], remat_policy="nothing_saveable")
+  train = TrainConfig(batch_size=a["batch_size"], no_noise_prob=a["no_noise_prob"], mask_ratio=a["mask_ratio"],
+                      mask_ratio_no_noise=a["mask_ratio_no_noise"], use_labels=a["use_labels"],
+                      beta_schedule="linear" if a["latent_diffusion"] else "cosine", timesteps=1000, diffusion_space=space,
+                      peak_lr=a["lr"], wd=a["wd"], betas=(0.9, a["beta2"]), clip_norm=1.0, total_epochs=a["epochs"],
+                      ema_decay=0.0001 * (a["batch_size"] / 256) if a["use_labels"] else None)
+  return model, train

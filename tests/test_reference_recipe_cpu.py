@@ -104,3 +104,33 @@ def test_parameter_tree_and_initialisers_match_reference_source(name):
       assert isinstance(got, tuple) and got[0] == want[0] and got[1:] == pytest.approx(want[1:], rel=1e-12), (lf.path, got, want)
     else:
       assert got == want, (lf.path, got, want)
+
+
+@pytest.mark.parametrize("name", sorted(RG.RECIPES))
+def test_get_config_resolves_the_reference_option_strings(name):
+  """config.get_config(arg) against what the reference's configs/ae_i1k.py::get_config resolved for the same string."""
+  from small_vision_b200.config import get_config
+  r = GOLD["recipes"][name]
+  model_kw, tc = get_config(r["arg"])
+  assert model_kw == r["model"]
+  t = r["train"]
+  assert (tc.batch_size, tc.no_noise_prob, tc.mask_ratio, tc.mask_ratio_no_noise, tc.use_labels, tc.ema_decay) == \
+      (r["batch_size"], t["no_noise_prob"], t["mask_ratio"], t["mask_ratio_no_noise"], bool(t["use_labels"]), t["ema_decay"])
+  assert list(tc.diffusion_space) == r["diffusion_space"] and tc.beta_schedule == r["diff_schedule"]["beta_schedule"]
+  c = tc.resolved()
+  s, a = r["schedule"], r["adamw"]
+  assert (c.total_steps, c.warmup_steps) == (s["decay_steps"], s["warmup_steps"])
+  assert c.scaled_peak_lr == pytest.approx(s["peak_value"], rel=1e-12)
+  assert (c.wd, list(c.betas), c.clip_norm, c.mu_dtype) == (a["weight_decay"], [a["b1"], a["b2"]], r["clip_norm"], a["mu_dtype"])
+  Model(**model_kw)
+
+
+def test_get_config_option_string_errors():
+  from small_vision_b200.config import get_config, parse_arg
+  assert parse_arg("S/4")["variant"] == "S/4"                      # a lone value goes to the first option
+  assert parse_arg("use_labels")["use_labels"] is True             # a bare flag
+  assert parse_arg("adaln=False,beta2=0.99") ["beta2"] == 0.99
+  with pytest.raises(ValueError):
+    parse_arg("no_such_option=1")
+  with pytest.raises(AssertionError):
+    get_config("latent_diffusion=True")                            # needs size=256 (ae_i1k.py:17)
