@@ -39,6 +39,19 @@ def test_library_exports_every_declared_symbol(L):
   assert not missing, f"declared in include/umd_b200.h but not exported: {missing}"
 
 
+def test_header_is_plain_c(tmp_path):
+  """The drop-in boundary is a C ABI: include/umd_b200.h must compile as strict C99 on its own (no C++ or torch types)."""
+  import shutil
+  gcc = shutil.which("gcc")
+  if gcc is None:
+    pytest.skip("gcc not present")
+  src = tmp_path / "abi.c"
+  src.write_text('#include "umd_b200.h"\nint main(void) { return (int)sizeof(umd_model_cfg) == 0; }\n')
+  r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", os.path.dirname(HEADER),
+                      str(src)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+  assert r.returncode == 0, r.stdout
+
+
 def test_library_is_sm100a_native():
   """cuobjdump shows tcgen05 / TMA SASS mnemonics (B200_PROFILING.md 'What proves a Blackwell-native kernel')."""
   exe = "/usr/local/cuda/bin/cuobjdump"
