@@ -335,12 +335,87 @@ def evaluator_vectors(ae, gdm):
   return out
 
 
+STEP = dict(case="umd_lbl_s4", ema_decay=0.01, update_seed=77, update_scale=1e-3)
+
+
+def step_updates(params_t):
+  """The stand-in for optax's output: a seeded small random update tree (sorted leaf order)."""
+  g = torch.Generator().manual_seed(STEP["update_seed"])
+  return {k: STEP["update_scale"] * torch.randn(tuple(v.shape), generator=g, dtype=torch.float64)
+          for k, v in sorted(flatten(params_t).items())}
+
+
+def update_fn_vectors(ae, gdm):
+  """The reference's whole `update_fn` (train_ae.py:287-382; decorators dropped) on the umd_lbl_s4 case: its own RNG split
+  tree, batch split `int(B * no_noise_prob)`, label slicing, q_sample call, loss_fn, measurements and EMA update.  Only the
+  library calls are stand-ins: `jax.value_and_grad` evaluates the loss (gradients are pinned by the slopes of the step
+  cases), `tx.update` returns a seeded update tree, `optax.apply_updates` / `incremental_update` are optax's two one-line
+  formulas (p + u;  old + s * (new - old))."""
+  import jax
+  import jax.numpy as jnp
+  path = os.path.join(REF, "big_vision", "trainers", "train_ae.py")
+  tree = ast.parse(open(path).read(), filename=path)
+  node = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "update_fn")
+  node.decorator_list = []
+  code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+  name = STEP["case"]
+  mkw, tkw, B, n_noise = CASES[name]
+  engine_model, _ = U.make_models(**mkw)
+  params_t = U.cpu_tree(U.perturb_init(engine_model, PARAM_SEED, "cpu"))
+  batch, rand = U.make_batch(engine_model, B, n_noise=n_noise, seed=BATCH_SEED, use_labels=tkw["use_labels"], device="cpu")
+  params = tree64(params_t)
+  upd = step_updates(params_t)
+  n_clean = B - n_noise
+  K = jax.Key
+  second = K({"split": [K(), K(), K({"uniform": np64(rand["mask_noise_noise"])}),
+                        K({"bernoulli": np64(rand["label_drop_noise"].double())})]})              # rng, model, mae, cfg (:303)
+  root = K({"split": [second, K(), K({"randint": rand["t"].numpy().astype(np.int32)}), K({"normal": np64(rand["noise"])}),
+                      K({"uniform": np64(rand["mask_noise_clean"])}), K({"bernoulli": np.zeros((n_clean,))})]})   # (:302)
+
+  def add(a, b):
+    return {k: (add(a[k], b[k]) if isinstance(a[k], dict) else a[k] + b[k]) for k in a}
+
+  def unflat(flat_t):
+    out = {}
+    for path_, v in flat_t.items():
+      d = out
+      for k in path_[:-1]:
+        d = d.setdefault(k, {})
+      d[path_[-1]] = v.numpy()
+    return out
+  updates = unflat(upd)
+  optax = types.SimpleNamespace(
+      apply_updates=add,
+      incremental_update=lambda new, old, s: {k: (optax.incremental_update(new[k], old[k], s) if isinstance(new[k], dict)
+                                                  else old[k] + s * (new[k] - old[k])) for k in new})
+  env = dict(jax=types.SimpleNamespace(random=jax.random, tree_util=jax.tree_util,
+                                       value_and_grad=lambda f: (lambda p: (f(p), None))),
+             jnp=jnp, optax=optax, q_sample=gdm.q_sample, model=ae.Model(**mkw),
+             tx=types.SimpleNamespace(update=lambda grads, opt, p: (updates, opt)),
+             config=Config(diffusion_space=(64, 64, 3), ema_decay=STEP["ema_decay"], **tkw))
+  exec(code, env)
+  state = {"params": params, "ema_params": jax.tree_map(lambda a: 0.9 * a, params), "opt": {"count": 0}, "rng": root,
+           "gd": gdm.create_gaussian_diffusion("cosine", 1000)}
+  new_state, meas = env["update_fn"](state, {"image": jnp.asarray(np64(batch["image"])),
+                                             "label": jnp.asarray(batch["label"].numpy().astype(np.int32))})
+  fl = flatten(new_state["params"])
+  fe = flatten(new_state["ema_params"])
+  probe = ("final_conv", "bias")
+  out = {"lines": (node.lineno, node.end_lineno), "training_loss": float(meas["training_loss"]),
+         "l2_params": float(meas["l2_params"]), "l2_updates": float(meas["l2_updates"]),
+         "new_param_probe": torch.from_numpy(np.asarray(fl[probe])), "new_ema_probe": torch.from_numpy(np.asarray(fe[probe])),
+         "state_keys": sorted(new_state)}
+  print("update_fn:", {k: out[k] for k in ("lines", "training_loss", "l2_params", "l2_updates", "state_keys")})
+  return out
+
+
 def main():
   ae, gdm, loss_code, loss_lines = load_reference()
   if sys.argv[1:] == ["sampler"]:
     path = os.path.join(HERE, "reference_sampler_golden.pt")
     torch.save({"provenance": "create_apply_fn + ddim_sample_loop of the reference executed over tests/golden/refshim",
-                "sampler": sampler_vectors(ae, gdm), "evaluators": evaluator_vectors(ae, gdm)}, path)
+                "sampler": sampler_vectors(ae, gdm), "evaluators": evaluator_vectors(ae, gdm),
+                "update_fn": update_fn_vectors(ae, gdm)}, path)
     print(path, os.path.getsize(path), "bytes")
     return
   gold = {"provenance": "reference source executed over tests/golden/refshim (numpy fp64); loss_fn = train_ae.py:%d-%d"

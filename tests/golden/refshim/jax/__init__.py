@@ -128,7 +128,7 @@ def _tree_flatten(tree):
   return leaves, _TreeDef(walk(tree))
 
 
-tree_util = _types.SimpleNamespace(tree_flatten=_tree_flatten, tree_map=tree_map)
+tree_util = _types.SimpleNamespace(tree_flatten=_tree_flatten, tree_map=tree_map, tree_leaves=lambda t: _tree_flatten(t)[0])
 
 
 def jit(fn=None, **_kw):

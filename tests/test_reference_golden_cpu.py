@@ -178,3 +178,31 @@ def test_evaluator_functions_match_reference_source():
   assert abs(float(loss) - gold["loss"]) <= 1e-11
   assert U.rel_l2(x_t[:2], gold["x_t"]) <= 1e-6 and U.rel_l2(pred[:2, ..., :C], gold["pred_x0"]) <= 1e-6
   assert U.rel_l2(O.predict_xstart_from_eps(gd, x_t, t, pred[..., C:])[:2], gold["pred_x0_eps"]) <= 1e-6
+
+
+def test_whole_update_fn_matches_reference_source():
+  """The reference's entire update_fn (train_ae.py:291-382, lifted; library calls stood in) on the umd_lbl_s4 case: its own RNG
+  split tree, batch split, label slicing, q_sample and loss must land on the loss the oracle's update_step computes from
+  the same draws; l2_params is the norm of the UPDATED parameters, l2_updates of the updates, and the EMA moves from the
+  old average towards the new parameters by ema_decay (train_ae.py:366-377)."""
+  import math
+  S = RG.STEP
+  gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_sampler_golden.pt"))["update_fn"]
+  model, ocfg, tkw, params, batch, rand, n_noise, want = rebuild(S["case"])
+  assert gold["training_loss"] == want["loss"]                       # update_fn and the separately lifted loss_fn agree exactly
+  p64 = to64(params)
+  state = {"params": p64, "gd": O.gaussian_diffusion_tables("cosine", 1000), "opt": O.init_opt_state(p64)}
+  hp = dict(clip_norm=1.0, peak_lr=1e-3, warmup_steps=0, total_steps=1000, b1=0.9, b2=0.95, wd=0.05)
+  _, meas, _ = O.update_step(state, batch, ocfg, tkw, hp, rand, dtype=F64)
+  # update_step forms x_t in float32 (as the reference does on device, train_ae.py:183-185) even when the model runs in float64
+  assert abs(meas["training_loss"] - gold["training_loss"]) <= 1e-9
+  upd = RG.step_updates(params)
+  flat = RG.flatten(p64)
+  assert gold["l2_updates"] == pytest.approx(math.sqrt(sum(float((u ** 2).sum()) for u in upd.values())), rel=1e-12)
+  assert gold["l2_params"] == pytest.approx(math.sqrt(sum(float(((flat[k] + upd[k]) ** 2).sum()) for k in flat)), rel=1e-12)
+  k = ("final_conv", "bias")
+  new_p = flat[k] + upd[k]
+  assert torch.allclose(gold["new_param_probe"], new_p, rtol=0, atol=1e-15)
+  old_ema = 0.9 * flat[k]
+  assert torch.allclose(gold["new_ema_probe"], old_ema + S["ema_decay"] * (new_p - old_ema), rtol=0, atol=1e-15)
+  assert gold["state_keys"] == ["ema_params", "gd", "opt", "params", "rng"]
