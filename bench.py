@@ -63,6 +63,79 @@ def step_flops_per_image(cfg, tkw):
   return 3.0 * ((1 - pn) * fwd(k0) + pn * fwd(k1))
 
 
+def make_device_batches(cfg, per_gpu, dev, rank, count=4):
+  """Synthetic batches of SURVEY.md §8d: image ~ U(-1, 1) f32[B,H,W,C], label ~ U{0..num_classes-1}, generated on the
+  device from seed 1 + rank (every rank gets its own shard of the global batch)."""
+  import torch
+  H, C = cfg.img_size, cfg.channels
+  g = torch.Generator(device=dev).manual_seed(1 + rank)
+  return [{"image": torch.rand(per_gpu, H, H, C, device=dev, generator=g) * 2 - 1,
+           "label": torch.randint(0, max(cfg.num_classes or 1, 1), (per_gpu,), device=dev, generator=g)}
+          for _ in range(count)]
+
+
+def first_loss_check(workload, per_gpu, world, first_loss):
+  """The loss of the first step (initial parameters, rank-0 batch and draws) against the value the fp32 oracle gives
+  for the same state, batch and draws (tests/golden/bench_loss_golden.json, written on a B200 by
+  tests/golden/make_bench_loss_golden.py and re-checked by tests/test_fullsize_gpu.py).  One GPU only: with N > 1 the
+  loss slot is the mean over ranks."""
+  path = os.path.join(ROOT, "tests", "golden", "bench_loss_golden.json")
+  if world != 1 or not os.path.exists(path):
+    return None
+  with open(path) as f:
+    g = json.load(f).get(workload)
+  if not g or g.get("per_gpu_batch") != per_gpu:
+    return None
+  rel = abs(first_loss - g["oracle_loss"]) / abs(g["oracle_loss"])
+  out = {"first_loss": first_loss, "oracle_fp32_loss": g["oracle_loss"], "rel_err": rel, "tolerance": 1e-2, "ok": rel <= 1e-2}
+  if not out["ok"]:
+    raise SystemExit(f"bench: first-step loss {first_loss} differs from the fp32 oracle's {g['oracle_loss']} by {rel:.3g} (> 1e-2)")
+  return out
+
+
+def dp_check(update_fn, state, model, dev_batches_of, world, rank, pg, dev):
+  """Data-parallel correctness on NCCL (train_ae.py:159-170,287-290,364), run once after the timed region at N > 1:
+    * the all-reduced gradient arena of one extra step against rank 0's own replay of EVERY rank's shard (same batches,
+      same per-rank draws) averaged on one GPU — i.e. the N-rank step against the 1-rank computation of the global batch;
+    * bit-equality across ranks of the parameters (and of the reduced gradients) after the timed steps."""
+  import torch
+  import torch.distributed as dist
+  n = model.layout.total
+  fb = update_fn.forward_backward
+  batch = dev_batches_of(rank)[0]
+  _, _, grads, _ = fb(state, batch, reduce=True)
+  torch.cuda.synchronize()
+  g_dp = grads[:n + 1].clone()           # slot n carries the loss
+  out = {}
+  # cross-rank equality: compare every rank's checksum pair with rank 0's
+  arena = state["params"].arena
+  sums = torch.stack([arena.double().sum(), arena.double().abs().sum(), g_dp[:n].double().sum(), g_dp[:n].double().abs().sum()])
+  gathered = [torch.empty_like(sums) for _ in range(world)]
+  dist.all_gather(gathered, sums, group=pg)
+  out["param_checksums_equal"] = all(torch.equal(gathered[0][:2], x[:2]) for x in gathered)
+  out["reduced_grad_checksums_equal"] = all(torch.equal(gathered[0][2:], x[2:]) for x in gathered)
+  out["param_checksum"] = float(gathered[0][0])
+  if rank == 0:
+    acc = torch.zeros(n + 1, dtype=torch.float64, device=dev)
+    for r in range(world):
+      b = dev_batches_of(r)[0]
+      _, _, g, _ = fb(state, b, rand_rank=r, reduce=False)
+      acc += g[:n + 1].double()
+    acc /= world
+    torch.cuda.synchronize()
+    d, ref = (g_dp[:n].double() - acc[:n]), acc[:n]
+    out["grad_rel_l2_vs_one_rank"] = float(d.norm() / ref.norm())
+    out["grad_cosine_vs_one_rank"] = float((g_dp[:n].double() @ ref) / (g_dp[:n].double().norm() * ref.norm()))
+    out["loss_dp"] = float(g_dp[n])
+    out["loss_one_rank"] = float(acc[n])
+    out["loss_rel_err"] = abs(out["loss_dp"] - out["loss_one_rank"]) / abs(out["loss_one_rank"])
+    # fp32 atomics reorder additions between runs (~1e-7 .. 5e-5 on a few leaves, tests/test_properties_gpu.py)
+    out["ok"] = bool(out["param_checksums_equal"] and out["reduced_grad_checksums_equal"] and
+                     out["grad_rel_l2_vs_one_rank"] <= 1e-3 and out["loss_rel_err"] <= 1e-5)
+  dist.barrier()
+  return out
+
+
 def load_peaks():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(p):
@@ -211,6 +284,7 @@ def main():
   ap.add_argument("--cpu-batch", type=int, default=8)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-dp-check", action="store_true")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 1)
   if args.impl == "reference":
@@ -250,11 +324,8 @@ def main():
   update_fn = make_update_fn(model, tcfg, process_group=pg)
 
   H, C = cfg.img_size, cfg.channels
-  g = torch.Generator(device=dev).manual_seed(1 + rank)
   n_dev_batches = 4   # 4 x 25 MB of inputs; activations written per step (tens of GB) flush the 126 MB L2 anyway
-  dev_batches = [{"image": torch.rand(per_gpu, H, H, C, device=dev, generator=g) * 2 - 1,
-                  "label": torch.randint(0, max(cfg.num_classes or 1, 1), (per_gpu,), device=dev, generator=g)}
-                 for _ in range(n_dev_batches)]
+  dev_batches = make_device_batches(cfg, per_gpu, dev, rank, n_dev_batches)
   host_batches = [{k: v.cpu().pin_memory() for k, v in b.items()} for b in dev_batches]
 
   def barrier():
@@ -352,6 +423,12 @@ def main():
   final_loss = float(losses[-1])
   if not math.isfinite(final_loss):
     raise SystemExit(f"non-finite training loss {final_loss}")
+  loss_check = first_loss_check(args.workload, per_gpu, world, float(losses[0])) if rank == 0 else None
+  dp = None
+  if world > 1 and not args.no_dp_check:
+    dp = dp_check(update_fn, state, model, lambda r: make_device_batches(cfg, per_gpu, dev, r, 1), world, rank, pg, dev)
+    if rank == 0 and not dp["ok"]:
+      raise SystemExit(f"bench: data-parallel check failed: {dp}")
 
   if rank == 0:
     peaks = load_peaks()
@@ -399,7 +476,7 @@ def main():
                    "precision": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / loss / AdamW (bf16 mu)"},
         "step_tflops_per_gpu": fl_img * value / world / 1e12,
         "step_frac_of_bf16_peak": fl_img * value / world / 1e12 / peaks["tf_sustained"],
-        "flops_per_image": fl_img, "final_loss": final_loss,
+        "flops_per_image": fl_img, "final_loss": final_loss, "loss_check": loss_check, "dp_check": dp,
         "roofline": roofline, "breakdown": breakdown, "profile_scopes_dropped": dropped,
         "ms_per_step_profiled": ms_step_prof,
         "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,

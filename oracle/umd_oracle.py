@@ -89,15 +89,16 @@ def q_sample(gd: dict, x_start: torch.Tensor, t: torch.Tensor, noise: torch.Tens
   """gaussian_diffusion.py:85-98,286-289.  Tables are float32 on device in the reference
   (train_ae.py:183-185 with x64 off), so they are cast to x_start's dtype before the gather."""
   dt = x_start.dtype
-  ca = torch.as_tensor(np.asarray(gd["sqrt_alphas_cumprod"])).to(dt)[t.reshape(-1).long()]
-  cb = torch.as_tensor(np.asarray(gd["sqrt_one_minus_alphas_cumprod"])).to(dt)[t.reshape(-1).long()]
+  dv = x_start.device   # the oracle also runs in fp32 on the GPU as the full-size secondary oracle (SURVEY.md §8c)
+  ca = torch.as_tensor(np.asarray(gd["sqrt_alphas_cumprod"])).to(device=dv, dtype=dt)[t.reshape(-1).long().to(dv)]
+  cb = torch.as_tensor(np.asarray(gd["sqrt_one_minus_alphas_cumprod"])).to(device=dv, dtype=dt)[t.reshape(-1).long().to(dv)]
   shp = (-1,) + (1,) * (x_start.dim() - 1)
   return ca.reshape(shp) * x_start + cb.reshape(shp) * noise
 
 
 def _extract(gd, key, t, x):
   """gaussian_diffusion.py:286-289 _extract_into_tensor (tables float32 on device, train_ae.py:183-185)."""
-  arr = torch.as_tensor(np.asarray(gd[key])).to(x.dtype)
+  arr = torch.as_tensor(np.asarray(gd[key])).to(device=x.device, dtype=x.dtype)
   return arr[t.reshape(-1).long()].reshape((-1,) + (1,) * (x.dim() - 1))
 
 
@@ -209,7 +210,7 @@ def random_masking(x, mask_ratio, noise):
   ids_restore = torch.argsort(ids_shuffle, dim=1, stable=True)
   ids_keep = ids_shuffle[:, :keep]
   x_masked = torch.gather(x, 1, ids_keep[:, :, None].expand(-1, -1, x.shape[2]))
-  mask = torch.ones(N, L, dtype=x.dtype)
+  mask = torch.ones(N, L, dtype=x.dtype, device=x.device)
   mask[:, :keep] = 0
   mask = torch.gather(mask, 1, ids_restore)
   return x_masked, mask, ids_restore
@@ -249,7 +250,7 @@ def time_embedding(t, width, dtype):
   """embeddings.py:13-31."""
   half = width // 2
   step = math.log(10000) / (half - 1)
-  freq = torch.exp(torch.arange(half, dtype=dtype) * -step)
+  freq = torch.exp(torch.arange(half, dtype=dtype, device=t.device) * -step)
   e = t.to(dtype) * freq
   return torch.cat([torch.sin(e), torch.cos(e)], dim=-1)
 
@@ -349,7 +350,7 @@ def model_apply(params, cfg, image, *, t=None, y=None, cfg_scale=None, mask=0.0,
     nh = image.shape[0]
     image = torch.cat([image, image], 0)
     t = torch.cat([t, t], 0)
-    y = torch.cat([y, torch.full((nh,), nc, dtype=y.dtype)], 0)
+    y = torch.cat([y, torch.full((nh,), nc, dtype=y.dtype, device=y.device)], 0)
   n = image.shape[0]
   # ---- embed
   pt = patchify(image, ps)
@@ -358,9 +359,9 @@ def model_apply(params, cfg, image, *, t=None, y=None, cfg_scale=None, mask=0.0,
   L = h * w
   x = x.reshape(n, L, D)
   if t is None:
-    t = torch.zeros(n, 1, dtype=torch.int32)
+    t = torch.zeros(n, 1, dtype=torch.int32, device=image.device)
   if y is None and nc is not None:
-    y = torch.full((n,), nc, dtype=torch.long)
+    y = torch.full((n,), nc, dtype=torch.long, device=image.device)
   if y is not None:
     assert nc is not None, "num_classes must be provided if y is not None"
     yy = y.long()
@@ -368,7 +369,7 @@ def model_apply(params, cfg, image, *, t=None, y=None, cfg_scale=None, mask=0.0,
       yy = torch.where(label_drop.bool(), torch.full_like(yy, nc), yy)
     y_cond = embedding_trunk(params["label_emb"]["embedding"]["embedding"][yy], params["label_trunk"])
   else:
-    y_cond = torch.zeros(n, D, dtype=dtype)
+    y_cond = torch.zeros(n, D, dtype=dtype, device=image.device)
   time_cond = embedding_trunk(time_embedding(t.reshape(n, 1), D, dtype), params["time_trunk"])
   cond = F.silu(time_cond + y_cond) if adaln else time_cond + y_cond
   # ---- encode
@@ -422,7 +423,7 @@ def loss_fn(params, cfg, tc, x0_noise, x_t_noise, x0_clean, t, noise, labels, ra
   B = n_noise + n_clean
   aux = {}
   if n_clean > 0:
-    pred, out = model_apply(params, cfg, x0_clean, t=torch.zeros(n_clean, 1, dtype=torch.int32), train=True,
+    pred, out = model_apply(params, cfg, x0_clean, t=torch.zeros(n_clean, 1, dtype=torch.int32, device=x0_clean.device), train=True,
                             mask=tc["mask_ratio_no_noise"], mask_noise=rand.get("mask_noise_clean"), dtype=dtype)
     m = out["mask"]
     se = (pred[..., :C] - x0_clean.to(dtype)) ** 2

@@ -102,12 +102,28 @@ def _normal(rng, shape, device):
   return torch.randn(shape, device=device, generator=rng if isinstance(rng, torch.Generator) else None)
 
 
-def _as_generator(rng, device):
+def seed_from_rng(rng, rank=0, stream=0):
+  """Integer seed from train_state["rng"] (a replicated int64 [seed, step] pair, the stand-in for the reference's
+  PRNGKey that update_fn splits every step, train_ae.py:302-303), an int, or None.  `rank` de-correlates the draws of
+  data-parallel ranks (the reference draws t / noise / masks i.i.d. over the GLOBAL batch, train_ae.py:302-317), `stream`
+  separates consumers of the same key (training step, evaluators)."""
+  import torch
+  if rng is None:
+    base = 0
+  elif isinstance(rng, torch.Tensor):
+    v = [int(x) for x in rng.reshape(-1).tolist()]
+    base = v[0] * 1_000_003 + (v[1] if len(v) > 1 else 0)
+  else:
+    base = int(rng)
+  return (base + 7_919 * int(rank) * 1_000_000_007 + 104_729 * int(stream)) % (2 ** 63 - 1)
+
+
+def _as_generator(rng, device, rank=0, stream=0):
   import torch
   if rng is None or isinstance(rng, torch.Generator):
     return rng
   g = torch.Generator(device=device)
-  g.manual_seed(int(rng))
+  g.manual_seed(seed_from_rng(rng, rank, stream))
   return g
 
 

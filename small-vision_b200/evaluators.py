@@ -41,7 +41,8 @@ def create_noised_pred_fn(model, t):
     batched_t = torch.full((B, 1), int(t), dtype=torch.int32, device=images.device)
     noise = _rand(batch, "noise")
     if noise is None:
-      noise = torch.randn(images.shape, device=images.device, generator=_d._as_generator(train_state.get("rng"), images.device))
+      noise = torch.randn(images.shape, device=images.device,
+                          generator=_d._as_generator(train_state.get("rng"), images.device, stream=1))
     x_t = _d.q_sample(gd=train_state["gd"], x_start=images, t=batched_t, noise=noise.to(images.device).contiguous())
     _, out = model.apply({"params": train_state["params"]}, x_t, t=batched_t + 1)
     return None, out
@@ -73,13 +74,15 @@ def make_eval_loss_fn(model, use_labels=False, channels=None):
     gd = train_state["gd"]
     dev = images.device
     labels = batch["label"].to(dev) if use_labels else None
-    g = _d._as_generator(train_state.get("rng"), dev)
+    g = None   # built only when a draw is needed (train_state["rng"] is the [seed, step] pair of create_train_state)
     t = _rand(batch, "t")
     if t is None:
+      g = _d._as_generator(train_state.get("rng"), dev, stream=2)
       t = torch.randint(0, int(gd["betas"].numel()), (B, 1), device=dev, generator=g, dtype=torch.int32)
     t = t.to(device=dev, dtype=torch.int32).reshape(B, 1)
     noise = _rand(batch, "noise")
     if noise is None:
+      g = g if g is not None else _d._as_generator(train_state.get("rng"), dev, stream=2)
       noise = torch.randn(images.shape, device=dev, generator=g)
     noise = noise.to(dev).contiguous()
     x_t = _d.q_sample(gd=gd, x_start=images, t=t, noise=noise)

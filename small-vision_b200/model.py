@@ -31,7 +31,6 @@ class ViTAE:
     self._mcfg = lib.model_cfg_struct(cfg)
     self._offsets = self.layout.offsets_tensor()
     self._ws = {}       # (shape tuple, train) -> workspace tensor
-    self._shadow = {}   # arena data_ptr -> (version, bf16 shadow)
     self.no_decay_list = cfg.no_decay_list
 
   # ---- reference surface -----------------------------------------------------------------
@@ -126,20 +125,28 @@ class ViTAE:
     return torch.rand(n, L, device=dev, generator=_generator(rng, dev))
 
   def shadow_of(self, arena):
-    """bf16 copy of the arena consumed by the GEMMs; refreshed whenever torch saw the arena change.
-    (The optimiser kernel rewrites it itself and registers the result through set_shadow.)"""
-    key = arena.data_ptr()
-    ver = arena._version
-    hit = self._shadow.get(key)
-    if hit is not None and hit[0] == ver and hit[1].numel() == arena.numel():
-      return hit[1]
-    sh = hit[1] if hit is not None and hit[1].numel() == arena.numel() else torch.empty_like(arena, dtype=torch.bfloat16)
+    """bf16 copy of the arena consumed by the GEMMs.  The shadow lives ON the arena tensor object (so it dies with it
+    and a new arena that reuses the address can never hit it) together with the torch version it was cast at and a
+    validity flag: writes through torch bump the version, writes through the C ABI (umd_adamw_step updates the
+    parameter and EMA arenas through raw pointers) must be announced with set_shadow / invalidate_shadow."""
+    ent = getattr(arena, "_umd_shadow", None)
+    if ent is not None and ent[0] and ent[1] == arena._version and ent[2].numel() == arena.numel():
+      return ent[2]
+    sh = ent[2] if ent is not None and ent[2].numel() == arena.numel() and ent[2].device == arena.device else \
+        torch.empty_like(arena, dtype=torch.bfloat16)
     lib.cast_bf16(arena, sh)
-    self._shadow[key] = (ver, sh)
+    arena._umd_shadow = (True, arena._version, sh)
     return sh
 
   def set_shadow(self, arena, shadow):
-    self._shadow[arena.data_ptr()] = (arena._version, shadow)
+    """The caller's kernel has just rewritten `shadow` from `arena` (umd_adamw_step refreshes params_bf16 itself)."""
+    arena._umd_shadow = (True, arena._version, shadow)
+
+  def invalidate_shadow(self, arena):
+    """`arena` was modified through the C ABI without refreshing its shadow (the EMA arena after every step)."""
+    ent = getattr(arena, "_umd_shadow", None)
+    if ent is not None:
+      arena._umd_shadow = (False, ent[1], ent[2])
 
   def workspace(self, shape, train, device):
     key = (shape.n0, shape.n1, shape.keep0, shape.keep1, shape.masked0, shape.masked1, bool(train), str(device))

@@ -77,11 +77,28 @@ def get_value_range(vmin=-1, vmax=1, in_min=0, in_max=255.0, clip_values=False):
   return _value_range
 
 
+class _Draws:
+  """Per-op random stream: seeded once (optionally per data-parallel rank) and advanced on every call, so that successive
+  batches get fresh crop windows / flips like the reference's per-example tf.random ops; data["_seed"] (an explicit
+  per-batch seed) still overrides it for reproducible runs."""
+
+  def __init__(self, seed=0, rank=0):
+    self.ss = np.random.SeedSequence([int(seed), int(rank)])
+    self.calls = 0
+
+  def next_seed(self, data):
+    if "_seed" in data:
+      return int(data["_seed"])
+    self.calls += 1
+    return int(np.random.SeedSequence([*self.ss.entropy, self.calls]).generate_state(1, dtype=np.uint64)[0] >> 1)
+
+
 def get_decode_jpeg_and_inception_crop(size=None, area_min=5, area_max=100, ratio_min=0.75, ratio_max=1.33,
-                                       method="bilinear", antialias=False):
+                                       method="bilinear", antialias=False, seed=0, rank=0):
   """pp/ops_image.py:197-242 on already decoded uint8 images: returns the resized crop as uint8.  The windows come from
   data["_boxes"] when present, else from sample_inception_boxes seeded by data.get("_seed", 0)."""
   assert method == "bilinear" and not antialias, "only the reference recipe's resize (bilinear, antialias=False) is fused"
+  draws = _Draws(seed, rank)
 
   def _inception_crop(data):
     img = torch.as_tensor(data["image"])
@@ -89,35 +106,40 @@ def get_decode_jpeg_and_inception_crop(size=None, area_min=5, area_max=100, rati
     boxes = data.get("_boxes")
     if boxes is None:
       boxes = sample_inception_boxes(n, H, W, area_min=area_min, area_max=area_max, ratio_min=ratio_min,
-                                     ratio_max=ratio_max, seed=data.get("_seed", 0))
+                                     ratio_max=ratio_max, seed=draws.next_seed(data))
     _, u8 = augment(img, boxes=boxes, size=size, return_uint8=True)
     return {**data, "image": u8}
   return _inception_crop
 
 
-def get_random_flip_lr():
+def get_random_flip_lr(seed=0, rank=0):
   """pp/ops_image.py:306-314: flips each image with probability 1/2 (data["_flips"] supplies the draws)."""
+  draws = _Draws(seed + 1, rank)
+
   def _random_flip_lr_pp(data):
     img = torch.as_tensor(data["image"])
     flips = data.get("_flips")
     if flips is None:
-      flips = np.random.default_rng(data.get("_seed", 0) + 1).random(img.shape[0]) < 0.5
+      flips = np.random.default_rng(draws.next_seed(data) + 1).random(img.shape[0]) < 0.5
     _, u8 = augment(img, flips=flips, return_uint8=True)
     return {**data, "image": u8}
   return _random_flip_lr_pp
 
 
-def make_train_preprocess(size, area_min=5, area_max=100, vmin=-1, vmax=1):
+def make_train_preprocess(size, area_min=5, area_max=100, vmin=-1, vmax=1, seed=0, rank=0):
   """The whole training string of configs/ae_i1k.py:64-69 after decoding, as a single launch."""
+  draws = _Draws(seed, rank)
+
   def _pp(data):
     img = torch.as_tensor(data["image"])
     n, H, W, _ = img.shape
     boxes = data.get("_boxes")
+    sd = draws.next_seed(data) if (boxes is None or data.get("_flips") is None) else 0
     if boxes is None:
-      boxes = sample_inception_boxes(n, H, W, area_min=area_min, area_max=area_max, seed=data.get("_seed", 0))
+      boxes = sample_inception_boxes(n, H, W, area_min=area_min, area_max=area_max, seed=sd)
     flips = data.get("_flips")
     if flips is None:
-      flips = np.random.default_rng(data.get("_seed", 0) + 1).random(n) < 0.5
+      flips = np.random.default_rng(sd + 1).random(n) < 0.5
     out = {"image": augment(img, boxes=boxes, flips=flips, size=size, vmin=vmin, vmax=vmax)}
     if "label" in data:
       out["label"] = data["label"]       # keep("image", "label")

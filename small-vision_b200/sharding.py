@@ -88,9 +88,11 @@ class GradientReducer:
     self.pg = process_group
     self.works = []
     self.world = 1
+    self.rank = 0
     if process_group is not None:
       import torch.distributed as dist
       self.world = dist.get_world_size(process_group)
+      self.rank = dist.get_rank(process_group)
 
   def bucket_view(self, grads, k):
     lo, hi = self.layout.bucket_bounds[k]

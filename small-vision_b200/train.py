@@ -14,7 +14,7 @@ import torch
 
 from . import lib
 from .config import TrainConfig, warmup_cosine_lr
-from .diffusion import create_gaussian_diffusion, q_sample, to_device
+from .diffusion import create_gaussian_diffusion, q_sample, seed_from_rng, to_device
 from .model import ViTAE, mask_argsort
 from .params import ParamTree, arena_from_tree, tree_from_arena
 from .sharding import GradientReducer
@@ -65,7 +65,40 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
   sc.grads = None
   wd_flags = {}
 
-  def update_fn(train_state, batch):
+  def draw_step_randoms(train_state, B, dev, *, supplied=None, rank=0):
+    """The draws the reference makes inside one step (train_ae.py:302-317, ae.py:14, embeddings.py:44), in a fixed
+    order from one generator: t ~ U{0..T-1} [n_noise], noise ~ N(0,1), the two branches' mask uniforms [n, L] and the
+    label-drop mask.  Entries of `supplied` (batch["_rand"]) replace the corresponding draws.  train_state["rng"] stays
+    replicated; every data-parallel rank draws for its own shard (i.i.d. over the global batch like the reference), so
+    the rank is mixed into the seed."""
+    supplied = supplied or {}
+    n_clean = int(B * tcfg.no_noise_prob)          # train_ae.py:304
+    n_noise = B - n_clean
+    L = cfg.num_patches
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed_from_rng(train_state["rng"], rank=rank))
+    T = train_state["gd"]["betas"].numel()
+    out = {}
+    out["t"] = supplied["t"].reshape(-1).to(device=dev, dtype=torch.int32) if "t" in supplied else \
+        torch.randint(0, T, (n_noise,), device=dev, generator=gen, dtype=torch.int32)
+    shape = (n_noise, cfg.img_size, cfg.img_size, cfg.channels)
+    out["noise"] = supplied["noise"].to(dev).contiguous() if "noise" in supplied else \
+        torch.randn(shape, device=dev, generator=gen)
+    if tcfg.mask_ratio > 0.0 and n_noise > 0:
+      out["mask_noise_noise"] = supplied["mask_noise_noise"].to(dev).float().contiguous() \
+          if "mask_noise_noise" in supplied else torch.rand(n_noise, L, device=dev, generator=gen)
+    if n_clean > 0:
+      out["mask_noise_clean"] = supplied["mask_noise_clean"].to(dev).float().contiguous() \
+          if "mask_noise_clean" in supplied else torch.rand(n_clean, L, device=dev, generator=gen)
+    if cfg.num_classes is not None and tcfg.use_labels and n_noise > 0:
+      out["label_drop_noise"] = supplied["label_drop_noise"].to(dev) if "label_drop_noise" in supplied else \
+          (torch.rand(n_noise, device=dev, generator=gen) < cfg.cfg_dropout_rate)
+    return out
+
+  def forward_backward(train_state, batch, *, rand_rank=None, reduce=True):
+    """Draws, q_sample, forward of both branches, loss and backward; with reduce the gradient arena is mean-all-reduced
+    over the process group.  Returns (arena, shadow, grads, loss_slot).  rand_rank overrides the rank that seeds the
+    draws (bench.py's data-parallel check replays other ranks' shards on rank 0)."""
     images = batch["image"]
     assert images.is_cuda and images.dtype == torch.float32, "batch['image'] must be a float32 CUDA tensor"
     images = images.contiguous()
@@ -74,32 +107,20 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     n_clean = int(B * tcfg.no_noise_prob)          # train_ae.py:304
     n_noise = B - n_clean
     L = cfg.num_patches
-    rand = batch.get("_rand", {})
-    rng = train_state["rng"]
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(int(rng[0]) * 1_000_003 + int(rng[1]))
-
-    # ---- draws (train_ae.py:316-317, ae.py:14, embeddings.py:44)
-    T = train_state["gd"]["betas"].numel()
-    t = rand["t"].reshape(-1).to(device=dev, dtype=torch.int32) if "t" in rand else \
-        torch.randint(0, T, (n_noise,), device=dev, generator=gen, dtype=torch.int32)
-    noise = rand["noise"].to(dev).contiguous() if "noise" in rand else \
-        torch.randn((n_noise,) + tuple(images.shape[1:]), device=dev, generator=gen)
     masked0 = tcfg.mask_ratio > 0.0 and n_noise > 0
     masked1 = n_clean > 0
     keep0 = cfg.len_keep(tcfg.mask_ratio) if masked0 else L
     keep1 = cfg.len_keep(tcfg.mask_ratio_no_noise) if masked1 else L
+    rand = draw_step_randoms(train_state, B, dev, supplied=batch.get("_rand"),
+                             rank=reducer.rank if rand_rank is None else rand_rank)
+    t, noise = rand["t"], rand["noise"]
     ids_shuffle = torch.empty(B, L, dtype=torch.int32, device=dev)
     ids_restore = torch.empty(B, L, dtype=torch.int32, device=dev)
     if masked0:
-      mn = rand["mask_noise_noise"].to(dev).float().contiguous() if "mask_noise_noise" in rand else \
-          torch.rand(n_noise, L, device=dev, generator=gen)
-      a, b, _ = mask_argsort(mn, keep0)
+      a, b, _ = mask_argsort(rand["mask_noise_noise"], keep0)
       ids_shuffle[:n_noise], ids_restore[:n_noise] = a, b
     if masked1:
-      mn = rand["mask_noise_clean"].to(dev).float().contiguous() if "mask_noise_clean" in rand else \
-          torch.rand(n_clean, L, device=dev, generator=gen)
-      a, b, _ = mask_argsort(mn, keep1)
+      a, b, _ = mask_argsort(rand["mask_noise_clean"], keep1)
       ids_shuffle[n_noise:], ids_restore[n_noise:] = a, b
 
     # ---- model inputs: x_t for the noise branch (q_sample, :318-321), x_0 for the clean branch
@@ -113,9 +134,7 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
       labels = torch.full((B,), cfg.num_classes, dtype=torch.int32, device=dev)   # y=None -> null class (ae.py:107-110)
       if tcfg.use_labels and n_noise > 0:
         y = batch["label"][:n_noise].to(device=dev, dtype=torch.int32)
-        drop = rand["label_drop_noise"].to(dev) if "label_drop_noise" in rand else \
-            (torch.rand(n_noise, device=dev, generator=gen) < cfg.cfg_dropout_rate)
-        labels[:n_noise] = torch.where(drop, torch.full_like(y, cfg.num_classes), y)
+        labels[:n_noise] = torch.where(rand["label_drop_noise"], torch.full_like(y, cfg.num_classes), y)
 
     # ---- forward + loss + backward
     params = train_state["params"]
@@ -133,8 +152,15 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     model.forward_arena(arena, shadow, image=model_in, t=tm, labels=labels, n0=n_noise, n1=n_clean, keep0=keep0,
                         keep1=keep1, masked0=masked0, masked1=masked1, ids_shuffle=ids_shuffle, ids_restore=ids_restore,
                         want_pred=False, train=True, x0=images, noise=noise, loss_out=loss_slot)
-    model.backward_arena(arena, shadow, grads, bucket_cb=lambda k: reducer.launch(grads, k))
-    reducer.finish()                                  # implicit GSPMD all-reduce of train_ae.py:364
+    model.backward_arena(arena, shadow, grads, bucket_cb=(lambda k: reducer.launch(grads, k)) if reduce else None)
+    if reduce:
+      reducer.finish()                                # implicit GSPMD all-reduce of train_ae.py:364
+    return arena, shadow, grads, loss_slot
+
+  def update_fn(train_state, batch):
+    arena, shadow, grads, loss_slot = forward_backward(train_state, batch)
+    dev = arena.device
+    rng = train_state["rng"]
 
     # ---- optimiser (train_ae.py:365-366 with the chain of :135-151)
     opt = train_state["opt"]
@@ -156,7 +182,9 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     a.scratch, a.scratch_floats = lib.ptr(sc.opt_scratch), sc.opt_scratch.numel()
     a.measurements = lib.ptr(sc.meas)
     lib.check(lib.load().umd_adamw_step(C.byref(a), lib.current_stream()), "umd_adamw_step")
-    model.set_shadow(arena, shadow)
+    model.set_shadow(arena, shadow)                     # the kernel refreshed the parameter shadow ...
+    if "ema_params" in train_state:                     # ... but moved the EMA arena behind torch's back
+      model.invalidate_shadow(train_state["ema_params"].arena)
     opt["count"] = count + 1
     rng = rng.clone()
     rng[1] += 1
@@ -167,4 +195,6 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     return train_state, measurements
 
   update_fn.grads = lambda: sc.grads
+  update_fn.forward_backward = forward_backward
+  update_fn.draw_step_randoms = draw_step_randoms
   return update_fn

@@ -202,3 +202,16 @@ def test_batch_partition_rules():
   assert local_batch_slice(4096, 3, 8) == slice(1536, 2048)
   with pytest.raises(ValueError, match="divisible"):
     check_batch_divisible(100, 8)
+
+
+def test_seed_from_rng_mixes_rank_and_stream():
+  """train_state["rng"] is replicated; data-parallel ranks and the evaluator closures must not share draws."""
+  import torch
+  from small_vision_b200.diffusion import seed_from_rng
+  rng = torch.tensor([1, 7], dtype=torch.int64)
+  base = seed_from_rng(rng)
+  assert base == seed_from_rng(rng.clone()) == 1 * 1_000_003 + 7
+  seeds = {seed_from_rng(rng, rank=r, stream=s) for r in range(8) for s in range(3)}
+  assert len(seeds) == 24
+  assert seed_from_rng(torch.tensor([1, 8])) != base and seed_from_rng(5) == 5 and seed_from_rng(None) == 0
+  assert all(0 <= x < 2 ** 63 for x in seeds)

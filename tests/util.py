@@ -130,6 +130,12 @@ def oracle_hp(tcfg):
 
 
 def _compare_updated(ours, ref, init, what):
+  """Updated parameters against the oracle's.  General bound: relative L2 <= 2e-3 of the leaf.  Adam normalises the
+  update to ~lr per element, so on leaves whose VALUES are themselves ~lr or smaller — the N(0, 1e-6) MLP biases and the
+  zero-initialised biases (every path that ends in "bias"), plus zero-initialised `cls` — the leaf-relative error is
+  dominated by sign flips of near-zero gradient elements; only those leaves are bounded against the size of the update
+  instead (error <= 25 % of the update norm).  The optimiser arithmetic itself is checked to fp32 round-off in
+  tests/test_kernels_gpu.py::test_adamw_step_matches_oracle."""
   fo, fr, f0 = O.flatten_tree(ours), O.flatten_tree(ref), O.flatten_tree(init)
   worst = 0.0
   for k in fr:
@@ -137,8 +143,13 @@ def _compare_updated(ours, ref, init, what):
     r = rel_l2(a, b)
     upd = float((b.double() - c.double()).norm())
     err = float((a.double() - b.double()).norm())
-    assert r <= 2e-3 or err <= 0.25 * upd, f"{what} {'/'.join(k)}: rel {r:.4g}, err {err:.4g}, update {upd:.4g}"
-    worst = max(worst, min(r, err / (upd + 1e-30)))
+    small_valued = k[-1] == "bias" or k[0] == "cls"
+    if small_valued:
+      assert r <= 2e-3 or err <= 0.25 * upd, f"{what} {'/'.join(k)}: rel {r:.4g}, err {err:.4g}, update {upd:.4g}"
+      worst = max(worst, min(r, err / (upd + 1e-30)))
+    else:
+      assert r <= 2e-3, f"{what} {'/'.join(k)}: rel {r:.4g}, err {err:.4g}, update {upd:.4g}"
+      worst = max(worst, r)
   return worst
 
 
