@@ -182,9 +182,12 @@ typedef struct umd_model_cfg {
   int flip_final_conv;  /* 1 = flax ConvTranspose(transpose_kernel=False) orientation */
 } umd_model_cfg;
 
-/* Leaves of the parameter tree.  offsets[] are element offsets into the arena
- * (params / grads / bf16 shadow share one layout); -1 marks an absent leaf.  Stacked block leaves keep
- * the Flax [depth, ...] layout. */
+/* Leaves of the parameter tree.  offsets[] (UMD_OFFSETS_LEN entries) are element offsets into the
+ * arena (params / grads / bf16 shadow / mu / nu share one layout); -1 marks an absent leaf.
+ * The scanned blocks are stored LAYER-MAJOR: a block leaf's offset is that of its layer-0 slice, layer l's slice starts
+ * offsets[UMD_P_ENC_LAYER_STRIDE] (resp. _DEC_) elements further per layer, i.e. all leaves of one layer are contiguous.
+ * (Flax stacks every scanned leaf over depth, vit.py:131-148; with that layout no encoder gradient would be final before
+ * layer 0's backward has run.  The host-side tree presents the same [depth, ...] shapes as strided views.) */
 enum {
   UMD_P_CLS = 0, UMD_P_POS, UMD_P_DEC_POS, UMD_P_MASK_TOKEN, UMD_P_EMBED_W, UMD_P_EMBED_B,
   UMD_P_TT_W0, UMD_P_TT_B0, UMD_P_TT_W1, UMD_P_TT_B1,
@@ -192,7 +195,10 @@ enum {
   UMD_P_FMOD_W, UMD_P_FMOD_B, UMD_P_FCONV_W, UMD_P_FCONV_B,
   UMD_P_ENC_BASE,                       /* + UMD_S_* */
   UMD_P_DEC_BASE = UMD_P_ENC_BASE + 20, /* + UMD_S_* */
-  UMD_P_COUNT = UMD_P_DEC_BASE + 20
+  UMD_P_COUNT = UMD_P_DEC_BASE + 20,
+  UMD_P_ENC_LAYER_STRIDE = UMD_P_COUNT, /* elements between consecutive encoder layer blocks */
+  UMD_P_DEC_LAYER_STRIDE,               /* ... decoder layer blocks */
+  UMD_OFFSETS_LEN
 };
 enum {
   UMD_S_ADA_W = 0, UMD_S_ADA_B, UMD_S_LN0_S, UMD_S_LN0_B, UMD_S_LN1_S, UMD_S_LN1_B,
@@ -227,8 +233,12 @@ int umd_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const lon
                 const void* params_bf16, const umd_io* io, void* workspace, size_t workspace_bytes, int train,
                 umd_stream_t stream);
 /* Backward of the loss computed by the preceding umd_forward(train=1) on the same workspace; accumulates
- * into grads (which the caller zeroes).  cb(user, k) is called on the host as soon as every kernel writing
- * gradient bucket k (0 decoder side, 1 encoder, 2 embeddings/conditioning) has been enqueued. */
+ * into grads (which the caller zeroes).  cb(user, event) is called on the host as soon as every kernel writing a part
+ * of the gradient arena has been enqueued on `stream`: event 0 = the decoder side (final_conv, final_modulation,
+ * Decoder, dec_pos_embedding, image_mask_embedding); event 1 + j, j = 0 .. depth-1 = encoder layer depth-1-j (its
+ * layer block of the arena; j = 0 also covers Encoder/encoder_norm); event 1 + depth = everything (embeddings and the
+ * conditioning trunks).  A data-parallel caller all-reduces the finished arena ranges behind these events while the
+ * rest of the backward runs (train_ae.py:287-290,364). */
 int umd_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const float* params,
                  const void* params_bf16, float* grads, const umd_io* io, void* workspace, size_t workspace_bytes,
                  umd_bucket_cb cb, void* cb_user, umd_stream_t stream);

@@ -39,8 +39,9 @@ struct Stack {
   int depth, rows, nsamples, D;
   RowMap rm;
   int base;                 // leaf id base (UMD_P_ENC_BASE / UMD_P_DEC_BASE)
-  float* ada;               // [B, depth*6D] fp32 or null
-  float* dada;              // [B, depth*6D] fp32 gradient
+  long long lstride;        // arena stride between the layer blocks of this stack (layer-major parameter arena)
+  float* ada;               // [depth][B][6D] fp32 or null: adaLN shift0|scale0|gate0|shift1|scale1|gate1 per layer and sample
+  float* dada;              // [depth][B][6D] fp32 gradient
   bf16* dada_bf16;
   std::vector<float*> x;    // depth+1 residual snapshots
   std::vector<LayerBufs> L;
@@ -185,6 +186,15 @@ struct Ctx {
   bool has(int leaf) const { return offs[leaf] >= 0; }
 };
 
+// The stacks' layer strides travel behind the leaf offsets (include/umd_b200.h: offsets[UMD_P_ENC_LAYER_STRIDE / _DEC_]).
+int set_layer_strides(Ctx& c) {
+  c.P.enc.lstride = c.offs[UMD_P_ENC_LAYER_STRIDE];
+  c.P.dec.lstride = c.offs[UMD_P_DEC_LAYER_STRIDE];
+  UMD_REQUIRE(c.P.enc.lstride > 0 && c.P.dec.lstride > 0 && c.P.enc.lstride % 64 == 0 && c.P.dec.lstride % 64 == 0,
+              "offsets[UMD_P_ENC_LAYER_STRIDE / UMD_P_DEC_LAYER_STRIDE] must hold the layer strides of the layer-major arena");
+  return UMD_OK;
+}
+
 umd_gemm_args gemm_base(const void* A, const void* B, int M, int N, int K) {
   umd_gemm_args g;
   memset(&g, 0, sizeof(g));
@@ -267,9 +277,9 @@ int cond_forward(Ctx& c, const umd_io& io) {
     Stack* stacks[2] = {&P.enc, &P.dec};
     for (Stack* s : stacks) {
       umd_gemm_args g = gemm_base(P.cond_bf16, c.WB(s->base + UMD_S_ADA_W), B, 6 * D, D);
-      g.b_mn = 1; g.lda = D; g.ldb = 6 * D; g.batch = s->depth; g.a_bs = 0; g.b_bs = static_cast<long long>(D) * 6 * D;
-      g.epi = UMD_EPI_F32; g.out0 = s->ada; g.ld0 = static_cast<long long>(s->depth) * 6 * D; g.bs0 = 6 * D;
-      g.bias = c.W(s->base + UMD_S_ADA_B); g.bias_bs = 6 * D;
+      g.b_mn = 1; g.lda = D; g.ldb = 6 * D; g.batch = s->depth; g.a_bs = 0; g.b_bs = s->lstride;
+      g.epi = UMD_EPI_F32; g.out0 = s->ada; g.ld0 = 6 * D; g.bs0 = static_cast<long long>(B) * 6 * D;
+      g.bias = c.W(s->base + UMD_S_ADA_B); g.bias_bs = s->lstride;
       UMD_TRY(gemm_bf16(g, c.st));
     }
     UMD_TRY(dense_fwd(c, P.cond_bf16, B, D, c.WB(UMD_P_FMOD_W), 2 * D, c.W(UMD_P_FMOD_B), UMD_EPI_F32, P.fmod));
@@ -286,15 +296,15 @@ void pending_residual(LnFwdArgs& ln, const Stack& s, int l, float* x_out) {
   const LayerBufs& lb = s.L[l];
   ln.x = lb.xmid;
   ln.res_branch = lb.z;
-  ln.res_gate = s.ada ? s.ada + static_cast<long long>(l) * 6 * s.D + 5 * s.D : nullptr;
-  ln.ldgate = static_cast<long long>(s.depth) * 6 * s.D;
+  ln.res_gate = s.ada ? s.ada + static_cast<long long>(l) * s.nsamples * 6 * s.D + 5 * s.D : nullptr;
+  ln.ldgate = 6 * s.D;
   ln.x_out = x_out;
 }
 
 int stack_forward(Ctx& c, Stack& s) {
   Plan& P = c.P;
   const int D = P.D, T = s.rows, M4 = P.M4;
-  const long long ldada = static_cast<long long>(s.depth) * 6 * D;
+  const long long ldada = 6 * D, ada_ls = static_cast<long long>(P.B) * 6 * D, ls = s.lstride;
   const long long qkv_sp = c.offs[s.base + UMD_S_K_W] - c.offs[s.base + UMD_S_Q_W];
   const long long qkvb_sp = c.offs[s.base + UMD_S_K_B] - c.offs[s.base + UMD_S_Q_B];
   UMD_REQUIRE(c.offs[s.base + UMD_S_V_W] - c.offs[s.base + UMD_S_K_W] == qkv_sp &&
@@ -302,7 +312,7 @@ int stack_forward(Ctx& c, Stack& s) {
               "query/key/value leaves must be equally spaced in the arena");
   for (int l = 0; l < s.depth; ++l) {
     LayerBufs& lb = s.L[l];
-    const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
+    const float* ada = s.ada ? s.ada + l * ada_ls : nullptr;
     LnFwdArgs ln;
     memset(&ln, 0, sizeof(ln));
     // LayerNorm_0 (+ modulate); for l > 0 it first forms x[l] = xmid[l-1] + gate1[l-1] * z[l-1] (vit.py:106-108),
@@ -313,36 +323,35 @@ int stack_forward(Ctx& c, Stack& s) {
       pending_residual(ln, s, l - 1, s.x[l]);
     }
     if (!P.adaln) { ln.cond_row = P.cond; ln.x_out = s.x[l]; }
-    ln.gamma = c.W(s.base + UMD_S_LN0_S, static_cast<long long>(l) * D);
-    ln.beta = c.W(s.base + UMD_S_LN0_B, static_cast<long long>(l) * D);
+    ln.gamma = c.W(s.base + UMD_S_LN0_S, l * ls);
+    ln.beta = c.W(s.base + UMD_S_LN0_B, l * ls);
     ln.shift = ada; ln.scale = ada ? ada + D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
     ln.out = lb.y0; ln.mean = lb.mean0; ln.rstd = lb.rstd0; ln.rows_out = T;
     UMD_TRY(ln_mod_fwd(ln, D, true, c.st));
     {  // q, k, v projections as one batch-3 GEMM into the packed [T, 3D] buffer
-      umd_gemm_args g = gemm_base(lb.y0, c.WB(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D), T, D, D);
+      umd_gemm_args g = gemm_base(lb.y0, c.WB(s.base + UMD_S_Q_W, l * ls), T, D, D);
       g.b_mn = 1; g.lda = D; g.ldb = D; g.batch = 3; g.a_bs = 0; g.b_bs = qkv_sp;
       g.epi = UMD_EPI_BF16; g.out0 = lb.qkv; g.ld0 = 3 * D; g.bs0 = D;
-      g.bias = c.W(s.base + UMD_S_Q_B, static_cast<long long>(l) * D); g.bias_bs = qkvb_sp;
+      g.bias = c.W(s.base + UMD_S_Q_B, l * ls); g.bias_bs = qkvb_sp;
       UMD_TRY(gemm_bf16(g, c.st));
     }
     AttnArgs at;
     at.qkv = lb.qkv; at.out = lb.o; at.lse = lb.lse; at.rm = s.rm; at.nsamples = s.nsamples; at.H = P.H; at.Dh = P.Dh;
     at.scale = 1.0f / sqrtf(static_cast<float>(P.Dh));
     UMD_TRY(attention_fwd(at, c.st));
-    UMD_TRY(dense_fwd(c, lb.o, T, D, c.WB(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D), D,
-                      c.W(s.base + UMD_S_O_B, static_cast<long long>(l) * D), UMD_EPI_BF16, lb.a));
+    UMD_TRY(dense_fwd(c, lb.o, T, D, c.WB(s.base + UMD_S_O_W, l * ls), D, c.W(s.base + UMD_S_O_B, l * ls), UMD_EPI_BF16, lb.a));
     // LayerNorm_1 (+ modulate) on xmid = x[l] + gate0 * a (vit.py:89-98)
     memset(&ln, 0, sizeof(ln));
     ln.x = s.x[l]; ln.res_branch = lb.a; ln.res_gate = ada ? ada + 2 * D : nullptr; ln.ldgate = ldada; ln.x_out = lb.xmid;
-    ln.gamma = c.W(s.base + UMD_S_LN1_S, static_cast<long long>(l) * D);
-    ln.beta = c.W(s.base + UMD_S_LN1_B, static_cast<long long>(l) * D);
+    ln.gamma = c.W(s.base + UMD_S_LN1_S, l * ls);
+    ln.beta = c.W(s.base + UMD_S_LN1_B, l * ls);
     ln.shift = ada ? ada + 3 * D : nullptr; ln.scale = ada ? ada + 4 * D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
     ln.out = lb.y1; ln.mean = lb.mean1; ln.rstd = lb.rstd1; ln.rows_out = T;
     UMD_TRY(ln_mod_fwd(ln, D, true, c.st));
-    UMD_TRY(dense_fwd(c, lb.y1, T, D, c.WB(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4), M4,
-                      c.W(s.base + UMD_S_FC1_B, static_cast<long long>(l) * M4), UMD_EPI_GELU, lb.u, lb.g));
-    UMD_TRY(dense_fwd(c, lb.g, T, M4, c.WB(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D), D,
-                      c.W(s.base + UMD_S_FC2_B, static_cast<long long>(l) * D), UMD_EPI_BF16, lb.z));
+    UMD_TRY(dense_fwd(c, lb.y1, T, D, c.WB(s.base + UMD_S_FC1_W, l * ls), M4, c.W(s.base + UMD_S_FC1_B, l * ls), UMD_EPI_GELU,
+                      lb.u, lb.g));
+    UMD_TRY(dense_fwd(c, lb.g, T, M4, c.WB(s.base + UMD_S_FC2_W, l * ls), D, c.W(s.base + UMD_S_FC2_B, l * ls), UMD_EPI_BF16,
+                      lb.z));
     // x[l+1] = xmid + gate1 * z is formed by whichever LayerNorm reads it next (pending_residual)
   }
   return UMD_OK;
@@ -353,50 +362,50 @@ int stack_forward(Ctx& c, Stack& s) {
 void gate_stage_mlp(const Ctx& c, const Stack& s, int l, LnBwdArgs& lnb) {
   const Plan& P = c.P;
   const int D = P.D;
-  const long long ldada = static_cast<long long>(s.depth) * 6 * D;
-  const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
-  float* dada = s.dada ? s.dada + static_cast<long long>(l) * 6 * D : nullptr;
+  const long long ldada = 6 * D, ada_ls = static_cast<long long>(P.B) * 6 * D;
+  const float* ada = s.ada ? s.ada + l * ada_ls : nullptr;
+  float* dada = s.dada ? s.dada + l * ada_ls : nullptr;
   lnb.g_dz = P.dzb; lnb.g_z = s.L[l].z;
   lnb.g_gate = ada ? ada + 5 * D : nullptr; lnb.g_ldgate = ldada;
   lnb.g_dgate = dada ? dada + 5 * D : nullptr; lnb.g_lddgate = ldada;
-  lnb.g_dbias = c.G(s.base + UMD_S_FC2_B, static_cast<long long>(l) * D);
+  lnb.g_dbias = c.G(s.base + UMD_S_FC2_B, l * s.lstride);
 }
 
 // Backward of the stack (App. E steps 1-10).  On entry dx holds d x[depth] and P.dzb the gated gradient of the
 // last block's MLP branch (gate_stage_mlp fused into the caller's LayerNorm backward); on exit dx holds d x[0].
-int stack_backward(Ctx& c, Stack& s, float* dx) {
+// Every parameter gradient of layer l (the adaLN projection included) is final once layer l's kernels have been
+// enqueued; then cb(cb_user, ev0 + depth-1-l) tells the host that the layer's arena block may be all-reduced.
+int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user, int ev0) {
   Plan& P = c.P;
-  const int D = P.D, T = s.rows, M4 = P.M4;
-  const long long ldada = static_cast<long long>(s.depth) * 6 * D;
+  const int D = P.D, T = s.rows, M4 = P.M4, B = P.B;
+  const long long ldada = 6 * D, ada_ls = static_cast<long long>(B) * 6 * D, ls = s.lstride;
   const long long qkv_sp = c.offs[s.base + UMD_S_K_W] - c.offs[s.base + UMD_S_Q_W];
   const long long qkvb_sp = c.offs[s.base + UMD_S_K_B] - c.offs[s.base + UMD_S_Q_B];
   for (int l = s.depth - 1; l >= 0; --l) {
     LayerBufs& lb = s.L[l];
-    const float* ada = s.ada ? s.ada + static_cast<long long>(l) * 6 * D : nullptr;
-    float* dada = s.dada ? s.dada + static_cast<long long>(l) * 6 * D : nullptr;
-    const long long lD = static_cast<long long>(l) * D;
+    const float* ada = s.ada ? s.ada + l * ada_ls : nullptr;
+    float* dada = s.dada ? s.dada + l * ada_ls : nullptr;
+    const long long lo = l * ls;   // arena offset of this layer's block relative to layer 0
     // ---- MLP branch (P.dzb = gate1 * dx)
-    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D), M4, UMD_EPI_DGELU,
-                        P.dgb, lb.u));
-    UMD_TRY(dense_wgrad(c, lb.g, T, M4, P.dzb, D, D, c.G(s.base + UMD_S_FC2_W, static_cast<long long>(l) * M4 * D)));
-    UMD_TRY(colsum_bf16(P.dgb, M4, T, M4, c.G(s.base + UMD_S_FC1_B, static_cast<long long>(l) * M4), c.st));
-    UMD_TRY(dense_dgrad(c, P.dgb, T, M4, c.WB(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4), D, UMD_EPI_BF16,
-                        P.dyb));
-    UMD_TRY(dense_wgrad(c, lb.y1, T, D, P.dgb, M4, M4, c.G(s.base + UMD_S_FC1_W, static_cast<long long>(l) * D * M4)));
+    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_FC2_W, lo), M4, UMD_EPI_DGELU, P.dgb, lb.u));
+    UMD_TRY(dense_wgrad(c, lb.g, T, M4, P.dzb, D, D, c.G(s.base + UMD_S_FC2_W, lo)));
+    UMD_TRY(colsum_bf16(P.dgb, M4, T, M4, c.G(s.base + UMD_S_FC1_B, lo), c.st));
+    UMD_TRY(dense_dgrad(c, P.dgb, T, M4, c.WB(s.base + UMD_S_FC1_W, lo), D, UMD_EPI_BF16, P.dyb));
+    UMD_TRY(dense_wgrad(c, lb.y1, T, D, P.dgb, M4, M4, c.G(s.base + UMD_S_FC1_W, lo)));
     LnBwdArgs lnb;
     memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dyb; lnb.x = lb.xmid; lnb.mean = lb.mean1; lnb.rstd = lb.rstd1;
-    lnb.gamma = c.W(s.base + UMD_S_LN1_S, lD); lnb.beta = c.W(s.base + UMD_S_LN1_B, lD);
+    lnb.gamma = c.W(s.base + UMD_S_LN1_S, lo); lnb.beta = c.W(s.base + UMD_S_LN1_B, lo);
     lnb.scale = ada ? ada + 4 * D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
     lnb.dshift = dada ? dada + 3 * D : nullptr; lnb.dscale = dada ? dada + 4 * D : nullptr; lnb.ldd = ldada;
-    lnb.dgamma = c.G(s.base + UMD_S_LN1_S, lD); lnb.dbeta = c.G(s.base + UMD_S_LN1_B, lD);
+    lnb.dgamma = c.G(s.base + UMD_S_LN1_S, lo); lnb.dbeta = c.G(s.base + UMD_S_LN1_B, lo);
     // ... followed in the same pass by the gate backward of the attention branch (App. E step 6)
     lnb.g_dz = P.dzb; lnb.g_z = lb.a; lnb.g_gate = ada ? ada + 2 * D : nullptr; lnb.g_ldgate = ldada;
-    lnb.g_dgate = dada ? dada + 2 * D : nullptr; lnb.g_lddgate = ldada; lnb.g_dbias = c.G(s.base + UMD_S_O_B, lD);
+    lnb.g_dgate = dada ? dada + 2 * D : nullptr; lnb.g_lddgate = ldada; lnb.g_dbias = c.G(s.base + UMD_S_O_B, lo);
     UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
     // ---- attention branch (P.dzb = gate0 * dx)
-    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D), D, UMD_EPI_BF16, P.dyb));
-    UMD_TRY(dense_wgrad(c, lb.o, T, D, P.dzb, D, D, c.G(s.base + UMD_S_O_W, static_cast<long long>(l) * D * D)));
+    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_O_W, lo), D, UMD_EPI_BF16, P.dyb));
+    UMD_TRY(dense_wgrad(c, lb.o, T, D, P.dzb, D, D, c.G(s.base + UMD_S_O_W, lo)));
     AttnBwdArgs ab;
     ab.qkv = lb.qkv; ab.out = lb.o; ab.dout = P.dyb; ab.lse = lb.lse; ab.dqkv = P.dqkv; ab.rm = s.rm;
     ab.nsamples = s.nsamples; ab.H = P.H; ab.Dh = P.Dh; ab.scale = 1.0f / sqrtf(static_cast<float>(P.Dh));
@@ -404,46 +413,44 @@ int stack_backward(Ctx& c, Stack& s, float* dx) {
     {  // dWq, dWk, dWv as one batch-3 wgrad GEMM
       umd_gemm_args g = gemm_base(lb.y0, P.dqkv, D, D, T);
       g.a_mn = 1; g.b_mn = 1; g.lda = D; g.ldb = 3 * D; g.batch = 3; g.a_bs = 0; g.b_bs = D;
-      g.epi = UMD_EPI_ATOMIC; g.out0 = c.G(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D); g.ld0 = D; g.bs0 = qkv_sp;
+      g.epi = UMD_EPI_ATOMIC; g.out0 = c.G(s.base + UMD_S_Q_W, lo); g.ld0 = D; g.bs0 = qkv_sp;
       g.split_k = pick_split(D, D, T, 3);
       UMD_TRY(gemm_bf16(g, c.st));
     }
-    UMD_TRY(colsum_bf16(P.dqkv, 3 * D, T, 3 * D, c.G(s.base + UMD_S_Q_B, lD), c.st, D, qkvb_sp));  // dbq | dbk | dbv
+    UMD_TRY(colsum_bf16(P.dqkv, 3 * D, T, 3 * D, c.G(s.base + UMD_S_Q_B, lo), c.st, D, qkvb_sp));  // dbq | dbk | dbv
     {  // dY0 = [dQ|dK|dV] [Wq|Wk|Wv]^T, contraction chunked over the three kernels
-      umd_gemm_args g = gemm_base(P.dqkv, c.WB(s.base + UMD_S_Q_W, static_cast<long long>(l) * D * D), T, D, 3 * D);
+      umd_gemm_args g = gemm_base(P.dqkv, c.WB(s.base + UMD_S_Q_W, lo), T, D, 3 * D);
       g.a_mn = 0; g.b_mn = 0; g.lda = 3 * D; g.ldb = D; g.b_bs = qkv_sp; g.b_kchunk = D;
       g.epi = UMD_EPI_BF16; g.out0 = P.dyb; g.ld0 = D;
       UMD_TRY(gemm_bf16(g, c.st));
     }
     memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dyb; lnb.x = s.x[l]; lnb.mean = lb.mean0; lnb.rstd = lb.rstd0;
-    lnb.gamma = c.W(s.base + UMD_S_LN0_S, lD); lnb.beta = c.W(s.base + UMD_S_LN0_B, lD);
+    lnb.gamma = c.W(s.base + UMD_S_LN0_S, lo); lnb.beta = c.W(s.base + UMD_S_LN0_B, lo);
     lnb.scale = ada ? ada + D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
     lnb.dshift = dada ? dada : nullptr; lnb.dscale = dada ? dada + D : nullptr; lnb.ldd = ldada;
-    lnb.dgamma = c.G(s.base + UMD_S_LN0_S, lD); lnb.dbeta = c.G(s.base + UMD_S_LN0_B, lD);
+    lnb.dgamma = c.G(s.base + UMD_S_LN0_S, lo); lnb.dbeta = c.G(s.base + UMD_S_LN0_B, lo);
     if (!P.adaln) lnb.dcond = P.dcond;            // token-0 row: gradient of the conditioning token (vit.py:73-74)
     if (l > 0) gate_stage_mlp(c, s, l - 1, lnb);  // dx is now d x[l]: start block l-1's MLP-branch backward
     UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
+    if (P.adaln) {
+      // adaLN projection of this layer (App. E step 10): dada[l] = [dshift0|dscale0|dgate0|dshift1|dscale1|dgate1] per
+      // sample is complete (the gate1 column was written by layer l+1's... no: by THIS layer's first LayerNorm backward of
+      // the caller / of layer l+1, all earlier in the stream)
+      bf16* dab = s.dada_bf16 + l * ada_ls;
+      UMD_TRY(cast_bf16(dada, ada_ls, dab, c.st));
+      UMD_TRY(colsum_f32(dada, ldada, B, 6 * D, c.G(s.base + UMD_S_ADA_B, lo), c.st));
+      UMD_TRY(dense_wgrad(c, P.cond_bf16, B, D, dab, 6 * D, ldada, c.G(s.base + UMD_S_ADA_W, lo)));
+    }
+    if (cb) cb(cb_user, ev0 + (s.depth - 1 - l));
   }
   if (P.adaln) {
-    // adaLN projection backward, all blocks of the stack at once (App. E step 10)
-    const int B = P.B;
-    const long long n = static_cast<long long>(B) * s.depth * 6 * D;
-    UMD_TRY(cast_bf16(s.dada, n, s.dada_bf16, c.st));
-    UMD_TRY(colsum_f32(s.dada, ldada, B, s.depth * 6 * D, c.G(s.base + UMD_S_ADA_B), c.st));
-    {
-      umd_gemm_args g = gemm_base(P.cond_bf16, s.dada_bf16, D, 6 * D, B);
-      g.a_mn = 1; g.b_mn = 1; g.lda = D; g.ldb = ldada; g.batch = s.depth; g.a_bs = 0; g.b_bs = 6 * D;
-      g.epi = UMD_EPI_ATOMIC; g.out0 = c.G(s.base + UMD_S_ADA_W); g.ld0 = 6 * D; g.bs0 = static_cast<long long>(D) * 6 * D;
-      UMD_TRY(gemm_bf16(g, c.st));
-    }
-    {
-      umd_gemm_args g = gemm_base(s.dada_bf16, c.WB(s.base + UMD_S_ADA_W), B, D, 6 * D);
-      g.a_mn = 0; g.b_mn = 0; g.lda = ldada; g.ldb = 6 * D; g.batch = s.depth; g.a_bs = 6 * D;
-      g.b_bs = static_cast<long long>(D) * 6 * D;
-      g.epi = UMD_EPI_ATOMIC; g.out0 = P.dcond; g.ld0 = D; g.bs0 = 0;
-      UMD_TRY(gemm_bf16(g, c.st));
-    }
+    // dcond += dada[l] W_ada[l]^T for all blocks of the stack in one batched GEMM (it feeds no parameter gradient
+    // directly, so it can wait for the end of the stack)
+    umd_gemm_args g = gemm_base(s.dada_bf16, c.WB(s.base + UMD_S_ADA_W), B, D, 6 * D);
+    g.a_mn = 0; g.b_mn = 0; g.lda = ldada; g.ldb = 6 * D; g.batch = s.depth; g.a_bs = ada_ls; g.b_bs = ls;
+    g.epi = UMD_EPI_ATOMIC; g.out0 = P.dcond; g.ld0 = D; g.bs0 = 0;
+    UMD_TRY(gemm_bf16(g, c.st));
   }
   return UMD_OK;
 }
@@ -512,6 +519,7 @@ int engine_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const 
   c.grads = nullptr; c.st = st;
   UMD_TRY(make_plan(c.P, *cfg, *shape, ws, train != 0));
   UMD_REQUIRE(c.P.bytes <= ws_bytes, "workspace too small: need %zu bytes, have %zu", c.P.bytes, ws_bytes);
+  UMD_TRY(set_layer_strides(c));
   Plan& P = c.P;
   const int D = P.D, B = P.B;
   UMD_TRY(cond_forward(c, *io));
@@ -556,6 +564,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
   c.grads = grads; c.st = st;
   UMD_TRY(make_plan(c.P, *cfg, *shape, ws, true));
   UMD_REQUIRE(c.P.bytes <= ws_bytes, "workspace too small: need %zu bytes, have %zu", c.P.bytes, ws_bytes);
+  UMD_TRY(set_layer_strides(c));
   Plan& P = c.P;
   const int D = P.D, B = P.B, BL = B * P.L;
   UMD_CHECK_CUDA(cudaMemsetAsync(P.dcond, 0, static_cast<size_t>(B) * D * sizeof(float), st));
@@ -592,7 +601,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     g.lda = 2 * D; g.ldb = 2 * D; g.epi = UMD_EPI_ATOMIC; g.out0 = P.dcond; g.ld0 = D;
     UMD_TRY(gemm_bf16(g, st));
   }
-  UMD_TRY(stack_backward(c, P.dec, P.dx_dec));
+  UMD_TRY(stack_backward(c, P.dec, P.dx_dec, nullptr, nullptr, 0));
   UMD_TRY(decoder_input_bwd(decin_args(c, *io), B, P.Te, P.dx_dec, P.dxf_enc, c.G(UMD_P_DEC_POS), c.G(UMD_P_MASK_TOKEN), st));
   if (cb) cb(cb_user, 0);
   {  // encoder_norm backward
@@ -605,8 +614,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     gate_stage_mlp(c, P.enc, P.enc.depth - 1, lnb);
     UMD_TRY(ln_mod_bwd(lnb, D, B, false, st));
   }
-  UMD_TRY(stack_backward(c, P.enc, P.dx_enc));
-  if (cb) cb(cb_user, 1);
+  UMD_TRY(stack_backward(c, P.enc, P.dx_enc, cb, cb_user, 1));
   UMD_TRY(embed_bwd(embed_args(c, *io), B, P.dx_enc, c.G(UMD_P_EMBED_W), c.G(UMD_P_EMBED_B), c.G(UMD_P_POS),
                     c.G(UMD_P_CLS), st));
   // ---- conditioning path backward (ae.py:121-124, embeddings.py:50-59)
@@ -629,7 +637,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
       UMD_TRY(scatter_add_rows(P.dlemb, io->labels, B, D, c.G(UMD_P_LABEL_TABLE), st));
     }
   }
-  if (cb) cb(cb_user, 2);
+  if (cb) cb(cb_user, 1 + P.enc.depth);
   return UMD_OK;
 }
 

@@ -3,8 +3,8 @@
 The reference declares shardings and lets GSPMD insert the gradient all-reduce
 (train_ae.py:159-170,287-290,364).  Here one process drives one GPU: parameters, optimiser state,
 schedule tables and RNG are replicated, the batch is split on axis 0 in rank order, and the flat
-gradient arena is all-reduced (mean) over NCCL in three buckets launched from the backward's bucket
-callback so that they overlap the rest of the backward pass.
+gradient arena is all-reduced (mean) over NCCL in buckets (decoder side, groups of encoder layers, embeddings)
+launched from the backward's event callback so that they overlap the rest of the backward pass.
 """
 from __future__ import annotations
 
@@ -79,9 +79,11 @@ def local_batch_slice(global_batch, rank, world):
 
 
 class GradientReducer:
-  """Mean all-reduce of the gradient arena in the three buckets of params.ArenaLayout, each issued
-  asynchronously from the backward's bucket callback (C1 in SURVEY.md §2.3).  With no process group
-  (single GPU) every method is a no-op."""
+  """Mean all-reduce of the gradient arena in the buckets of params.ArenaLayout (the decoder side, groups of encoder
+  layer blocks from the top down, the embeddings), each issued asynchronously from the backward's event callback as
+  soon as the engine has enqueued the last kernel that writes it (C1 in SURVEY.md §2.3), so that the reduction of
+  every bucket but the last overlaps the rest of the backward pass.  With no process group (single GPU) every method
+  is a no-op."""
 
   def __init__(self, layout, process_group=None):
     self.layout = layout
@@ -96,9 +98,15 @@ class GradientReducer:
 
   def bucket_view(self, grads, k):
     lo, hi = self.layout.bucket_bounds[k]
-    if k == len(self.layout.bucket_bounds) - 1:
-      hi = grads.numel()  # trailing scalar slots (loss) ride on the last bucket
+    if hi == self.layout.total:
+      hi = grads.numel()  # trailing scalar slots (loss) ride on the bucket that ends the arena
     return grads[lo:hi]
+
+  def on_event(self, grads, event):
+    """Backward event `event` (include/umd_b200.h, umd_backward) has been enqueued: launch the buckets it completes."""
+    for k, e in enumerate(self.layout.bucket_events):
+      if e == event:
+        self.launch(grads, k)
 
   def launch(self, grads, k):
     if self.pg is None or self.world == 1:

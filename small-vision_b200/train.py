@@ -152,7 +152,7 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     model.forward_arena(arena, shadow, image=model_in, t=tm, labels=labels, n0=n_noise, n1=n_clean, keep0=keep0,
                         keep1=keep1, masked0=masked0, masked1=masked1, ids_shuffle=ids_shuffle, ids_restore=ids_restore,
                         want_pred=False, train=True, x0=images, noise=noise, loss_out=loss_slot)
-    model.backward_arena(arena, shadow, grads, bucket_cb=(lambda k: reducer.launch(grads, k)) if reduce else None)
+    model.backward_arena(arena, shadow, grads, bucket_cb=(lambda e: reducer.on_event(grads, e)) if reduce else None)
     if reduce:
       reducer.finish()                                # implicit GSPMD all-reduce of train_ae.py:364
     return arena, shadow, grads, loss_slot

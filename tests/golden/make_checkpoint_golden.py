@@ -39,7 +39,7 @@ def make_tree(seed=0):
   from small_vision_b200.model import Model
   rng = np.random.default_rng(seed)
   tree = {}
-  for lf in Model(**MODEL).layout.leaves:
+  for lf in Model(**MODEL).layout.init_order:   # the seeded order the fixture was generated with
     d = tree
     for k in lf.path[:-1]:
       d = d.setdefault(k, {})

@@ -176,10 +176,23 @@ def test_weight_decay_flags_follow_no_decay_list():
   flags = lay.wd_flags("cpu")
   assert flags.numel() * 64 == lay.total
   for lf in lay.leaves:
-    assert int(flags[lf.offset // 64]) == int(lay.decay(lf))
-  # buckets partition the arena in backward order: decoder side, encoder, embeddings
-  b = lay.bucket_bounds
-  assert len(b) == 3 and b[0][0] == 0 and b[0][1] == b[1][0] and b[1][1] == b[2][0] and b[2][1] == lay.total
+    for l in range(lf.shape[0] if lf.stack else 1):
+      assert int(flags[(lf.offset + l * lf.lstride) // 64]) == int(lay.decay(lf))
+  # buckets tile the arena; launch order = backward order: decoder side, encoder layer groups from the top down (the
+  # first one ends the arena: it carries Encoder/encoder_norm and the trailing loss slot), the last group merged with
+  # the embeddings / conditioning leaves in front of layer 0
+  b, ev = lay.bucket_bounds, lay.bucket_events
+  assert len(b) == 5 and ev == [0, 3, 6, 9, 13] and lay.num_events == 14
+  assert b[0][0] == 0 and b[1][1] == lay.total and b[-1][0] == b[0][1]
+  cov = sorted(b)
+  assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1)) and cov[-1][1] == lay.total
+  enc0, es = lay.stack_start["Encoder"], lay.layer_stride["Encoder"]
+  assert b[1][0] == enc0 + 9 * es and b[2] == (enc0 + 6 * es, enc0 + 9 * es) and b[4][1] == enc0 + 3 * es
+  # a scanned leaf is a strided [depth, ...] view: layer l's slice is contiguous inside layer block l
+  q = lay.by_path[("Encoder", "ScanCheckpointEncoder1DBlock_0", "MultiHeadDotProductAttention_0", "query", "kernel")]
+  v = q.view(torch.arange(lay.total, dtype=torch.float32))
+  assert tuple(v.shape) == (12, 384, 6, 64) and v.stride(0) == es and v[0].is_contiguous()
+  assert float(v[5, 0, 0, 0]) == q.offset + 5 * es
 
 
 # ------------------------------------------------------------------------------------------ sharding.py

@@ -58,9 +58,9 @@ def perturb_init(model, seed, device):
   from small_vision_b200.params import tree_from_arena, init_arena
   arena = init_arena(model.layout, seed, "cpu", nonzero_adaln=True)
   g = torch.Generator().manual_seed(seed + 1234)
-  for lf in model.layout.leaves:
+  for lf in model.layout.init_order:
     if lf.init in ("zeros", "ones"):
-      arena[lf.offset:lf.offset + lf.size] += 0.05 * torch.randn(lf.size, generator=g)
+      lf.view(arena).add_(0.05 * torch.randn(lf.size, generator=g).view(lf.shape))
   arena = arena.to(device)
   return tree_from_arena(model.layout, arena)
 

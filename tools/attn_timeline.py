@@ -52,5 +52,5 @@ if len(sys.argv) > 1 and sys.argv[1] == "fwd":
   for n, S in ((512, 257), (256, 164), (256, 68)):
     run_fwd(n, S)
 else:
-  for n, S in ((512, 257),):
+  for n, S in ((512, 257), (256, 164), (256, 68)):
     run(n, S)

@@ -25,7 +25,7 @@ worst = max(range(1, len(gs)), key=lambda i: rels[i - 1])
 d = (gs[0] - gs[worst])
 rows = []
 for lf in model.layout.leaves:
-  a, b = gs[0][lf.offset:lf.offset + lf.size].double(), d[lf.offset:lf.offset + lf.size].double()
+  a, b = lf.view(gs[0]).double().reshape(-1), lf.view(d).double().reshape(-1)
   if float(b.abs().max()) > 0:
     rows.append((float(b.norm() / (a.norm() + 1e-30)), "/".join(lf.path), int((b != 0).sum()), lf.size))
 rows.sort(reverse=True)
