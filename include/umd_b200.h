@@ -5,7 +5,8 @@
  * The reference (philippe-eecs/small-vision) is pure Python/JAX and has no FFI; the seams
  * this library replaces are Python callables:
  *   - big_vision/models/ae.py:176-197      _ViTAE.__call__      -> umd_forward
- *   - big_vision/trainers/train_ae.py:287-382  update_fn         -> umd_train_step + umd_adamw_step
+ *   - big_vision/trainers/train_ae.py:287-382  update_fn         -> umd_train_step (= umd_qsample, umd_mask_argsort,
+ *                                                  umd_forward, umd_backward, umd_comm all-reduce, umd_adamw_step)
  *   - big_vision/gaussian_diffusion.py:85-98   q_sample          -> umd_qsample
  *   - big_vision/models/ae.py:9-28         random_masking        -> umd_mask_argsort
  * Every function is asynchronous on the caller's cudaStream_t, allocates nothing, takes raw
@@ -242,6 +243,63 @@ int umd_forward(const umd_model_cfg* cfg, const umd_step_shape* shape, const lon
 int umd_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const long long* offsets, const float* params,
                  const void* params_bf16, float* grads, const umd_io* io, void* workspace, size_t workspace_bytes,
                  umd_bucket_cb cb, void* cb_user, umd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel communicator (big_vision/sharding.py:33-55 + the implicit GSPMD gradient all-reduce of
+ * trainers/train_ae.py:159-170,287-290,364).  NCCL is resolved at run time (libnccl.so.2); every collective runs on a
+ * stream owned by the communicator and is ordered against the caller's streams with events.  One communicator per
+ * process / GPU.  id128 is an ncclUniqueId obtained on one rank and distributed by the host (any side channel).
+ * ------------------------------------------------------------------------------------------ */
+int umd_comm_available(void);      /* 1 when libnccl.so.2 could be loaded */
+int umd_comm_nccl_version(void);
+int umd_comm_unique_id(unsigned char* id128);
+int umd_comm_init(int rank, int world, const unsigned char* id128, void** comm);
+/* wraps an ncclComm_t the host already owns (not destroyed by umd_comm_destroy) */
+int umd_comm_from_nccl(void* nccl_comm, void** comm);
+int umd_comm_world(void* comm);
+int umd_comm_rank(void* comm);
+/* buf[0, n) <- mean over ranks, ordered behind `stream`; `stream` waits for the result */
+int umd_comm_allreduce_mean(void* comm, float* buf, long long n, umd_stream_t stream);
+int umd_comm_destroy(void* comm);
+
+/* ------------------------------------------------------------------------------------------
+ * One whole training step — update_fn of big_vision/trainers/train_ae.py:287-382 — in one call: q_sample noising
+ * (:318-321), masking index work (ae.py:9-28), forward of both branches, the loss (:323-361), backward (:364), the
+ * data-parallel gradient mean (each bucket handed to `comm` behind the backward event that completes it), global-norm
+ * clip + AdamW + EMA (:365-374) and the step measurements (:367-371).  Every random draw of the reference is an
+ * argument (:302-317, ae.py:14, embeddings.py:44).  Asynchronous on `stream`; nothing is allocated.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  UMD_STEP_NO_OPTIMIZER = 1,  /* stop after the (reduced) gradients: opt.params / mu / nu stay untouched */
+};
+typedef struct umd_train_step_args {
+  const umd_model_cfg* cfg;
+  umd_step_shape shape;            /* n0 noised + n1 clean samples; keep counts = int(L (1 - mask_ratio)) (ae.py:11) */
+  const long long* offsets;        /* UMD_OFFSETS_LEN entries */
+  umd_adamw_args opt;              /* params, mu, nu, params_bf16 (required), ema, hyper-parameters of this step (opt.grads is
+                                      ignored); opt.measurements: device float[4] <- loss, l2_params, l2_updates, grad_norm */
+  float* grads;                    /* [opt.n + 64] fp32 scratch: on return the (reduced) gradients, slot opt.n the (mean) loss */
+  const float* image;              /* [B, H, W, C] x_0 in [-1, 1]; the first n0 samples take the noise branch (:307-308) */
+  const long long* label;          /* [B] or NULL */
+  int use_labels;
+  const int* t;                    /* [n0] in [0, T) */
+  const float* noise;              /* [n0, H, W, C] ~ N(0, 1) */
+  const float* mask_noise0;        /* [n0, L] ~ U[0, 1), NULL when segment 0 is not masked */
+  const float* mask_noise1;        /* [n1, L] */
+  const unsigned char* label_drop; /* [n0] 1 = replace the label by the null class, or NULL */
+  const float* sqrt_alphas_cumprod;            /* [T] */
+  const float* sqrt_one_minus_alphas_cumprod;  /* [T] */
+  void* workspace;                 /* umd_train_workspace_bytes(cfg, shape) bytes */
+  size_t workspace_bytes;
+  void* comm;                      /* NULL = single GPU */
+  const long long* bucket_bounds;  /* [num_buckets][2] element ranges of grads, each reduced behind ... */
+  const int* bucket_events;        /* [num_buckets] ... this backward event (see umd_backward); a range that ends at
+                                      opt.n is extended by the 64 trailing slots */
+  int num_buckets;
+  int flags;
+} umd_train_step_args;
+size_t umd_train_workspace_bytes(const umd_model_cfg* cfg, const umd_step_shape* shape);
+int umd_train_step(const umd_train_step_args* args, umd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Few-shot ridge probe on `pre_logits`: big_vision/evaluators/fewshot_lsr.py.

@@ -592,58 +592,77 @@ int gate_bwd(const GateBwdArgs& a, int D, int nsamples, cudaStream_t st) {
 
 // =========================================================================================
 // Column sums of a bf16 [rows, N] matrix accumulated into fp32 out[N] (bias gradients).
+// No shared memory and 34 registers: the step engine runs these passes on a side stream so that they share the SMs
+// with the tensor-bound GEMM that follows on the main stream (a persistent GEMM CTA leaves ~2 KB of shared memory), and
+// their HBM traffic hides behind it.  Warp w of a CTA walks over rows r0 + w, r0 + w + 8, ...; a lane owns 8 adjacent
+// columns and adds its partial sums with two vector reductions (red.global.add.v4.f32).
 // =========================================================================================
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows,
                                                           int N, float* __restrict__ out, int rows_per_cta, int seg_cols,
                                                           long long seg_stride) {
-  __shared__ float sm[8][256];
   const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int col = blockIdx.x * 256 + cg * 8;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
+  if (col >= N) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (col < N) {
-    int r = r0 + rl;
-    // four independent 16-byte loads in flight per thread
-    for (; r + 24 < r1; r += 32) {
-      uint4 v[4];
+  int r = r0 + rl;
+  // four independent 16-byte loads in flight per thread
+  for (; r + 24 < r1; r += 32) {
+    uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * u) * ld + col);
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * u) * ld + col);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
-        acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
-      }
-    }
-    for (; r < r1; r += 8) {
-      uint4 v = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld + col);
-      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
-      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    for (int u = 0; u < 4; ++u) {
+      acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
+      acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) sm[rl][cg * 8 + j] = acc[j];
-  __syncthreads();
-  const int c = threadIdx.x;
-  if (blockIdx.x * 256 + c < N) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += sm[w][c];
-    const int col_out = blockIdx.x * 256 + c;
-    // column c of segment j = c / seg_cols goes to out[j * seg_stride + c % seg_cols] (q | k | v bias leaves)
-    const long long o = seg_cols > 0 ? (col_out / seg_cols) * seg_stride + (col_out % seg_cols) : col_out;
-    atomicAdd(out + o, t);
+  for (; r < r1; r += 8) {
+    uint4 v = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld + col);
+    acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+    acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
   }
+  // column c of segment j = c / seg_cols goes to out[j * seg_stride + c % seg_cols] (q | k | v bias leaves); a lane's 8
+  // columns never straddle a segment (seg_cols % 8 == 0) and every segment base is 16-byte aligned
+  const long long o = seg_cols > 0 ? (col / seg_cols) * seg_stride + (col % seg_cols) : col;
+  red_add_v4(out + o, acc[0], acc[1], acc[2], acc[3]);
+  red_add_v4(out + o + 4, acc[4], acc[5], acc[6], acc[7]);
 }
 
 int colsum_bf16(const void* x, long long ld, int rows, int N, float* out, cudaStream_t st, int seg_cols,
                 long long seg_stride) {
   if (rows <= 0) return UMD_OK;
   UMD_REQUIRE(N % 8 == 0 && ld % 8 == 0, "colsum_bf16: N and ld must be multiples of 8");
+  UMD_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (seg_cols == 0 || (seg_cols % 8 == 0 && seg_stride % 4 == 0)),
+              "colsum_bf16: out must be 16-byte aligned, segments multiples of 8 columns at 16-byte aligned strides");
   ProfScope prof(PC_COLSUM, static_cast<double>(rows) * N * 2, st);
-  const int rpc = 256;
+  const int rpc = rows >= 8192 ? 1024 : 256;
   dim3 grid(ceil_div(N, 256), ceil_div(rows, rpc));
   colsum_bf16_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, N, out, rpc, seg_cols, seg_stride);
+  UMD_LAUNCH_CHECK();
+  return UMD_OK;
+}
+
+// =========================================================================================
+// Model-side timestep and label vectors of one training step (see kernels.cuh)
+// =========================================================================================
+__global__ void step_prep_kernel(const int* __restrict__ t, const long long* __restrict__ label,
+                                 const unsigned char* __restrict__ drop, int n0, int B, int num_classes, int use_labels,
+                                 int* __restrict__ t_model, int* __restrict__ labels_model) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  t_model[i] = i < n0 ? t[i] + 1 : 0;
+  if (labels_model) {
+    int y = num_classes;
+    if (use_labels && i < n0 && label && !(drop && drop[i])) y = static_cast<int>(label[i]);
+    labels_model[i] = y;
+  }
+}
+int step_prep(const int* t, const long long* label, const unsigned char* label_drop, int n0, int B, int num_classes,
+              int use_labels, int* t_model, int* labels_model, cudaStream_t st) {
+  if (B <= 0) return UMD_OK;
+  step_prep_kernel<<<ceil_div(B, 256), 256, 0, st>>>(t, label, label_drop, n0, B, num_classes, use_labels, t_model, labels_model);
   UMD_LAUNCH_CHECK();
   return UMD_OK;
 }

@@ -71,6 +71,64 @@ struct Plan {
 
 int g_sm = 0;
 
+// ------------------------------------------------------------------------------------------
+// Side stream.  The bias-gradient column sums (fc1 bias from the dGELU output, q/k/v biases from dqkv) are pure
+// HBM passes over tensors that a GEMM has just written and that two more GEMMs are about to read.  They run on a
+// library-owned low-priority stream, forked behind their producer and joined at the end of the layer, so that
+// their CTAs (no shared memory, 34 registers) share the SMs with the tensor-bound GEMMs of the main stream instead
+// of taking 2.4 ms of the step for themselves.  One caller per device (see the header), hence plain statics.
+// ------------------------------------------------------------------------------------------
+struct Side {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[64];
+  int next = 0;
+  int state = -1;   // -1 unknown, 0 off, 1 ready
+  int device = -1;
+};
+Side g_side;
+int g_side_enabled = -1;   // UMD_SIDE_STREAM=0 / umd_debug_side_stream(0) keep everything on the caller's stream
+
+bool side_ready() {
+  if (g_side_enabled < 0) {
+    const char* e = getenv("UMD_SIDE_STREAM");
+    g_side_enabled = e ? (atoi(e) != 0) : 1;
+  }
+  if (!g_side_enabled) return false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (g_side.state == 1 && g_side.device == dev) return true;
+  if (g_side.state == 1) return false;   // created for another device: stay on the caller's stream
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least priority
+  if (cudaStreamCreateWithPriority(&g_side.st, cudaStreamNonBlocking, lo) != cudaSuccess) { g_side.state = 0; g_side_enabled = 0; return false; }
+  for (int i = 0; i < 64; ++i)
+    if (cudaEventCreateWithFlags(&g_side.ev[i], cudaEventDisableTiming) != cudaSuccess) { g_side.state = 0; g_side_enabled = 0; return false; }
+  g_side.state = 1;
+  g_side.device = dev;
+  return true;
+}
+cudaEvent_t side_event() { return g_side.ev[g_side.next++ & 63]; }
+
+// Runs fn(stream) behind everything enqueued on `main` so far, on the side stream when there is one; returns the event
+// that marks its completion (null when it ran on `main`)
+template <typename F>
+int on_side(cudaStream_t main, cudaEvent_t* done, F&& fn) {
+  *done = nullptr;
+  if (!side_ready()) return fn(main);
+  cudaEvent_t e = side_event();
+  UMD_CHECK_CUDA(cudaEventRecord(e, main));
+  UMD_CHECK_CUDA(cudaStreamWaitEvent(g_side.st, e, 0));
+  UMD_TRY(fn(g_side.st));
+  cudaEvent_t d = side_event();
+  UMD_CHECK_CUDA(cudaEventRecord(d, g_side.st));
+  *done = d;
+  return UMD_OK;
+}
+int join_side(cudaStream_t main, cudaEvent_t done) {
+  if (done) UMD_CHECK_CUDA(cudaStreamWaitEvent(main, done, 0));
+  return UMD_OK;
+}
+
 void carve_stack(Bump& b, Stack& s, const Plan& P, int depth, int rows, int nsamples, const RowMap& rm, int base,
                  bool train) {
   s.depth = depth; s.rows = rows; s.nsamples = nsamples; s.rm = rm; s.base = base;
@@ -389,7 +447,10 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
     // ---- MLP branch (P.dzb = gate1 * dx)
     UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_FC2_W, lo), M4, UMD_EPI_DGELU, P.dgb, lb.u));
     UMD_TRY(dense_wgrad(c, lb.g, T, M4, P.dzb, D, D, c.G(s.base + UMD_S_FC2_W, lo)));
-    UMD_TRY(colsum_bf16(P.dgb, M4, T, M4, c.G(s.base + UMD_S_FC1_B, lo), c.st));
+    cudaEvent_t side_a = nullptr, side_b = nullptr;
+    UMD_TRY(on_side(c.st, &side_a, [&](cudaStream_t st) {   // d fc1-bias = column sums of dU, behind the next GEMMs
+      return colsum_bf16(P.dgb, M4, T, M4, c.G(s.base + UMD_S_FC1_B, lo), st);
+    }));
     UMD_TRY(dense_dgrad(c, P.dgb, T, M4, c.WB(s.base + UMD_S_FC1_W, lo), D, UMD_EPI_BF16, P.dyb));
     UMD_TRY(dense_wgrad(c, lb.y1, T, D, P.dgb, M4, M4, c.G(s.base + UMD_S_FC1_W, lo)));
     LnBwdArgs lnb;
@@ -417,7 +478,9 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
       g.split_k = pick_split(D, D, T, 3);
       UMD_TRY(gemm_bf16(g, c.st));
     }
-    UMD_TRY(colsum_bf16(P.dqkv, 3 * D, T, 3 * D, c.G(s.base + UMD_S_Q_B, lo), c.st, D, qkvb_sp));  // dbq | dbk | dbv
+    UMD_TRY(on_side(c.st, &side_b, [&](cudaStream_t st) {   // dbq | dbk | dbv
+      return colsum_bf16(P.dqkv, 3 * D, T, 3 * D, c.G(s.base + UMD_S_Q_B, lo), st, D, qkvb_sp);
+    }));
     {  // dY0 = [dQ|dK|dV] [Wq|Wk|Wv]^T, contraction chunked over the three kernels
       umd_gemm_args g = gemm_base(P.dqkv, c.WB(s.base + UMD_S_Q_W, lo), T, D, 3 * D);
       g.a_mn = 0; g.b_mn = 0; g.lda = 3 * D; g.ldb = D; g.b_bs = qkv_sp; g.b_kchunk = D;
@@ -442,6 +505,9 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
       UMD_TRY(colsum_f32(dada, ldada, B, 6 * D, c.G(s.base + UMD_S_ADA_B, lo), c.st));
       UMD_TRY(dense_wgrad(c, P.cond_bf16, B, D, dab, 6 * D, ldada, c.G(s.base + UMD_S_ADA_W, lo)));
     }
+    // the side passes read P.dgb / P.dqkv (rewritten by the next layer) and write this layer's bias gradients
+    UMD_TRY(join_side(c.st, side_a));
+    UMD_TRY(join_side(c.st, side_b));
     if (cb) cb(cb_user, ev0 + (s.depth - 1 - l));
   }
   if (P.adaln) {
@@ -664,6 +730,118 @@ extern "C" int umd_backward(const umd_model_cfg* cfg, const umd_step_shape* shap
                          static_cast<cudaStream_t>(stream));
 }
 
+// ------------------------------------------------------------------------------------------
+// update_fn in one call (train_ae.py:287-382)
+// ------------------------------------------------------------------------------------------
+namespace umd {
+namespace {
+struct StepScratch {
+  float* model_in;
+  int* t_model;
+  int* labels_model;
+  int* ids_shuffle;
+  int* ids_restore;
+  size_t bytes;   // appended to the engine workspace
+};
+StepScratch carve_step(const umd_model_cfg& c, const umd_step_shape& sh, void* base) {
+  Bump b(base);
+  const long long B = sh.n0 + sh.n1, L = static_cast<long long>(c.img_size / c.patch) * (c.img_size / c.patch);
+  StepScratch s;
+  s.model_in = b.take<float>(B * c.img_size * c.img_size * c.channels);
+  s.t_model = b.take<int>(B);
+  s.labels_model = b.take<int>(B);
+  s.ids_shuffle = b.take<int>(B * L);
+  s.ids_restore = b.take<int>(B * L);
+  s.bytes = (b.off + 255) & ~size_t(255);
+  return s;
+}
+struct ReduceCtx {
+  const umd_train_step_args* a;
+  Comm* comm;
+  cudaStream_t st;
+  int rc;
+};
+void reduce_cb(void* user, int event) {
+  ReduceCtx* r = static_cast<ReduceCtx*>(user);
+  if (r->rc != UMD_OK) return;
+  const umd_train_step_args& a = *r->a;
+  for (int k = 0; k < a.num_buckets; ++k) {
+    if (a.bucket_events[k] != event) continue;
+    long long lo = a.bucket_bounds[2 * k], hi = a.bucket_bounds[2 * k + 1];
+    if (hi == a.opt.n) hi += 64;   // the trailing scalar slots (loss) ride on the bucket that ends the arena
+    const int rc = comm_allreduce_mean_after(r->comm, a.grads + lo, hi - lo, r->st, nullptr);
+    if (rc != UMD_OK) { r->rc = rc; return; }
+  }
+}
+}  // namespace
+}  // namespace umd
+
+extern "C" size_t umd_train_workspace_bytes(const umd_model_cfg* cfg, const umd_step_shape* shape) {
+  const size_t w = umd_workspace_bytes(cfg, shape, 1);
+  if (w == 0) return 0;
+  return w + carve_step(*cfg, *shape, nullptr).bytes;
+}
+
+extern "C" int umd_train_step(const umd_train_step_args* a, umd_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  UMD_REQUIRE(a && a->cfg && a->offsets && a->workspace, "umd_train_step: null argument");
+  const umd_model_cfg& c = *a->cfg;
+  const umd_step_shape& sh = a->shape;
+  const int B = sh.n0 + sh.n1;
+  UMD_REQUIRE(B > 0 && a->image && a->opt.params && a->grads && a->opt.params_bf16 && a->opt.n > 0,
+              "umd_train_step: image, opt.params, opt.params_bf16 and grads are required");
+  UMD_REQUIRE(sh.n0 == 0 || (a->t && a->noise && a->sqrt_alphas_cumprod && a->sqrt_one_minus_alphas_cumprod),
+              "umd_train_step: t, noise and the schedule tables are required for the noise branch");
+  UMD_REQUIRE(!(sh.masked0 && sh.n0 > 0) || a->mask_noise0, "umd_train_step: mask_noise0 is required (segment 0 is masked)");
+  UMD_REQUIRE(!(sh.masked1 && sh.n1 > 0) || a->mask_noise1, "umd_train_step: mask_noise1 is required (segment 1 is masked)");
+  UMD_REQUIRE(!a->comm || (a->num_buckets > 0 && a->bucket_bounds && a->bucket_events), "umd_train_step: a communicator needs the bucket table");
+  const bool optimise = !(a->flags & UMD_STEP_NO_OPTIMIZER);
+  UMD_REQUIRE(!optimise || (a->opt.mu && a->opt.nu && a->opt.wd_flags && a->opt.scratch && a->opt.measurements),
+              "umd_train_step: the optimiser needs mu, nu, wd_flags, scratch and measurements");
+  const size_t ws_engine = umd_workspace_bytes(&c, &sh, 1);
+  UMD_REQUIRE(ws_engine > 0, "umd_train_step: %s", umd_last_error());
+  StepScratch ss = carve_step(c, sh, static_cast<uint8_t*>(a->workspace) + ws_engine);
+  UMD_REQUIRE(ws_engine + ss.bytes <= a->workspace_bytes, "umd_train_step: workspace too small: need %zu bytes, have %zu",
+              ws_engine + ss.bytes, a->workspace_bytes);
+  const int L = (c.img_size / c.patch) * (c.img_size / c.patch);
+  const long long per = static_cast<long long>(c.img_size) * c.img_size * c.channels;
+  float* grads = a->grads;
+  float* loss = grads + a->opt.n;
+  UMD_CHECK_CUDA(cudaMemsetAsync(grads, 0, static_cast<size_t>(a->opt.n + 64) * sizeof(float), st));
+  // ---- model inputs: x_t for the noise branch (q_sample, :318-321), x_0 for the clean branch
+  if (sh.n0 > 0)
+    UMD_TRY(qsample(a->image, a->noise, a->t, a->sqrt_alphas_cumprod, a->sqrt_one_minus_alphas_cumprod, sh.n0,
+                    static_cast<int>(per), ss.model_in, st));
+  if (sh.n1 > 0)
+    UMD_CHECK_CUDA(cudaMemcpyAsync(ss.model_in + sh.n0 * per, a->image + sh.n0 * per, static_cast<size_t>(sh.n1) * per * sizeof(float),
+                                   cudaMemcpyDeviceToDevice, st));
+  UMD_TRY(step_prep(a->t, a->label, a->label_drop, sh.n0, B, c.num_classes, a->use_labels, ss.t_model,
+                    c.num_classes > 0 ? ss.labels_model : nullptr, st));
+  if (sh.masked0 && sh.n0 > 0) UMD_TRY(mask_argsort(a->mask_noise0, sh.n0, L, sh.keep0, ss.ids_shuffle, ss.ids_restore, nullptr, st));
+  if (sh.masked1 && sh.n1 > 0)
+    UMD_TRY(mask_argsort(a->mask_noise1, sh.n1, L, sh.keep1, ss.ids_shuffle + static_cast<long long>(sh.n0) * L,
+                         ss.ids_restore + static_cast<long long>(sh.n0) * L, nullptr, st));
+  umd_io io;
+  memset(&io, 0, sizeof(io));
+  io.image = ss.model_in; io.t = ss.t_model; io.labels = c.num_classes > 0 ? ss.labels_model : nullptr;
+  io.ids_shuffle = ss.ids_shuffle; io.ids_restore = ss.ids_restore; io.x0 = a->image; io.noise = a->noise; io.loss = loss;
+  UMD_TRY(engine_forward(&c, &sh, a->offsets, a->opt.params, a->opt.params_bf16, &io, a->workspace, ws_engine, 1, st));
+  ReduceCtx red{a, static_cast<Comm*>(a->comm), st, UMD_OK};
+  const bool reduce = a->comm != nullptr && comm_world(red.comm) > 1;
+  UMD_TRY(engine_backward(&c, &sh, a->offsets, a->opt.params, a->opt.params_bf16, grads, &io, a->workspace, ws_engine,
+                          reduce ? reduce_cb : nullptr, &red, st));
+  UMD_TRY(red.rc);
+  if (reduce) UMD_TRY(comm_join(red.comm, st));   // implicit GSPMD all-reduce of train_ae.py:364
+  if (optimise) {
+    umd_adamw_args o = a->opt;
+    o.grads = grads;
+    o.measurements = a->opt.measurements + 1;
+    UMD_TRY(umd_adamw_step(&o, st));
+    UMD_CHECK_CUDA(cudaMemcpyAsync(a->opt.measurements, loss, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  return UMD_OK;
+}
+
 extern "C" int umd_qsample(const float* x0, const float* noise, const int* t, const float* sa, const float* sb, int n,
                            int per_sample, float* out, umd_stream_t stream) {
   return qsample(x0, noise, t, sa, sb, n, per_sample, out, static_cast<cudaStream_t>(stream));
@@ -755,3 +933,5 @@ extern "C" int umd_ln_modulate_bwd_gated(const void* dy, int dy_is_bf16, const f
 extern "C" int umd_cast_f32_to_bf16(const float* x, long long n, void* out, umd_stream_t stream) {
   return cast_bf16(x, n, out, static_cast<cudaStream_t>(stream));
 }
+// measurement aid: 0 = keep the bias-gradient passes on the caller's stream (per-kernel timings then do not overlap)
+extern "C" void umd_debug_side_stream(int on) { umd::g_side_enabled = on ? 1 : 0; }

@@ -200,6 +200,18 @@ int attention_bwd(const AttnBwdArgs& a, cudaStream_t st);
 int attention_fwd_simt(const AttnArgs& a, cudaStream_t st);
 int attention_bwd_simt(const AttnBwdArgs& a, cudaStream_t st);
 
+// model-side timestep / label vectors of one training step (train_ae.py:327,341; ae.py:107-110; embeddings.py:43-45):
+// t_model[i] = t[i] + 1 for the n0 noised samples, 0 for the clean ones; labels_model[i] = label[i] (the null class
+// num_classes where label_drop[i] != 0) for the noised samples when use_labels, else the null class
+int step_prep(const int* t, const long long* label, const unsigned char* label_drop, int n0, int B, int num_classes,
+              int use_labels, int* t_model, int* labels_model, cudaStream_t st);
+
+// ---- data-parallel communicator (comm.cu) -------------------------------------------------
+struct Comm;
+int comm_world(const Comm* c);
+int comm_allreduce_mean_after(Comm* c, float* buf, long long n, cudaStream_t after, cudaEvent_t after2);
+int comm_join(Comm* c, cudaStream_t stream);
+
 // ---- optimiser (optimizer.cu) -----------------------------------------------------------
 int sumsq(const float* x, long long n, float* partials, int max_partials, float* out, cudaStream_t st);
 

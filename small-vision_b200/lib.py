@@ -125,6 +125,29 @@ class AdamwArgs(C.Structure):
 
 BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int)
 
+UMD_STEP_NO_OPTIMIZER = 1
+
+
+class TrainStepArgs(C.Structure):
+  """umd_train_step_args (include/umd_b200.h)."""
+  _fields_ = [
+      ("cfg", C.POINTER(ModelCfg)), ("shape", StepShape), ("offsets", C.c_void_p), ("opt", AdamwArgs), ("grads", C.c_void_p),
+      ("image", C.c_void_p), ("label", C.c_void_p), ("use_labels", C.c_int), ("t", C.c_void_p), ("noise", C.c_void_p),
+      ("mask_noise0", C.c_void_p), ("mask_noise1", C.c_void_p), ("label_drop", C.c_void_p),
+      ("sqrt_alphas_cumprod", C.c_void_p), ("sqrt_one_minus_alphas_cumprod", C.c_void_p),
+      ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("comm", C.c_void_p),
+      ("bucket_bounds", C.c_void_p), ("bucket_events", C.c_void_p), ("num_buckets", C.c_int), ("flags", C.c_int),
+  ]
+
+
+def train_workspace_bytes(mcfg, shape):
+  lib = load()
+  lib.umd_train_workspace_bytes.restype = C.c_size_t
+  n = lib.umd_train_workspace_bytes(C.byref(mcfg), C.byref(shape))
+  if n == 0:
+    raise UmdError("umd_train_workspace_bytes: " + lib.umd_last_error().decode())
+  return int(n)
+
 
 def model_cfg_struct(cfg):
   m = ModelCfg()

@@ -127,3 +127,48 @@ class GradientReducer:
       else:
         w.wait()
     self.works = []
+
+
+class Communicator:
+  """The C-level data-parallel communicator (umd_comm_*, NCCL below the C ABI) of one rank.  torch.distributed is only
+  the side channel that carries rank 0's ncclUniqueId to the other ranks; the gradient all-reduce itself is issued by
+  umd_train_step on the communicator's own stream behind the backward events."""
+
+  def __init__(self, process_group):
+    import ctypes as C
+    import torch.distributed as dist
+    from . import lib
+    self._lib = lib
+    L = lib.load()
+    if not L.umd_comm_available():
+      raise lib.UmdError("libnccl.so.2 could not be loaded: no data-parallel path without NCCL")
+    self.world = dist.get_world_size(process_group)
+    self.rank = dist.get_rank(process_group)
+    buf = (C.c_ubyte * 128)()
+    if self.rank == 0:
+      lib.check(L.umd_comm_unique_id(buf), "umd_comm_unique_id")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(process_group, 0), group=process_group)
+    idb = (C.c_ubyte * 128).from_buffer_copy(box[0])
+    h = C.c_void_p()
+    lib.check(L.umd_comm_init(C.c_int(self.rank), C.c_int(self.world), idb, C.byref(h)), "umd_comm_init")
+    self.handle = h
+
+  def allreduce_mean(self, t):
+    import ctypes as C
+    lib = self._lib
+    assert t.is_cuda and t.dtype.is_floating_point and t.element_size() == 4 and t.is_contiguous()
+    lib.check(lib.load().umd_comm_allreduce_mean(self.handle, lib.ptr(t), C.c_longlong(t.numel()), lib.current_stream()),
+              "umd_comm_allreduce_mean")
+    return t
+
+  def close(self):
+    if getattr(self, "handle", None):
+      self._lib.load().umd_comm_destroy(self.handle)
+      self.handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass

@@ -63,7 +63,8 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
   reducer = GradientReducer(layout, process_group)
   sc = _Scratch()
   sc.grads = None
-  wd_flags = {}
+  sc.comm = None
+  sc.ws = {}
 
   def draw_step_randoms(train_state, B, dev, *, supplied=None, rank=0):
     """The draws the reference makes inside one step (train_ae.py:302-317, ae.py:14, embeddings.py:44), in a fixed
@@ -95,10 +96,10 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
           (torch.rand(n_noise, device=dev, generator=gen) < cfg.cfg_dropout_rate)
     return out
 
-  def forward_backward(train_state, batch, *, rand_rank=None, reduce=True):
-    """Draws, q_sample, forward of both branches, loss and backward; with reduce the gradient arena is mean-all-reduced
-    over the process group.  Returns (arena, shadow, grads, loss_slot).  rand_rank overrides the rank that seeds the
-    draws (bench.py's data-parallel check replays other ranks' shards on rank 0)."""
+  def run_step(train_state, batch, *, rand_rank=None, reduce=True, optimise=True):
+    """One umd_train_step call (include/umd_b200.h): draws -> q_sample -> masking -> forward of both branches -> loss
+    -> backward -> gradient mean over the ranks -> clip + AdamW + EMA.  Returns (arena, shadow, grads, meas) with meas =
+    device float[4]: loss, l2_params, l2_updates, grad_norm (the last three only with optimise)."""
     images = batch["image"]
     assert images.is_cuda and images.dtype == torch.float32, "batch['image'] must be a float32 CUDA tensor"
     images = images.contiguous()
@@ -111,32 +112,9 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     masked1 = n_clean > 0
     keep0 = cfg.len_keep(tcfg.mask_ratio) if masked0 else L
     keep1 = cfg.len_keep(tcfg.mask_ratio_no_noise) if masked1 else L
+    comm = communicator(dev) if reduce else None
     rand = draw_step_randoms(train_state, B, dev, supplied=batch.get("_rand"),
                              rank=reducer.rank if rand_rank is None else rand_rank)
-    t, noise = rand["t"], rand["noise"]
-    ids_shuffle = torch.empty(B, L, dtype=torch.int32, device=dev)
-    ids_restore = torch.empty(B, L, dtype=torch.int32, device=dev)
-    if masked0:
-      a, b, _ = mask_argsort(rand["mask_noise_noise"], keep0)
-      ids_shuffle[:n_noise], ids_restore[:n_noise] = a, b
-    if masked1:
-      a, b, _ = mask_argsort(rand["mask_noise_clean"], keep1)
-      ids_shuffle[n_noise:], ids_restore[n_noise:] = a, b
-
-    # ---- model inputs: x_t for the noise branch (q_sample, :318-321), x_0 for the clean branch
-    model_in = images.clone()
-    if n_noise > 0:
-      q_sample(gd=train_state["gd"], x_start=images[:n_noise], t=t, noise=noise, out=model_in[:n_noise])
-    tm = torch.zeros(B, dtype=torch.int32, device=dev)
-    tm[:n_noise] = t + 1                              # :341 (clean branch sees t = 0, :327)
-    labels = None
-    if cfg.num_classes is not None:
-      labels = torch.full((B,), cfg.num_classes, dtype=torch.int32, device=dev)   # y=None -> null class (ae.py:107-110)
-      if tcfg.use_labels and n_noise > 0:
-        y = batch["label"][:n_noise].to(device=dev, dtype=torch.int32)
-        labels[:n_noise] = torch.where(rand["label_drop_noise"], torch.full_like(y, cfg.num_classes), y)
-
-    # ---- forward + loss + backward
     params = train_state["params"]
     arena = arena_from_tree(layout, params, dev)
     if not (isinstance(params, ParamTree) and params.arena is arena):
@@ -145,53 +123,91 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
     if sc.grads is None or sc.grads.device != dev:
       sc.grads = torch.empty(layout.total + N_EXTRA, dtype=torch.float32, device=dev)
       sc.opt_scratch = torch.empty(4096, dtype=torch.float32, device=dev)
-      sc.meas = torch.zeros(4, dtype=torch.float32, device=dev)
+      sc.wd_flags = layout.wd_flags(dev)
+      sc.bounds = (C.c_longlong * (2 * len(layout.bucket_bounds)))(*[x for lo_hi in layout.bucket_bounds for x in lo_hi])
+      sc.events = (C.c_int * len(layout.bucket_events))(*layout.bucket_events)
     grads = sc.grads
-    grads.zero_()
-    loss_slot = grads[layout.total:layout.total + 1]
-    model.forward_arena(arena, shadow, image=model_in, t=tm, labels=labels, n0=n_noise, n1=n_clean, keep0=keep0,
-                        keep1=keep1, masked0=masked0, masked1=masked1, ids_shuffle=ids_shuffle, ids_restore=ids_restore,
-                        want_pred=False, train=True, x0=images, noise=noise, loss_out=loss_slot)
-    model.backward_arena(arena, shadow, grads, bucket_cb=(lambda e: reducer.on_event(grads, e)) if reduce else None)
-    if reduce:
-      reducer.finish()                                # implicit GSPMD all-reduce of train_ae.py:364
-    return arena, shadow, grads, loss_slot
+    shape = model.step_shape(n_noise, n_clean, keep0, keep1, masked0, masked1)
+    wkey = (n_noise, n_clean, keep0, keep1, str(dev))
+    ws = sc.ws.get(wkey)
+    if ws is None:
+      ws = sc.ws[wkey] = torch.empty(lib.train_workspace_bytes(model._mcfg, shape), dtype=torch.uint8, device=dev)
+    meas = torch.empty(4, dtype=torch.float32, device=dev)   # fresh per step: the caller may read it at a later log step
+    gd = train_state["gd"]
+    a = lib.TrainStepArgs()
+    a.cfg = C.pointer(model._mcfg)
+    a.shape = shape
+    a.offsets = C.cast(model._offsets, C.c_void_p)
+    o = a.opt
+    o.params = lib.ptr(arena)
+    o.params_bf16 = lib.ptr(shadow)
+    o.n = layout.total
+    o.measurements = lib.ptr(meas)
+    a.grads = lib.ptr(grads)
+    if optimise:
+      opt = train_state["opt"]
+      count = int(opt["count"])
+      b1, b2 = tcfg.betas
+      o.mu, o.nu = lib.ptr(opt["mu"].arena), lib.ptr(opt["nu"].arena)
+      o.ema = lib.ptr(train_state["ema_params"].arena) if "ema_params" in train_state else None
+      o.wd_flags = lib.ptr(sc.wd_flags)
+      o.clip_norm, o.b1, o.b2, o.eps, o.wd = tcfg.clip_norm, b1, b2, 1e-8, tcfg.wd
+      # optax evaluates the schedule at the pre-increment count (train_ae.py:135-151)
+      o.lr = warmup_cosine_lr(count, peak=tcfg.scaled_peak_lr, warmup_steps=tcfg.warmup_steps, decay_steps=tcfg.total_steps)
+      o.bias_corr1, o.bias_corr2 = 1.0 - b1 ** (count + 1), 1.0 - b2 ** (count + 1)
+      o.ema_decay = tcfg.ema_decay or 0.0
+      o.scratch, o.scratch_floats = lib.ptr(sc.opt_scratch), sc.opt_scratch.numel()
+    else:
+      a.flags = lib.UMD_STEP_NO_OPTIMIZER
+    a.image = lib.ptr(images)
+    label = None
+    if cfg.num_classes is not None and tcfg.use_labels and n_noise > 0:
+      label = batch["label"].to(device=dev, dtype=torch.int64).contiguous()
+      a.use_labels = 1
+    a.label = lib.ptr(label)
+    drop = rand["label_drop_noise"].to(torch.uint8) if "label_drop_noise" in rand else None
+    a.label_drop = lib.ptr(drop)
+    a.t, a.noise = lib.ptr(rand["t"]), lib.ptr(rand["noise"])
+    a.mask_noise0 = lib.ptr(rand.get("mask_noise_noise"))
+    a.mask_noise1 = lib.ptr(rand.get("mask_noise_clean"))
+    a.sqrt_alphas_cumprod = lib.ptr(gd["sqrt_alphas_cumprod"])
+    a.sqrt_one_minus_alphas_cumprod = lib.ptr(gd["sqrt_one_minus_alphas_cumprod"])
+    a.workspace, a.workspace_bytes = lib.ptr(ws), ws.numel()
+    if comm is not None:
+      a.comm = comm.handle
+      a.bucket_bounds = C.cast(sc.bounds, C.c_void_p)
+      a.bucket_events = C.cast(sc.events, C.c_void_p)
+      a.num_buckets = len(layout.bucket_bounds)
+    lib.check(lib.load().umd_train_step(C.byref(a), lib.current_stream()), "umd_train_step")
+    return arena, shadow, grads, meas
+
+  def communicator(dev):
+    """The C-level NCCL communicator of this rank, created on first use (None on a single GPU)."""
+    if process_group is None or reducer.world == 1:
+      return None
+    if sc.comm is None:
+      from .sharding import Communicator
+      sc.comm = Communicator(process_group)
+    return sc.comm
+
+  def forward_backward(train_state, batch, *, rand_rank=None, reduce=True):
+    """Draws, q_sample, forward of both branches, loss and backward, no optimiser; with reduce the gradient arena is
+    mean-all-reduced over the process group.  Returns (arena, shadow, grads, loss_slot).  rand_rank overrides the rank
+    that seeds the draws (bench.py's data-parallel check replays other ranks' shards on rank 0)."""
+    arena, shadow, grads, _ = run_step(train_state, batch, rand_rank=rand_rank, reduce=reduce, optimise=False)
+    return arena, shadow, grads, grads[layout.total:layout.total + 1]
 
   def update_fn(train_state, batch):
-    arena, shadow, grads, loss_slot = forward_backward(train_state, batch)
-    dev = arena.device
-    rng = train_state["rng"]
-
-    # ---- optimiser (train_ae.py:365-366 with the chain of :135-151)
-    opt = train_state["opt"]
-    count = int(opt["count"])
-    lr = warmup_cosine_lr(count, peak=tcfg.scaled_peak_lr, warmup_steps=tcfg.warmup_steps, decay_steps=tcfg.total_steps)
-    b1, b2 = tcfg.betas
-    if dev not in wd_flags:
-      wd_flags[dev] = layout.wd_flags(dev)
-    a = lib.AdamwArgs()
-    a.params, a.grads = lib.ptr(arena), lib.ptr(grads)
-    a.mu, a.nu = lib.ptr(opt["mu"].arena), lib.ptr(opt["nu"].arena)
-    a.params_bf16 = lib.ptr(shadow)
-    a.ema = lib.ptr(train_state["ema_params"].arena) if "ema_params" in train_state else None
-    a.wd_flags = lib.ptr(wd_flags[dev])
-    a.n = layout.total
-    a.clip_norm, a.lr, a.b1, a.b2, a.eps, a.wd = tcfg.clip_norm, lr, b1, b2, 1e-8, tcfg.wd
-    a.bias_corr1, a.bias_corr2 = 1.0 - b1 ** (count + 1), 1.0 - b2 ** (count + 1)
-    a.ema_decay = tcfg.ema_decay or 0.0
-    a.scratch, a.scratch_floats = lib.ptr(sc.opt_scratch), sc.opt_scratch.numel()
-    a.measurements = lib.ptr(sc.meas)
-    lib.check(lib.load().umd_adamw_step(C.byref(a), lib.current_stream()), "umd_adamw_step")
+    arena, shadow, grads, meas = run_step(train_state, batch)
     model.set_shadow(arena, shadow)                     # the kernel refreshed the parameter shadow ...
     if "ema_params" in train_state:                     # ... but moved the EMA arena behind torch's back
       model.invalidate_shadow(train_state["ema_params"].arena)
-    opt["count"] = count + 1
-    rng = rng.clone()
+    train_state["opt"]["count"] = int(train_state["opt"]["count"]) + 1
+    rng = train_state["rng"].clone()
     rng[1] += 1
     train_state["rng"] = rng
-    # ---- measurements (train_ae.py:367-371); device scalars, read them only at log steps (:643-652)
-    m = torch.cat([loss_slot, sc.meas[:3]])
-    measurements = {"training_loss": m[0], "l2_params": m[1], "l2_updates": m[2], "grad_norm": m[3]}
+    # measurements (train_ae.py:367-371): device scalars, read them only at log steps (:643-652)
+    measurements = {"training_loss": meas[0], "l2_params": meas[1], "l2_updates": meas[2], "grad_norm": meas[3]}
     return train_state, measurements
 
   update_fn.grads = lambda: sc.grads
