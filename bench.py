@@ -136,6 +136,21 @@ def dp_check(update_fn, state, model, dev_batches_of, world, rank, pg, dev):
   return out
 
 
+def attention_bytes_per_step(cfg, tkw, per_gpu):
+  """Algorithmic HBM bytes of the fused attention kernels per step: forward reads q, k, v and writes o (bf16) + lse
+  (fp32); backward reads q, k, v, o, dO and writes dq, dk, dv + reads lse.  rows x D x 2 B per tensor."""
+  L, D, H = cfg.num_patches, cfg.width, cfg.num_heads
+  tok0 = 0 if cfg.adaln else 1
+  n1 = int(per_gpu * tkw["no_noise_prob"])
+  n0 = per_gpu - n1
+  k0 = cfg.len_keep(tkw["mask_ratio"]) if tkw["mask_ratio"] > 0 else L
+  k1 = cfg.len_keep(tkw["mask_ratio_no_noise"])
+  rows_enc = n0 * (k0 + cfg.num_cls + tok0) + n1 * (k1 + cfg.num_cls + tok0)
+  rows_dec = per_gpu * (L + 1 + tok0)
+  rows = cfg.depth * rows_enc + cfg.dec_depth * rows_dec
+  return {"attention_fwd": rows * (4 * D * 2 + H * 4), "attention_bwd": rows * (8 * D * 2 + H * 4)}
+
+
 def load_peaks():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(p):
@@ -403,9 +418,12 @@ def main():
   # switched on (two event records per launch cost ~1 % of the step) for the roofline / breakdown.
   ms_total = timed(step_resident, args.steps)
   launches = lib.launch_count() - launches0
+  # (the side stream is switched off for this pass so that the per-kernel event times do not overlap one another)
+  L.umd_debug_side_stream(0)
   L.umd_profile_enable(1)
   ms_profiled = timed(step_resident, args.steps)
   L.umd_profile_enable(0)
+  L.umd_debug_side_stream(1)
   prof_ms = (Ct.c_float * ncat)()
   prof_work = (Ct.c_double * ncat)()
   prof_n = (Ct.c_longlong * ncat)()
@@ -456,6 +474,7 @@ def main():
                 "algorithmic_flops_per_launch": gm["work_per_step"] / max(gm["launches_per_step"], 1), "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": gm["launches_per_step"], "share_of_step": gm["ms_per_step"] / ms_step_prof}
     breakdown = {}
+    attn_bytes = attention_bytes_per_step(cfg, tkw, per_gpu)
     for nm, c in cats.items():
       if c["ms_per_step"] <= 0:
         continue
@@ -465,6 +484,12 @@ def main():
                        "launches": c["launches_per_step"],
                        ("tflops" if tensor else "gbs"): round(rate / (1e12 if tensor else 1e9), 1),
                        "frac_of_peak": round(rate / ((peaks["tf_sustained"] * 1e12) if tensor else (peaks["hbm"] * 1e9)), 3)}
+      if nm in attn_bytes:
+        # arithmetic intensity ~ S / 2 flop/B (128 for the 257-token decoder) is below the ridge (1414.5 TF / 6.55 TB/s =
+        # 216 flop/B): at these sequence lengths fused attention is HBM-bound, so the HBM fraction is the one that counts
+        gbs = attn_bytes[nm] / (c["ms_per_step"] * 1e-3) / 1e9
+        breakdown[nm].update(bound="hbm", gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peaks["hbm"], 3),
+                             frac_of_tensor_peak=breakdown[nm].pop("frac_of_peak"))
     line = {
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -478,6 +503,7 @@ def main():
         "step_frac_of_bf16_peak": fl_img * value / world / 1e12 / peaks["tf_sustained"],
         "flops_per_image": fl_img, "final_loss": final_loss, "loss_check": loss_check, "dp_check": dp,
         "roofline": roofline, "breakdown": breakdown, "profile_scopes_dropped": dropped,
+        "breakdown_note": "per-kernel CUDA-event times of a second pass of K steps with the side stream off (no overlap between kernels)",
         "ms_per_step_profiled": ms_step_prof,
         "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": launches / args.steps,
         "clocks": clocks,

@@ -62,6 +62,9 @@ enum {
                            out1(f32) = aux(f32) + gate[sample(row)] * a        vit.py:89-94,106-108 */
   UMD_EPI_DGELU = 4,    /* out0(bf16) = acc * gelu_tanh'(aux(bf16))                             */
   UMD_EPI_ATOMIC = 5,   /* out0(f32) += acc   (split-K weight gradients)                        */
+  UMD_EPI_BF16_DELTA = 6, /* out0(bf16) = acc ; out1(f32)[row, c / 64] = sum over the 64-column group c of acc * aux(bf16):
+                             dO = dA Wo^T together with delta = rowsum(dO o O) per head; N % 64 == 0,
+                             ld1 = number of 64-column groups per row of out1 */
 };
 
 typedef struct umd_gemm_args {
@@ -119,6 +122,10 @@ int umd_attention_fwd(const void* qkv_bf16, void* out_bf16, float* lse, int n0, 
                       umd_stream_t stream);
 int umd_attention_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse,
                       void* dqkv_bf16, int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream);
+/* Backward with delta[rows, H] = rowsum(dO o O) per head supplied (the step engine gets it from the epilogue of the
+ * out-projection dgrad GEMM, UMD_EPI_BF16_DELTA) instead of the forward output: 20 % fewer bytes, no prologue. */
+int umd_attention_bwd_delta(const void* qkv_bf16, const void* dout_bf16, const float* lse, const float* delta,
+                            void* dqkv_bf16, int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream);
 /* same contract on the CUDA-core kernels (the in-library checker of the tcgen05 attention path) */
 int umd_attention_fwd_simt(const void* qkv_bf16, void* out_bf16, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
                            umd_stream_t stream);

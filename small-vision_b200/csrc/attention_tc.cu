@@ -545,6 +545,7 @@ struct BwdParams {
   const __nv_bfloat16* out;
   const __nv_bfloat16* dout;
   const float* lse;
+  const float* delta;   // [rows, H] rowsum(dO o O) from the out-projection dgrad epilogue; null = form it here from O
   __nv_bfloat16* dqkv;
   int row_base;
   int S, SP, H;
@@ -610,11 +611,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     const int row0 = p.row_base + sample * S;
     // O (for delta) and this sample's [S][H] block of log-sum-exps are parked in the P^T / dS^T tile region,
     // which has no other use until the first score tile has been processed
-    const uint32_t lse_bytes = p.lse_bulk ? static_cast<uint32_t>(S) * p.H * 4u : 0u;
-    mbar_expect_tx(bar_ld0, 2u * SP * AT_ROW + lse_bytes);
-    load_rows(sdO, &td128, &td16, bar_ld0, h * AT_DH, sample, SP);
-    load_rows(sPt, &to128, &to16, bar_ld0, h * AT_DH, sample, SP);
-    if (p.lse_bulk) bulk_load_1d(sPt + SP * AT_ROW, p.lse + static_cast<long long>(row0) * p.H, lse_bytes, bar_ld0);
+    if (p.delta) {   // delta and lse come straight from global memory (one float each per query row): only dO to fetch
+      mbar_expect_tx(bar_ld0, 1u * SP * AT_ROW);
+      load_rows(sdO, &td128, &td16, bar_ld0, h * AT_DH, sample, SP);
+    } else {
+      const uint32_t lse_bytes = p.lse_bulk ? static_cast<uint32_t>(S) * p.H * 4u : 0u;
+      mbar_expect_tx(bar_ld0, 2u * SP * AT_ROW + lse_bytes);
+      load_rows(sdO, &td128, &td16, bar_ld0, h * AT_DH, sample, SP);
+      load_rows(sPt, &to128, &to16, bar_ld0, h * AT_DH, sample, SP);
+      if (p.lse_bulk) bulk_load_1d(sPt + SP * AT_ROW, p.lse + static_cast<long long>(row0) * p.H, lse_bytes, bar_ld0);
+    }
     mbar_expect_tx(bar_ld, 3u * SP * AT_ROW);
     load_rows(sK, &tq128, &tq16, bar_ld, D + h * AT_DH, sample, SP);
     load_rows(sQ, &tq128, &tq16, bar_ld, h * AT_DH, sample, SP);
@@ -626,7 +632,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       prefetch_rows(&tq128, &tq16, h2 * AT_DH, s2, SP);
       prefetch_rows(&tq128, &tq16, 2 * D + h2 * AT_DH, s2, SP);
       prefetch_rows(&td128, &td16, h2 * AT_DH, s2, SP);
-      prefetch_rows(&to128, &to16, h2 * AT_DH, s2, SP);
+      if (!p.delta) prefetch_rows(&to128, &to16, h2 * AT_DH, s2, SP);
     }
   };
   if (warp == 0 && lane == 0) {
@@ -748,26 +754,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       }
       const int kq = nq >> 4, kkv = nkv >> 4;
       if (elect_one()) {
+      // (fully unrolled with constant descriptor increments: the rolled loops cost ~60 cycles of address arithmetic
+      // per MMA, 1.5 k cycles per block on the critical path between P^T / dS^T and the next block's tiles)
       {  // dV_j += P^T dO_i
         const uint64_t bb = o_mn + static_cast<uint64_t>(i * 128 * ROW16);
-#pragma unroll 1
-        for (int kk = 0; kk < kq; ++kk)
-          umma_f16_ss(tmem_base + col_dv, pt_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
-                      bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t d0 = tmem_base + col_dv;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (kk < kq)
+            umma_f16_ss(d0, pt_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
+                        bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
       }
       {  // dK_j += dS^T Q_i
         const uint64_t bb = q_mn + static_cast<uint64_t>(i * 128 * ROW16);
-#pragma unroll 1
-        for (int kk = 0; kk < kq; ++kk)
-          umma_f16_ss(tmem_base + col_dk, st_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
-                      bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t d0 = tmem_base + col_dk;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (kk < kq)
+            umma_f16_ss(d0, st_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
+                        bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
       }
       {  // dQ_i += dS K_j   (dS^T tile read as an MN-major A operand)
         const uint64_t bb = k_mn + static_cast<uint64_t>(j * 128 * ROW16);
-#pragma unroll 1
-        for (int kk = 0; kk < kkv; ++kk)
-          umma_f16_ss(tmem_base + col_dq + 64 * i, st_mn + static_cast<uint64_t>(kk * 16 * ROW16),
-                      bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_mn, (j > 0 || kk > 0) ? 1u : 0u);
+        const uint32_t d0 = tmem_base + col_dq + 64 * i;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (kk < kkv)
+            umma_f16_ss(d0, st_mn + static_cast<uint64_t>(kk * 16 * ROW16), bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_mn,
+                        (j > 0 || kk > 0) ? 1u : 0u);
       }
       umma_commit(bar_tfree);
       if (i == nt - 1) umma_commit(bar_acc);
@@ -799,7 +813,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     // delta = rowsum(dO * O) and lse in log2 units, both from shared memory, one query row per thread (the
     // 128B swizzle makes the row-per-lane reads conflict-free); the region O and the lse block are read from
     // becomes the P^T / dS^T tiles after the barrier below
-    {
+    if (p.delta) {
+      // one query row per thread: lse (log2 units) and delta from global memory, no wait on the operand loads
+      const int q = tid;
+      if (q < SP) {
+        float ls = 0.f, dl = 0.f;
+        if (q < S) {
+          const long long o = static_cast<long long>(row0 + q) * p.H + h;
+          ls = __ldg(p.lse + o) * LOG2E;
+          dl = __ldg(p.delta + o);
+        }
+        sDelta[q] = dl;
+        sLse[q] = ls;
+      }
+    } else {
       const float* lse_blk = reinterpret_cast<const float*>(sPt + SP * AT_ROW);   // [S][H]
       float lse_direct = 0.f;
       if (!p.lse_bulk && tid < S) lse_direct = p.lse[static_cast<long long>(row0 + tid) * p.H + h];
@@ -1203,14 +1230,16 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     UMD_TRY(make_tmap_bf16(&td128, dout, D, S, n, D, static_cast<uint64_t>(S) * D, 128));
     UMD_TRY(make_tmap_bf16(&td16, dout, D, S, n, D, static_cast<uint64_t>(S) * D, tail_rows(S)));
     UMD_TRY(make_tmap_bf16(&tmdq, dqkv, 3 * D, S, n, 3 * D, static_cast<uint64_t>(S) * 3 * D, 128));
-    const __nv_bfloat16* outp = a.out + static_cast<long long>(seg[k].row_base) * D;
+    UMD_REQUIRE(a.out || a.delta, "attention_bwd: either the forward output or delta = rowsum(dO o O) is required");
+    // (with delta supplied the O maps are never used: point them at dO so that they stay valid descriptors)
+    const __nv_bfloat16* outp = a.delta ? dout : a.out + static_cast<long long>(seg[k].row_base) * D;
     CUtensorMap to128, to16;
     UMD_TRY(make_tmap_bf16(&to128, outp, D, S, n, D, static_cast<uint64_t>(S) * D, 128));
     UMD_TRY(make_tmap_bf16(&to16, outp, D, S, n, D, static_cast<uint64_t>(S) * D, tail_rows(S)));
     BwdParams p;
     p.lse_bulk = ((S * a.H * 4) % 16 == 0) && ((static_cast<long long>(seg[k].row_base) * a.H * 4) % 16 == 0) &&
                  ((reinterpret_cast<uintptr_t>(a.lse) & 15) == 0) && (((S + 15) & ~15) * AT_ROW + S * a.H * 4 <= 4 * AT_SLAB);
-    p.out = a.out; p.dout = a.dout; p.lse = a.lse; p.dqkv = a.dqkv; p.row_base = seg[k].row_base;
+    p.out = a.out; p.dout = a.dout; p.lse = a.lse; p.delta = a.delta; p.dqkv = a.dqkv; p.row_base = seg[k].row_base;
     p.S = S; p.SP = (p.S + 15) & ~15; p.H = a.H;
     split_tail(S, tail_limit(true), &p.nt, &p.ntail);
     p.nbuf = p.nt <= 2 ? 2 : 1;

@@ -63,7 +63,7 @@ struct Plan {
   bf16* Wf_mat; float* biasm; float* predp; bf16* dpredp; float* loss_partials; int n_loss_partials;
   // backward scratch
   float* dx_dec; float* dx_enc; float* dxf_enc;
-  bf16* dzb; bf16* dgb; bf16* dyb; bf16* dqkv;
+  bf16* dzb; bf16* dgb; bf16* dyb; bf16* dqkv; float* delta;
   float* dcond; bf16* ds; bf16* dta1; bf16* dth1; bf16* dla1; bf16* dlh1; float* dlemb;
   float* dWf_mat; float* dbiasm;
   size_t bytes;
@@ -218,6 +218,7 @@ int make_plan(Plan& P, const umd_model_cfg& c, const umd_step_shape& sh, void* w
     P.dxf_enc = b.take<float>(static_cast<long long>(P.Te) * D);
     P.dzb = b.take<bf16>(Tmax * D); P.dgb = b.take<bf16>(Tmax * P.M4); P.dyb = b.take<bf16>(Tmax * D);
     P.dqkv = b.take<bf16>(Tmax * 3 * D);
+    P.delta = b.take<float>(Tmax * P.H);
     P.dcond = b.take<float>(static_cast<long long>(B) * D); P.ds = b.take<bf16>(static_cast<long long>(B) * D);
     P.dta1 = b.take<bf16>(static_cast<long long>(B) * 2 * D); P.dth1 = b.take<bf16>(static_cast<long long>(B) * 2 * D);
     P.dla1 = P.has_label ? b.take<bf16>(static_cast<long long>(B) * 2 * D) : nullptr;
@@ -465,10 +466,16 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
     lnb.g_dgate = dada ? dada + 2 * D : nullptr; lnb.g_lddgate = ldada; lnb.g_dbias = c.G(s.base + UMD_S_O_B, lo);
     UMD_TRY(ln_mod_bwd(lnb, D, s.nsamples, true, c.st));
     // ---- attention branch (P.dzb = gate0 * dx)
-    UMD_TRY(dense_dgrad(c, P.dzb, T, D, c.WB(s.base + UMD_S_O_W, lo), D, UMD_EPI_BF16, P.dyb));
+    {  // dO = dA Wo^T, with delta = rowsum(dO o O) per head from the same accumulators (App. E step 7): the attention
+       // backward then needs neither O nor a prologue of its own
+      umd_gemm_args g = gemm_base(P.dzb, c.WB(s.base + UMD_S_O_W, lo), T, D, D);
+      g.a_mn = 0; g.b_mn = 0; g.lda = D; g.ldb = D;
+      g.epi = UMD_EPI_BF16_DELTA; g.out0 = P.dyb; g.ld0 = D; g.aux = lb.o; g.ldaux = D; g.out1 = P.delta; g.ld1 = P.H;
+      UMD_TRY(gemm_bf16(g, c.st));
+    }
     UMD_TRY(dense_wgrad(c, lb.o, T, D, P.dzb, D, D, c.G(s.base + UMD_S_O_W, lo)));
     AttnBwdArgs ab;
-    ab.qkv = lb.qkv; ab.out = lb.o; ab.dout = P.dyb; ab.lse = lb.lse; ab.dqkv = P.dqkv; ab.rm = s.rm;
+    ab.qkv = lb.qkv; ab.out = nullptr; ab.delta = P.delta; ab.dout = P.dyb; ab.lse = lb.lse; ab.dqkv = P.dqkv; ab.rm = s.rm;
     ab.nsamples = s.nsamples; ab.H = P.H; ab.Dh = P.Dh; ab.scale = 1.0f / sqrtf(static_cast<float>(P.Dh));
     UMD_TRY(attention_bwd(ab, c.st));
     {  // dWq, dWk, dWv as one batch-3 wgrad GEMM
@@ -873,6 +880,7 @@ static AttnArgs mk_attn(const void* qkv, void* out, float* lse, int n0, int s0, 
 static AttnBwdArgs mk_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n0,
                                int s0, int n1, int s1, int H, int Dh) {
   AttnBwdArgs a;
+  a.delta = nullptr;
   a.qkv = static_cast<const __nv_bfloat16*>(qkv); a.out = static_cast<const __nv_bfloat16*>(out);
   a.dout = static_cast<const __nv_bfloat16*>(dout); a.lse = lse; a.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   a.rm = ragged_rowmap(n0, s0, n1, s1); a.nsamples = n0 + n1; a.H = H; a.Dh = Dh; a.scale = 1.0f / sqrtf(static_cast<float>(Dh));
@@ -885,6 +893,13 @@ extern "C" int umd_attention_fwd(const void* qkv, void* out, float* lse, int n0,
 extern "C" int umd_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int n0,
                                  int s0, int n1, int s1, int H, int Dh, umd_stream_t stream) {
   return attention_bwd(mk_attn_bwd(qkv, out, dout, lse, dqkv, n0, s0, n1, s1, H, Dh), static_cast<cudaStream_t>(stream));
+}
+extern "C" int umd_attention_bwd_delta(const void* qkv, const void* dout, const float* lse, const float* delta, void* dqkv,
+                                       int n0, int s0, int n1, int s1, int H, int Dh, umd_stream_t stream) {
+  UMD_REQUIRE(delta != nullptr, "umd_attention_bwd_delta: delta is required");
+  AttnBwdArgs a = mk_attn_bwd(qkv, nullptr, dout, lse, dqkv, n0, s0, n1, s1, H, Dh);
+  a.delta = delta;
+  return attention_bwd(a, static_cast<cudaStream_t>(stream));
 }
 extern "C" int umd_attention_fwd_simt(const void* qkv, void* out, float* lse, int n0, int s0, int n1, int s1, int H, int Dh,
                                       umd_stream_t stream) {

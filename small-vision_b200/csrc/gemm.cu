@@ -116,7 +116,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
   // bf16 results leave through swizzled shared memory and TMA stores (full 128-byte lines, M/N tails clipped by
   // the tensor map) instead of one 16-byte store per lane per row
-  constexpr bool STAGED = (BN >= 128) && (EPI == UMD_EPI_BF16 || EPI == UMD_EPI_GELU || EPI == UMD_EPI_DGELU);
+  constexpr bool STAGED = (BN >= 128) && (EPI == UMD_EPI_BF16 || EPI == UMD_EPI_GELU || EPI == UMD_EPI_DGELU || EPI == UMD_EPI_BF16_DELTA);
+  constexpr bool AUX_TILE = (EPI == UMD_EPI_DGELU || EPI == UMD_EPI_BF16_DELTA);   // the epilogue reads a bf16 operand tile fetched by TMA
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -130,7 +131,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (STAGED) {
       tma_prefetch_desc(&tmO0);
       if (EPI == UMD_EPI_GELU) tma_prefetch_desc(&tmO1);
-      if (EPI == UMD_EPI_DGELU) tma_prefetch_desc(&tmAux);
+      if (AUX_TILE) tma_prefetch_desc(&tmAux);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -297,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // staging buffer of this chunk; bulk_wait_read<NB-1>: the store that last used it has drained
           uint8_t* sbuf = sbuf0 + (nstaged % NB) * 4096;
           uint8_t* my_row = sbuf + lane * 128;
-          if (EPI == UMD_EPI_DGELU && active && lane == 0) {
+          if (AUX_TILE && active && lane == 0) {
             bulk_wait_read<NB - 1>();
             mbar_expect_tx(&aux_bar[ew], 4096);
             tma_load_3d(sbuf, &tmAux, &aux_bar[ew], col0, trow, 0);
@@ -313,7 +314,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               v[j] = __uint_as_float(r0[j]);
               v[32 + j] = __uint_as_float(r1[j]);
             }
-            if (EPI != UMD_EPI_DGELU && bias) {
+            if (!AUX_TILE && bias) {
 #pragma unroll
               for (int j = 0; j < 64; j += 4) {
                 if (col0 + j < p.N) {
@@ -334,6 +335,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   v[8 * j + 2 * q + 1] *= gelu_tanh_grad(bf16_hi(uw[q]));
                 }
               }
+            } else if (EPI == UMD_EPI_BF16_DELTA) {
+              // delta[row, head] = sum_c dO[row, c] O[row, c] over the 64 columns of this chunk (one head: Dh = 64)
+              mbar_wait(&aux_bar[ew], (aux_uses++) & 1);
+              float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 uu = ld_shared_v4(smem_u32(my_row) + ((j ^ sw) << 4));
+                const uint32_t uw[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  d4[q] = fmaf(v[8 * j + 2 * q], bf16_lo(uw[q]), d4[q]);
+                  d4[q] = fmaf(v[8 * j + 2 * q + 1], bf16_hi(uw[q]), d4[q]);
+                }
+              }
+              if (row_ok) reinterpret_cast<float*>(p.out1)[static_cast<long long>(row) * p.ld1 + (col0 >> 6)] = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+              __syncwarp();   // every lane has read its operand row before the chunk is overwritten below
             } else {
               if (lane == 0) bulk_wait_read<NB - 1>();
               __syncwarp();
@@ -566,6 +583,9 @@ static int launch_gemm_epi(int epi, const CUtensorMap* tm, const GemmParams& p, 
       case UMD_EPI_GELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GELU>(tm, p, s);
       case UMD_EPI_GATE_RES: return launch_gemm_t<BN, false, B_MN, UMD_EPI_GATE_RES>(tm, p, s);
       case UMD_EPI_DGELU: return launch_gemm_t<BN, false, B_MN, UMD_EPI_DGELU>(tm, p, s);
+      case UMD_EPI_BF16_DELTA:
+        if (BN >= 128) return launch_gemm_t<(BN >= 128 ? BN : 128), false, B_MN, UMD_EPI_BF16_DELTA>(tm, p, s);
+        break;
       default: break;
     }
   }
@@ -633,7 +653,9 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
   else         UMD_TRY(make_tmap_bf16(&tmB, a.B, a.N, a.K, b_batch, a.ldb, a.b_bs, BK));
 
   tm[2] = tm[3] = tm[4] = tmA;  // placeholders for the epilogues that do not use them
-  if (bn >= 128 && (a.epi == UMD_EPI_BF16 || a.epi == UMD_EPI_GELU || a.epi == UMD_EPI_DGELU)) {
+  UMD_REQUIRE(a.epi != UMD_EPI_BF16_DELTA || (bn >= 128 && a.N % 64 == 0 && a.out1 && a.ld1 > 0 && a.batch == 1),
+              "umd_gemm_bf16: the delta epilogue needs N %% 64 == 0 (N > 64), out1 with ld1 = groups per row, batch 1");
+  if (bn >= 128 && (a.epi == UMD_EPI_BF16 || a.epi == UMD_EPI_GELU || a.epi == UMD_EPI_DGELU || a.epi == UMD_EPI_BF16_DELTA)) {
     UMD_REQUIRE(a.out0 && (reinterpret_cast<uintptr_t>(a.out0) & 15) == 0 && a.ld0 % 8 == 0 && a.bs0 % 8 == 0,
                 "umd_gemm_bf16: bf16 outputs must be 16-byte aligned with ld0 / bs0 multiples of 8");
     UMD_TRY(make_tmap_bf16(&tm[2], a.out0, a.N, a.M, a.batch, a.ld0, a.bs0, 32));
@@ -642,9 +664,9 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
                   "umd_gemm_bf16: GELU epilogue needs an aligned out1 with ld1 %% 8 == 0 and batch 1");
       UMD_TRY(make_tmap_bf16(&tm[3], a.out1, a.N, a.M, 1, a.ld1, 0, 32));
     }
-    if (a.epi == UMD_EPI_DGELU) {
+    if (a.epi == UMD_EPI_DGELU || a.epi == UMD_EPI_BF16_DELTA) {
       UMD_REQUIRE(a.aux && (reinterpret_cast<uintptr_t>(a.aux) & 15) == 0 && a.ldaux % 8 == 0 && a.batch == 1,
-                  "umd_gemm_bf16: DGELU epilogue needs an aligned aux with ldaux %% 8 == 0 and batch 1");
+                  "umd_gemm_bf16: DGELU / delta epilogues need an aligned aux with ldaux %% 8 == 0 and batch 1");
       UMD_TRY(make_tmap_bf16(&tm[4], a.aux, a.N, a.M, 1, a.ldaux, 0, 32));
     }
   }

@@ -186,7 +186,8 @@ struct AttnArgs {
 };
 struct AttnBwdArgs {
   const __nv_bfloat16* qkv;
-  const __nv_bfloat16* out;
+  const __nv_bfloat16* out;   // [rows, H*Dh] forward output, or null when delta is supplied
+  const float* delta;         // [rows, H] rowsum(dO o O) per head (produced by the out-projection dgrad epilogue), or null
   const __nv_bfloat16* dout;  // [rows, H*Dh]
   const float* lse;
   __nv_bfloat16* dqkv;        // [rows, 3*H*Dh]

@@ -34,7 +34,7 @@ class GemmArgs(C.Structure):
   ]
 
 
-EPI_BF16, EPI_F32, EPI_GELU, EPI_GATE_RES, EPI_DGELU, EPI_ATOMIC = range(6)
+EPI_BF16, EPI_F32, EPI_GELU, EPI_GATE_RES, EPI_DGELU, EPI_ATOMIC, EPI_BF16_DELTA = range(7)
 
 _lib = None
 

@@ -149,6 +149,26 @@ def test_dgelu_epilogue():
   _close(out, ref, rtol=2 ** -6)
 
 
+@pytest.mark.parametrize("M,H", [(514, 12), (300, 6), (131, 2)])
+def test_delta_epilogue(M, H):
+  """dO = dA Wo^T (bf16) together with delta[row, head] = sum_c dO[row, c] O[row, c] over each head's 64 columns
+   from the same accumulators."""
+  lib = _lib()
+  D = 64 * H
+  dA = _rand((M, D), seed=21)
+  Wo = _rand((D, D), scale=D ** -0.5, seed=22)   # out kernel [H*Dh, D] viewed [N = D_in, K = D_out]: dO = dA Wo^T
+  O = _rand((M, D), seed=23)
+  out = torch.empty(M, D, device="cuda", dtype=torch.bfloat16)
+  delta = torch.full((M, H), float("nan"), device="cuda")
+  lib.gemm(dA, Wo, M=M, N=D, K=D, epi=lib.EPI_BF16_DELTA, out0=out, aux=O, ldaux=D, out1=delta, ld1=H)
+  torch.cuda.synchronize()
+  ref = dA.float() @ Wo.float().t()
+  _close(out, ref, rtol=2 ** -6)
+  dref = (ref * O.float()).reshape(M, H, 64).sum(-1)
+  assert torch.isfinite(delta).all()
+  assert float((delta - dref).abs().max()) <= 2e-2 * float(dref.abs().max()) + 1e-3
+
+
 def test_many_tiles_persistent_phases():
   """More work items than SMs x TMEM stages: exercises ring/accumulator phase wrap-around."""
   lib = _lib()

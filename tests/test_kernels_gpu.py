@@ -256,6 +256,37 @@ def test_attention_fwd_bwd(n0, s0, n1, s1, H, impl, monkeypatch):
     assert r < 2e-2, f"d{name} rel-L2 {r}"
 
 
+@pytest.mark.parametrize("n0,s0,n1,s1,H", [(2, 164, 2, 68, 6), (3, 257, 0, 0, 12), (0, 0, 2, 69, 6), (2, 260, 0, 0, 6),
+                                           (3, 165, 1, 258, 16), (1, 16, 1, 1, 2), (40, 257, 64, 68, 12)])
+def test_attention_bwd_with_supplied_delta(n0, s0, n1, s1, H):
+  """umd_attention_bwd_delta (delta = rowsum(dO o O) per head from the out-projection dgrad epilogue, no O operand)
+  gives the gradients of umd_attention_bwd, which forms delta itself from O."""
+  lib = _lib()
+  L = lib.load()
+  Dh, D = 64, H * 64
+  rows = n0 * s0 + n1 * s1
+  g = torch.Generator().manual_seed(rows + 3 * H)
+  qg = (torch.randn(rows, 3 * D, generator=g) * 1.2).to(torch.bfloat16).to(DEV)
+  dg = torch.randn(rows, D, generator=g).to(torch.bfloat16).to(DEV)
+  out = torch.empty(rows, D, device=DEV, dtype=torch.bfloat16)
+  lse = torch.empty(rows, H, device=DEV)
+  lib.check(L.umd_attention_fwd(lib.ptr(qg), lib.ptr(out), lib.ptr(lse), n0, s0, n1, s1, H, Dh, lib.current_stream()), "attn fwd")
+  d_o = torch.full((rows, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+  lib.check(L.umd_attention_bwd(lib.ptr(qg), lib.ptr(out), lib.ptr(dg), lib.ptr(lse), lib.ptr(d_o), n0, s0, n1, s1, H, Dh,
+                                lib.current_stream()), "attn bwd")
+  delta = (dg.float() * out.float()).reshape(rows, H, Dh).sum(-1).contiguous()
+  d_d = torch.full((rows, 3 * D), float("nan"), device=DEV, dtype=torch.bfloat16)
+  lib.check(L.umd_attention_bwd_delta(lib.ptr(qg), lib.ptr(dg), lib.ptr(lse), lib.ptr(delta), lib.ptr(d_d), n0, s0, n1, s1, H,
+                                      Dh, lib.current_stream()), "attn bwd delta")
+  torch.cuda.synchronize()
+  assert torch.isfinite(d_d.float()).all()
+  assert U.rel_l2(d_d.float().cpu(), d_o.float().cpu()) < 2e-3
+  # and against autograd
+  ref_in = qg.float().cpu().requires_grad_(True)
+  _attn_ref(ref_in, n0, s0, n1, s1, H, Dh).backward(dg.float().cpu())
+  assert U.rel_l2(d_d.float().cpu(), ref_in.grad) < 2e-2
+
+
 @pytest.mark.parametrize("n0,s0,n1,s1,H", [(2, 258, 0, 0, 6), (2, 260, 1, 129, 4), (1, 131, 2, 257, 12), (3, 132, 0, 0, 2)])
 def test_attention_tail_rows_on_control_warps(n0, s0, n1, s1, H):
   """Tails of 1..4 rows behind a full 128-row tile computed on the idle control warps, forward and backward (the

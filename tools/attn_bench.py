@@ -40,12 +40,17 @@ def main():
     f = lambda: lib.check(L.umd_attention_fwd(lib.ptr(qkv), lib.ptr(out), lib.ptr(lse), n0, s0, n1, s1, H, Dh, st))
     b = lambda: lib.check(L.umd_attention_bwd(lib.ptr(qkv), lib.ptr(out), lib.ptr(dout), lib.ptr(lse), lib.ptr(dqkv), n0, s0,
                                               n1, s1, H, Dh, st))
+    delta = torch.randn(rows, H, device="cuda")
+    bd = lambda: lib.check(L.umd_attention_bwd_delta(lib.ptr(qkv), lib.ptr(dout), lib.ptr(lse), lib.ptr(delta), lib.ptr(dqkv),
+                                                     n0, s0, n1, s1, H, Dh, st))
     flops = 4.0 * Dh * H * (n0 * s0 * s0 + n1 * s1 * s1)
-    tf, tb = bench(f, iters), bench(b, iters)
-    by_f = rows * D * 2 * 4 + rows * H * 4
-    by_b = rows * D * 2 * 9 + rows * H * 4
+    tf, tb, td = bench(f, iters), bench(b, iters), bench(bd, iters)
+    by_f = rows * D * 2 * 4 + rows * H * 4            # q, k, v in; o, lse out
+    by_b = rows * D * 2 * 8 + rows * H * 4            # q, k, v, o, dO, lse in; dq, dk, dv out
+    by_d = rows * D * 2 * 7 + rows * H * 8            # ... with delta [rows, H] instead of o
     print(f"{name:10s} fwd {tf:7.3f} ms {flops / tf / 1e9:7.1f} TF/s {by_f / tf / 1e6:7.1f} GB/s | "
-          f"bwd {tb:7.3f} ms {2.5 * flops / tb / 1e9:7.1f} TF/s {by_b / tb / 1e6:7.1f} GB/s")
+          f"bwd {tb:7.3f} ms {2.5 * flops / tb / 1e9:7.1f} TF/s {by_b / tb / 1e6:7.1f} GB/s | "
+          f"bwd(delta) {td:7.3f} ms {by_d / td / 1e6:7.1f} GB/s")
 
 
 if __name__ == "__main__":

@@ -16,7 +16,8 @@ def run(n, S, H=12):
   tl = torch.zeros(11 * 64, dtype=torch.int64, device="cuda")
   for it in range(2):
     L.umd_debug_attn_timeline(C.c_void_p(tl.data_ptr()))
-    lib.check(L.umd_attention_bwd(lib.ptr(qkv), lib.ptr(out), lib.ptr(dout), lib.ptr(lse), lib.ptr(dqkv), n, S, 0, 0, H, Dh, st))
+    delta = (dout.float() * out.float()).reshape(rows, H, Dh).sum(-1).contiguous()
+    lib.check(L.umd_attention_bwd_delta(lib.ptr(qkv), lib.ptr(dout), lib.ptr(lse), lib.ptr(delta), lib.ptr(dqkv), n, S, 0, 0, H, Dh, st))
     torch.cuda.synchronize()
   L.umd_debug_attn_timeline(None)
   t = tl.cpu().reshape(11, 64)
