@@ -151,7 +151,22 @@ class Communicator:
     dist.broadcast_object_list(box, src=dist.get_global_rank(process_group, 0), group=process_group)
     idb = (C.c_ubyte * 128).from_buffer_copy(box[0])
     h = C.c_void_p()
-    lib.check(L.umd_comm_init(C.c_int(self.rank), C.c_int(self.world), idb, C.byref(h)), "umd_comm_init")
+    # NCCL announces its version on stdout when the first communicator of a process is created (NCCL_DEBUG=VERSION/WARN);
+    # stdout belongs to the caller (bench.py prints exactly one JSON line there), so the banner is sent to stderr
+    import os
+    import sys
+    sys.stdout.flush()
+    libc = C.CDLL(None)
+    libc.fflush(None)
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      rc = L.umd_comm_init(C.c_int(self.rank), C.c_int(self.world), idb, C.byref(h))
+    finally:
+      libc.fflush(None)
+      os.dup2(saved, 1)
+      os.close(saved)
+    lib.check(rc, "umd_comm_init")
     self.handle = h
 
   def allreduce_mean(self, t):

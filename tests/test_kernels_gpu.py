@@ -287,6 +287,30 @@ def test_attention_bwd_with_supplied_delta(n0, s0, n1, s1, H):
   assert U.rel_l2(d_d.float().cpu(), ref_in.grad) < 2e-2
 
 
+def test_attention_rejects_shapes_outside_the_tensor_core_path():
+  """No silent CUDA-core fallback: the product entry points return UMD_ERR_UNSUPPORTED (3)."""
+  lib = _lib()
+  L = lib.load()
+  for (n, s, H, Dh) in ((1, 300, 2, 64), (1, 64, 2, 32)):
+    rows, D = n * s, H * Dh
+    qkv = torch.zeros(rows, 3 * D, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(rows, D, device=DEV, dtype=torch.bfloat16)
+    lse = torch.zeros(rows, H, device=DEV)
+    rc = L.umd_attention_fwd(lib.ptr(qkv), lib.ptr(out), lib.ptr(lse), n, s, 0, 0, H, Dh, lib.current_stream())
+    assert rc == 3 and b"unsupported shape" in L.umd_last_error()
+    rc = L.umd_attention_bwd(lib.ptr(qkv), lib.ptr(out), lib.ptr(out), lib.ptr(lse), lib.ptr(qkv), n, s, 0, 0, H, Dh,
+                             lib.current_stream())
+    assert rc == 3
+  # the checker kernels stay reachable by name
+  n, s, H, Dh = 1, 64, 2, 64
+  qkv = torch.randn(n * s, 3 * H * Dh, device=DEV).to(torch.bfloat16)
+  out = torch.zeros(n * s, H * Dh, device=DEV, dtype=torch.bfloat16)
+  lse = torch.zeros(n * s, H, device=DEV)
+  lib.check(L.umd_attention_fwd_simt(lib.ptr(qkv), lib.ptr(out), lib.ptr(lse), n, s, 0, 0, H, Dh, lib.current_stream()), "simt")
+  torch.cuda.synchronize()
+  assert torch.isfinite(out.float()).all()
+
+
 @pytest.mark.parametrize("n0,s0,n1,s1,H", [(2, 258, 0, 0, 6), (2, 260, 1, 129, 4), (1, 131, 2, 257, 12), (3, 132, 0, 0, 2)])
 def test_attention_tail_rows_on_control_warps(n0, s0, n1, s1, H):
   """Tails of 1..4 rows behind a full 128-row tile computed on the idle control warps, forward and backward (the
