@@ -322,7 +322,20 @@ def main():
   dev = torch.device("cuda", local)
   pg = None
   if world > 1:
-    dist.init_process_group("nccl", device_id=dev)
+    # NCCL prints a version banner on stdout when a process creates its first communicator; stdout carries the one JSON
+    # line of this benchmark, so the banner goes to stderr
+    import ctypes
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      dist.init_process_group("nccl", device_id=dev)
+      dist.barrier()
+      torch.cuda.synchronize()
+    finally:
+      ctypes.CDLL(None).fflush(None)
+      os.dup2(saved, 1)
+      os.close(saved)
     pg = dist.group.WORLD
   assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 

@@ -5,8 +5,15 @@ sorted order (`_traverse_with_names`, big_vision/utils.py:650-673) and rebuilds 
 (utils.py:857-884); `load_params` (utils.py:239-290) accepts a file holding the whole train state ("params/..."),
 a Flax-optimizer state ("opt/target/...") or the bare parameter tree, and an optional ":sub/key" suffix on the path.
 The functions below keep those names and behaviours, so a `.npz` written by the reference's tooling loads into
-`Model.apply` / `create_train_state` unchanged, and one written here loads there.  (The tensorstore directory format
-of utils.py:886-1016 needs the `tensorstore` package, which this image does not have; it is out of scope.)
+`Model.apply` / `create_train_state` unchanged, and one written here loads there.
+
+The reference's other on-disk layout — the tensorstore directories of `save_checkpoint_ts` / `load_checkpoint_ts`
+(utils.py:886-1016): `{path}-{step:09d}[-tmp]/` holding one array per leaf in a sub-directory named by the leaf path
+with '/' replaced by '~', plus a `{path}-LAST` pointer file — is restated at the end of this file.  The arrays are
+zarr-v2 stores (what jax.experimental.array_serialization writes through tensorstore's "zarr" driver): a `.zarray`
+JSON header and chunk files named by '.'-joined chunk indices.  `tensorstore` itself is not in this image, so the byte
+format follows the zarr v2 specification (PARITY UNPINNED for the bytes; the directory / pointer protocol is checked
+against the reference's own functions in tests/test_checkpoint_ts_cpu.py).
 
 Host-side only: numpy in, numpy out; no CUDA, no torch requirement.
 """
@@ -112,9 +119,15 @@ def load_params(ckpt):
     m = re.match(r"^(.*?/.*?)(?::([\w/]+))?$", ckpt)
     if m:  # '/path/to/file.npz:Encoder' -> ('/path/to/file.npz', 'Encoder')
       ckpt, key = m.groups()
-    if not ckpt.endswith(".npz"):
-      raise NotImplementedError("only .npz checkpoints are supported (tensorstore directories need `tensorstore`)")
-    checkpoint = load_checkpoint_np(ckpt)
+    if ckpt.endswith(".npz"):
+      checkpoint = load_checkpoint_np(ckpt)
+    else:
+      # utils.py:279-283: anything else is a tensorstore checkpoint (a directory, or a prefix with a -LAST pointer), of
+      # which only the parameters (and only `key`) are read.  (The reference formats the pattern as f"params/{key}/.*"
+      # even when key is None, which matches nothing; without a key the whole "params/" sub-tree is loaded here.)
+      checkpoint = load_checkpoint_ts(ckpt, regex=f"params/{key}/.*" if key is not None else "params/.*")
+      params = checkpoint["params"]
+      return tree_get(params, key) if key is not None else params
   else:
     checkpoint = ckpt if not _is_flat(ckpt) else load_checkpoint_np(ckpt)
   if "params" in checkpoint:
@@ -130,3 +143,132 @@ def load_params(ckpt):
 
 def _is_flat(d):
   return isinstance(d, Mapping) and any(isinstance(k, str) and "/" in k for k in d.keys())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tensorstore-layout checkpoints (utils.py:886-1016)
+# ----------------------------------------------------------------------------------------------------------------------
+_ZARR_DTYPES = {"float32": "<f4", "float64": "<f8", "float16": "<f2", "int32": "<i4", "int64": "<i8", "int16": "<i2",
+                "int8": "|i1", "uint8": "|u1", "uint16": "<u2", "uint32": "<u4", "uint64": "<u8", "bool": "|b1"}
+
+
+def _zarr_write(dirname, arr, compressor=None):
+  """One array as a zarr-v2 store with a single chunk (what array_serialization writes for an unsharded array:
+  chunks = the whole array).  bfloat16 leaves (optimiser moments) are stored as float32."""
+  import json
+  arr = np.asarray(arr)
+  arr = arr if arr.ndim == 0 else np.ascontiguousarray(arr)   # (ascontiguousarray would turn a scalar into shape [1])
+  if arr.dtype.name not in _ZARR_DTYPES:
+    raise TypeError(f"dtype {arr.dtype} has no zarr v2 encoding here")
+  os.makedirs(dirname, exist_ok=True)
+  shape = list(arr.shape)
+  meta = {"chunks": shape if shape else [], "compressor": compressor, "dtype": _ZARR_DTYPES[arr.dtype.name], "fill_value": None,
+          "filters": None, "order": "C", "shape": shape, "zarr_format": 2, "dimension_separator": "."}
+  raw = arr.tobytes()
+  if compressor is not None:
+    if compressor.get("id") != "zstd":
+      raise NotImplementedError(f"compressor {compressor}")
+    import pyarrow as pa
+    raw = pa.compress(raw, codec="zstd", asbytes=True)
+  with open(os.path.join(dirname, ".zarray"), "w") as f:
+    json.dump(meta, f)
+  chunk = ".".join("0" for _ in shape) if shape else "0"
+  with open(os.path.join(dirname, chunk), "wb") as f:
+    f.write(raw)
+
+
+def _zarr_read(dirname):
+  """Reads a zarr-v2 array directory: any regular chunk grid, '.' or '/' separated chunk keys, no filters, compressor
+  null or zstd (through pyarrow), missing chunks = fill_value."""
+  import itertools
+  import json
+  with open(os.path.join(dirname, ".zarray")) as f:
+    meta = json.load(f)
+  if meta.get("zarr_format") != 2 or meta.get("filters"):
+    raise NotImplementedError(f"{dirname}: only unfiltered zarr v2 arrays are supported")
+  dtype = np.dtype(meta["dtype"])
+  shape, chunks = tuple(meta["shape"]), tuple(meta["chunks"])
+  order = meta.get("order", "C")
+  sep = meta.get("dimension_separator", ".")
+  comp = meta.get("compressor")
+  fill = meta.get("fill_value")
+  out = np.empty(shape, dtype=dtype)
+  out[...] = 0 if fill is None else fill
+  grid = [range(-(-s // c)) for s, c in zip(shape, chunks)] if shape else [range(1)]
+  for idx in itertools.product(*grid):
+    key = sep.join(str(i) for i in idx) if shape else "0"
+    fn = os.path.join(dirname, *key.split("/"))
+    if not os.path.exists(fn):
+      continue
+    raw = open(fn, "rb").read()
+    n_elem = int(np.prod(chunks)) if shape else 1
+    if comp is not None:
+      if comp.get("id") != "zstd":
+        raise NotImplementedError(f"{dirname}: compressor {comp}")
+      import pyarrow as pa
+      raw = pa.decompress(raw, decompressed_size=n_elem * dtype.itemsize, codec="zstd", asbytes=True)
+    blk = np.frombuffer(raw, dtype=dtype, count=n_elem).reshape(chunks if shape else (), order=order)
+    if not shape:
+      out[...] = blk
+      continue
+    sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
+    out[sl] = blk[tuple(slice(0, x.stop - x.start) for x in sl)]
+  return out
+
+
+def tssave(pytree, path, compressor=None):
+  """utils.py:886-910: one array directory per leaf, named by the leaf path with '/' -> '~'."""
+  names_and_vals = tree_flatten_with_names(pytree)
+  for name, _ in names_and_vals:
+    if "~" in name:
+      raise ValueError(f"Symbol '~' is not allowed in names. Found in {name}.")
+  os.makedirs(path, exist_ok=True)
+  names = []
+  for name, val in names_and_vals:
+    a = _to_numpy(val)
+    _zarr_write(os.path.join(path, name.replace("/", "~")), a, compressor)
+    names.append(name.replace("/", "~"))
+  return names
+
+
+def save_checkpoint_ts(checkpoint, path, step, keep=True, compressor=None):
+  """utils.py:913-959: write `{path}-{step:09d}` (`-tmp` appended unless keep), then atomically point `{path}-LAST`
+  at it and remove the previous checkpoint if that one was temporary."""
+  import shutil
+  curr = f"{step:09d}{'-tmp' if not keep else ''}"
+  tssave(checkpoint, f"{path}-{curr}", compressor)
+  with open(f"{path}-CUR", "w") as f:
+    f.write(curr)
+  last = ""
+  if os.path.exists(f"{path}-LAST"):
+    with open(f"{path}-LAST") as f:
+      last = f.read()
+  os.replace(f"{path}-CUR", f"{path}-LAST")
+  if last.endswith("-tmp") and last != curr:
+    shutil.rmtree(f"{path}-{last}", ignore_errors=True)
+  return curr
+
+
+def tsload(path, *, tree=None, regex=None):
+  """utils.py:975-1016: array names from `tree`, or from the directory listing ('~' -> '/', optional regex filter)."""
+  if (tree is not None) and (regex is not None):
+    raise ValueError("If tree is specified, regex filtering is not allowed.")
+  if tree is None:
+    names = sorted(set(p.replace("~", "/") for p in os.listdir(path)))
+    rx = re.compile(regex) if regex is not None else re.compile(".*")
+    names = [p for p in names if rx.match(p)]
+  else:
+    names = [n for n, _ in tree_flatten_with_names(tree)]
+  vals = [_zarr_read(os.path.join(path, n.replace("/", "~"))) for n in names]
+  return recover_tree(names, vals)
+
+
+def load_checkpoint_ts(path, **tsload_kw):
+  """utils.py:962-972: follow `{path}-LAST` when it exists, else `path` is the checkpoint directory itself."""
+  to_load = path
+  try:
+    with open(f"{path}-LAST") as f:
+      to_load = f"{path}-{f.read()}"
+  except OSError:
+    pass
+  return tsload(to_load, **tsload_kw)

@@ -105,3 +105,27 @@ def test_ranks_draw_different_randoms():
   for k in r0:
     assert torch.equal(r0[k], r0b[k])
   assert not torch.equal(r0["noise"], r1["noise"]) and not torch.equal(r0["mask_noise_clean"], r1["mask_noise_clean"])
+
+
+@pytest.mark.parametrize("fmt", ["npz", "ts"])
+def test_checkpoint_file_loads_into_the_arena_and_reproduces_the_forward(tmp_path, fmt):
+  """A parameter file in either of the reference's on-disk layouts (flat .npz, utils.py:218-236; tensorstore-style
+  directory, utils.py:886-1016) -> load_params -> Model.apply: pre_logits and pred equal those of the tree that was saved."""
+  from small_vision_b200 import checkpoint as CK
+  model, _ = U.make_models("S/4", adaln=True, num_classes=10, depth=2, dec_depth=1)
+  params = U.perturb_init(model, 5, DEV)
+  x = torch.rand(3, 64, 64, 3, device=DEV) * 2 - 1
+  t = torch.tensor([[5], [400], [999]], dtype=torch.int32, device=DEV)
+  y = torch.tensor([1, 7, 3], device=DEV)
+  pred0, out0 = model.apply({"params": params}, x, t=t, y=y)
+  if fmt == "npz":
+    path = str(tmp_path / "ck.npz")
+    CK.save_checkpoint_np(path, {"params": params, "opt": {"count": 3}})
+  else:
+    path = str(tmp_path / "ck")
+    CK.save_checkpoint_ts({"params": params, "opt": {"count": torch.tensor(3)}}, path, 100, keep=False)
+  loaded = CK.load_params(path)                      # plain nested dict of numpy arrays
+  pred1, out1 = model.apply({"params": loaded}, x, t=t, y=y)
+  assert torch.equal(pred0, pred1) and torch.equal(out0["pre_logits"], out1["pre_logits"])
+  sub = CK.load_params(path + ":Encoder/encoder_norm")
+  assert sorted(sub) == ["bias", "scale"]
