@@ -474,16 +474,20 @@ def main():
                   "launches_per_step": prof_n[i] / args.steps}
     gm = cats["gemm"]
     gemm_tf = gm["work_per_step"] / (gm["ms_per_step"] * 1e-3) / 1e12 if gm["ms_per_step"] > 0 else 0.0
-    traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_summary.json")
-    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, launch-weighted over the forward / dgrad GEMM shapes of
+    # one step, from the committed per-shape table (tools/traffic_table.py; regenerated by tools/profile_round.sh)
+    traffic, traffic_src, traffic_alg = None, None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic_table.json")
+    if os.path.exists(tpath) and args.workload == "umd_b4" and per_gpu == WORKLOADS["umd_b4"][2]:
       with open(tpath) as f:
         tj = json.load(f)
-      traffic = tj.get("traffic_bytes_per_launch_mean")
-      traffic_src = "profiles/r01_ncu_gemm_summary.json (%d captured launches, mean)" % len(tj.get("launches", []))
+      traffic = tj.get("fwd_dgrad_traffic_bytes_per_launch")
+      traffic_alg = tj.get("fwd_dgrad_algorithmic_bytes_per_launch")
+      traffic_src = "profiles/r02_traffic_table.json (commit %s: %d launches of one step under ncu, %d shapes)" % (
+          tj.get("commit"), tj.get("fwd_dgrad_launches_per_step", 0), len(tj.get("shapes", {})))
     roofline = {"bound": "tensor", "kernel": "gemm_kernel (tcgen05 forward/dgrad GEMMs)", "achieved": gemm_tf,
                 "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
-                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": traffic_alg,
                 "algorithmic_flops_per_launch": gm["work_per_step"] / max(gm["launches_per_step"], 1), "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": gm["launches_per_step"], "share_of_step": gm["ms_per_step"] / ms_step_prof}
     breakdown = {}

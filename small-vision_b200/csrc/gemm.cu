@@ -670,6 +670,21 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
       UMD_TRY(make_tmap_bf16(&tm[4], a.aux, a.N, a.M, 1, a.ldaux, 0, 32));
     }
   }
+  {
+    // measurement aid (tools/traffic_table.py): UMD_GEMM_LOG=<file> appends one line per launch, in launch order, so that an
+    // ncu launch list of the same process can be joined with the problem shapes
+    static FILE* logf = nullptr;
+    static int log_state = 0;
+    if (log_state == 0) {
+      const char* e = getenv("UMD_GEMM_LOG");
+      logf = (e && *e) ? fopen(e, "a") : nullptr;
+      log_state = 1;
+    }
+    if (logf) {
+      fprintf(logf, "%d %d %d %d %d %d %d %d %d %d\n", a.M, a.N, a.K, a.batch, a.a_mn, a.b_mn, a.epi, p.split_k, bn, p.cta2);
+      fflush(logf);
+    }
+  }
   ProfScope prof(a.a_mn ? PC_GEMM_WGRAD : PC_GEMM, 2.0 * a.M * static_cast<double>(a.N) * a.K * a.batch, stream);
   switch (bn) {
     case 256: return launch_gemm_bn<256>(a.a_mn, a.b_mn, a.epi, tm, p, stream);

@@ -143,8 +143,9 @@ class ArenaLayout:
   encoder layer in backward order (layer depth-1-j) is final; 1 + depth = everything is final.  `bucket_bounds[i]` is a
   contiguous arena range that may be all-reduced once event `bucket_events[i]` has been signalled, listed in that order:
   the decoder side, then groups of ENC_LAYERS_PER_BUCKET encoder layers from the top down (the first one also carries
-  Encoder/encoder_norm and whatever trails the arena), the last group merged with the embeddings / conditioning leaves
-  that precede layer 0 in the arena (their gradients are the last to become final)."""
+  Encoder/encoder_norm and whatever trails the arena), and last — the only bucket whose reduction nothing overlaps, so
+  it is kept small — layer 0 together with the embeddings / conditioning leaves that precede it in the arena (their
+  gradients are the last to become final)."""
 
   def __init__(self, cfg: ModelConfig):
     self.cfg = cfg
@@ -196,7 +197,9 @@ class ArenaLayout:
     hi_layer, hi = depth, self.total
     while hi_layer > 0:
       lo_layer = max(hi_layer - k, 0)
-      if lo_layer == 0:   # the last group: merged with the embeddings / conditioning leaves in front of layer 0
+      if lo_layer == 0 and hi_layer > 1:
+        lo_layer = 1      # keep the bucket that cannot overlap anything small: layer 0 alone travels with the embeddings
+      if lo_layer == 0:   # the last bucket: layer 0 merged with the embeddings / conditioning leaves in front of it
         self.bucket_bounds.append((rest0, hi))
         self.bucket_events.append(depth + 1)
       else:

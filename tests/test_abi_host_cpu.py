@@ -182,12 +182,13 @@ def test_weight_decay_flags_follow_no_decay_list():
   # first one ends the arena: it carries Encoder/encoder_norm and the trailing loss slot), the last group merged with
   # the embeddings / conditioning leaves in front of layer 0
   b, ev = lay.bucket_bounds, lay.bucket_events
-  assert len(b) == 5 and ev == [0, 3, 6, 9, 13] and lay.num_events == 14
+  assert len(b) == 6 and ev == [0, 3, 6, 9, 11, 13] and lay.num_events == 14
   assert b[0][0] == 0 and b[1][1] == lay.total and b[-1][0] == b[0][1]
   cov = sorted(b)
   assert all(cov[i][1] == cov[i + 1][0] for i in range(len(cov) - 1)) and cov[-1][1] == lay.total
   enc0, es = lay.stack_start["Encoder"], lay.layer_stride["Encoder"]
-  assert b[1][0] == enc0 + 9 * es and b[2] == (enc0 + 6 * es, enc0 + 9 * es) and b[4][1] == enc0 + 3 * es
+  assert b[1][0] == enc0 + 9 * es and b[2] == (enc0 + 6 * es, enc0 + 9 * es) and b[4] == (enc0 + es, enc0 + 3 * es)
+  assert b[5][1] == enc0 + es
   # a scanned leaf is a strided [depth, ...] view: layer l's slice is contiguous inside layer block l
   q = lay.by_path[("Encoder", "ScanCheckpointEncoder1DBlock_0", "MultiHeadDotProductAttention_0", "query", "kernel")]
   v = q.view(torch.arange(lay.total, dtype=torch.float32))
