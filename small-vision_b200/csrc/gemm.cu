@@ -77,16 +77,19 @@ __device__ __forceinline__ float gelu_tanh_grad(float u) {
 struct WorkItem {
   int m0, n0, b, kb0, kb1;
 };
-// item order: n fastest, then batch, then k-split, then m — CTAs running concurrently share the A row-panel.
+// item order: n fastest, then batch, then m, then k-split.  CTAs that run concurrently then share the A row-panel (all n
+// and batch items of one m) AND, in a split-K weight gradient, the B column-panel (all m of one k-range): with the k-split
+// inside m the three m-tiles of a K = 131 584 wgrad ran in different waves and re-read the B panel from HBM once each
+// (ncu: 2.0 GB against 0.8 GB algorithmic for the batched q/k/v weight gradient).
 template <int BN, int TM = BM>
-__device__ __forceinline__ WorkItem decode_item(long long item, int n_tiles, int batch, int split_k, int kb_total) {
+__device__ __forceinline__ WorkItem decode_item(long long item, int n_tiles, int m_tiles, int batch, int split_k, int kb_total) {
   WorkItem w;
   const int n = static_cast<int>(item % n_tiles);
   long long r = item / n_tiles;
   w.b = static_cast<int>(r % batch);
   r /= batch;
-  const int ks = static_cast<int>(r % split_k);
-  const int m = static_cast<int>(r / split_k);
+  const int m = static_cast<int>(r % m_tiles);
+  const int ks = static_cast<int>(r / m_tiles);
   w.m0 = m * TM;
   w.n0 = n * BN;
   w.kb0 = static_cast<int>(static_cast<long long>(ks) * kb_total / split_k);
@@ -180,7 +183,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (CTA2) tma_load_3d_2sm(dst, tm, bar, c0, c1, c2); else tma_load_3d(dst, tm, bar, c0, c1, c2);
     };
     for (long long item = worker; item < total_items; item += nworkers) {
-      const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const WorkItem w = decode_item<BN, TM>(item, n_tiles, m_tiles, p.batch, p.split_k, kb_total);
       const int m0 = w.m0 + rank * BM, n0 = w.n0 + rank * BNL, b = w.b, kb0 = w.kb0, kb1 = w.kb1;
       const int ba = p.a_bcast ? 0 : b;
       const int bb = p.b_bcast ? 0 : b;
@@ -227,7 +230,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int it = 0;
     for (long long item = worker; item < total_items; item += nworkers, ++it) {
-      const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const WorkItem w = decode_item<BN, TM>(item, n_tiles, m_tiles, p.batch, p.split_k, kb_total);
       const int kb0 = w.kb0, kb1 = w.kb1;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -272,7 +275,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t nstaged = 0;   // chunks staged by this warp so far (selects the staging buffer)
     int it = 0;
     for (long long item = worker; item < total_items; item += nworkers, ++it) {
-      const WorkItem w = decode_item<BN, TM>(item, n_tiles, p.batch, p.split_k, kb_total);
+      const WorkItem w = decode_item<BN, TM>(item, n_tiles, m_tiles, p.batch, p.split_k, kb_total);
       const int m0 = w.m0 + rank * BM, n0 = w.n0, b = w.b;   // this CTA's 128 rows of the accumulator, all BN columns
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -681,7 +684,8 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream) {
       log_state = 1;
     }
     if (logf) {
-      fprintf(logf, "%d %d %d %d %d %d %d %d %d %d\n", a.M, a.N, a.K, a.batch, a.a_mn, a.b_mn, a.epi, p.split_k, bn, p.cta2);
+      fprintf(logf, "%d %d %d %d %d %d %d %d %d %d %d %d\n", a.M, a.N, a.K, a.batch, a.a_mn, a.b_mn, a.epi, p.split_k, bn, p.cta2,
+              p.a_bcast, p.b_bcast);
       fflush(logf);
     }
   }

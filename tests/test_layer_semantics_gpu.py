@@ -76,7 +76,8 @@ def test_layernorm_epsilon_is_1e_6(D):
   gamma, beta = 1 + 0.1 * torch.randn(D, generator=g), 0.1 * torch.randn(D, generator=g)
   out = torch.empty(rows, D, device=DEV)
   mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
-  lib.check(L.umd_ln_modulate_fwd(lib.ptr(x.to(DEV)), lib.ptr(gamma.to(DEV)), lib.ptr(beta.to(DEV)), None, None, C.c_longlong(0),
+  xg, gg, bg = x.to(DEV), gamma.to(DEV), beta.to(DEV)      # named: the buffers must outlive the asynchronous launch
+  lib.check(L.umd_ln_modulate_fwd(lib.ptr(xg), lib.ptr(gg), lib.ptr(bg), None, None, C.c_longlong(0),
                                   C.c_int(1), C.c_int(rows), C.c_int(0), C.c_int(0), C.c_int(D), lib.ptr(out), C.c_int(0),
                                   lib.ptr(mean), lib.ptr(rstd), lib.current_stream()), "ln fwd")
   torch.cuda.synchronize()

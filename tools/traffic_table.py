@@ -39,11 +39,13 @@ def main(csv_path, log_path, out_path):
   assert len(shapes) >= len(launches) > 0, (len(shapes), len(launches))
   shapes = shapes[:len(launches)]
   table = OrderedDict()
-  for L, (M, N, K, batch, a_mn, b_mn, epi, split_k, bn, cta2) in zip(launches, shapes):
+  for L, shp in zip(launches, shapes):
+    M, N, K, batch, a_mn, b_mn, epi, split_k, bn, cta2 = shp[:10]
+    a_bc, b_bc = (shp[10], shp[11]) if len(shp) >= 12 else (0, 0)
     role = "wgrad" if a_mn else ("dgrad" if not b_mn else "fwd")
     key = f"{role} M={M} N={N} K={K} batch={batch} epi={EPI[epi]}"
     e = table.setdefault(key, {"role": role, "M": M, "N": N, "K": K, "batch": batch, "epilogue": EPI[epi], "split_k": split_k,
-                               "tile_n": bn, "cta_pairs": cta2, "kernel": L["kernel"], "launches": 0, "dram_bytes": 0.0, "dur_us": 0.0,
+                               "tile_n": bn, "cta_pairs": cta2, "a_broadcast": a_bc, "b_broadcast": b_bc, "kernel": L["kernel"], "launches": 0, "dram_bytes": 0.0, "dur_us": 0.0,
                                "tensor_pct": 0.0})
     e["launches"] += 1
     e["dram_bytes"] += L.get("dram__bytes_read.sum", 0.0) + L.get("dram__bytes_write.sum", 0.0)
@@ -54,7 +56,9 @@ def main(csv_path, log_path, out_path):
     e["dram_bytes_per_launch"] = e.pop("dram_bytes") / n
     e["dur_us_per_launch"] = e.pop("dur_us") / n
     e["tensor_pipe_active_pct"] = e.pop("tensor_pct") / n
-    e["algorithmic_bytes_per_launch"] = 2 * e["batch"] * (e["M"] * e["K"] + e["K"] * e["N"]) + out_bytes(e["M"], e["N"], e["batch"], [k for k, v in EPI.items() if v == e["epilogue"]][0])
+    na = 1 if e.get("a_broadcast") else e["batch"]      # a broadcast operand is read once for the whole batch
+    nb = 1 if e.get("b_broadcast") else e["batch"]
+    e["algorithmic_bytes_per_launch"] = 2 * (na * e["M"] * e["K"] + nb * e["K"] * e["N"]) + out_bytes(e["M"], e["N"], e["batch"], [k for k, v in EPI.items() if v == e["epilogue"]][0])
     e["traffic_over_algorithmic"] = e["dram_bytes_per_launch"] / e["algorithmic_bytes_per_launch"]
     e["flops_per_launch"] = 2.0 * e["M"] * e["N"] * e["K"] * e["batch"]
   fd = [e for e in table.values() if e["role"] != "wgrad"]
