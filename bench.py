@@ -300,6 +300,8 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-dp-check", action="store_true")
+  ap.add_argument("--residual", default="float32", choices=["float32", "bfloat16"],
+                  help="dtype of the residual stream between the blocks (bfloat16 = the reference's dtype_mm='bfloat16' flow)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 1)
   if args.impl == "reference":
@@ -342,7 +344,7 @@ def main():
   mkw, tkw, per_gpu = WORKLOADS[args.workload]
   if args.per_gpu_batch:
     per_gpu = args.per_gpu_batch
-  model = Model(**mkw)
+  model = Model(**mkw, residual_dtype=args.residual)
   cfg = model.cfg
   B_global = per_gpu * world
   tcfg = TrainConfig(batch_size=B_global, **tkw)
@@ -515,7 +517,7 @@ def main():
                                f"({per_gpu - int(per_gpu * tkw['no_noise_prob'])} noised + {int(per_gpu * tkw['no_noise_prob'])} clean)",
                    "global_batch": B_global, "per_gpu_batch": per_gpu, "parallelism": f"dp{world}",
                    "params": model.layout.num_params, "l2": "inputs rotate over 4 batches; each step writes > 10 GB of activations (>> 126 MB L2)",
-                   "precision": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream / LayerNorm / loss / AdamW (bf16 mu)"},
+                   "precision": "bf16 GEMM/attention operands, fp32 accumulate, %s residual stream, fp32 LayerNorm statistics / gradient stream / loss / AdamW (bf16 mu)" % ("bf16" if args.residual == "bfloat16" else "fp32")},
         "step_tflops_per_gpu": fl_img * value / world / 1e12,
         "step_frac_of_bf16_peak": fl_img * value / world / 1e12 / peaks["tf_sustained"],
         "flops_per_image": fl_img, "final_loss": final_loss, "loss_check": loss_check, "dp_check": dp,

@@ -51,6 +51,10 @@ class ModelConfig:
   no_decay_list: Sequence[str] = ("cls", "image_mask_embedding", "bias")
   # not a reference field: orientation of final_conv; True = flax default
   flip_final_conv: bool = True
+  # not a reference field: dtype of the residual stream between the blocks during training.  "float32" (default) keeps
+  # the stream of the reference's default dtype_mm="float32"; "bfloat16" is the stream of its dtype_mm="bfloat16" flow
+  # (ae.py:51,100: Dense / Conv outputs and x + y are bf16, LayerNorm statistics fp32)
+  residual_dtype: str = "float32"
 
   @property
   def patch(self) -> int:

@@ -57,7 +57,9 @@ __device__ __forceinline__ float4 load_row4(const __nv_bfloat16* p) {
 #ifndef LN_FWD_MIN_CTAS
 #define LN_FWD_MIN_CTAS 4
 #endif
-template <int NV, typename OutT>
+// XinT / XoutT: dtype of the residual stream read / written (float, or __nv_bfloat16 with umd_model_cfg.residual_bf16: the
+// reference's own dtype_mm="bfloat16" flow, ae.py:51,100; statistics stay fp32 either way).
+template <int NV, typename OutT, typename XinT, typename XoutT>
 __global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdArgs a, int rows_per_chunk) {
   constexpr int D = NV * 128;
   __shared__ __align__(16) float sA[D];
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdA
       r = in_row = row_of(a.rm, n, tok);
     }
     const bool is_cond = a.cond_row && (a.gather_L > 0 ? a.gather_off + tok : tok) == 0;
-    const float* src = is_cond ? a.cond_row + static_cast<long long>(n) * D : a.x + static_cast<long long>(in_row) * D;
+    const XinT* src = reinterpret_cast<const XinT*>(a.x) + static_cast<long long>(in_row) * D;
+    const float* csrc = is_cond ? a.cond_row + static_cast<long long>(n) * D : nullptr;
     const __nv_bfloat16* bp = (a.res_branch && !is_cond) ? a.res_branch + static_cast<long long>(in_row) * D : nullptr;
     // every HBM load of the row is issued before the first store: x_out may alias x, so a store in between would
     // pin all later loads behind it
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdA
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane * 4 + 128 * i;
-      v[i] = *reinterpret_cast<const float4*>(src + c);
+      v[i] = csrc ? load_row4(csrc + c) : load_row4(src + c);
       braw[i] = bp ? *reinterpret_cast<const uint2*>(bp + c) : make_uint2(0u, 0u);
     }
     if (bp) {
@@ -111,9 +114,17 @@ __global__ void __launch_bounds__(256, LN_FWD_MIN_CTAS) ln_mod_fwd_kernel(LnFwdA
       }
     }
     if (a.x_out) {
+      XoutT* xo = reinterpret_cast<XoutT*>(a.x_out) + static_cast<long long>(in_row) * D + lane * 4;
 #pragma unroll
-      for (int i = 0; i < NV; ++i)
-        *reinterpret_cast<float4*>(a.x_out + static_cast<long long>(in_row) * D + lane * 4 + 128 * i) = v[i];
+      for (int i = 0; i < NV; ++i) store_row4(xo + 128 * i, v[i].x, v[i].y, v[i].z, v[i].w);
+      if (sizeof(XoutT) == 2) {
+        // the stream IS what was stored: normalise the rounded values so that forward and backward see the same x
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          v[i].x = __bfloat162float(__float2bfloat16_rn(v[i].x)); v[i].y = __bfloat162float(__float2bfloat16_rn(v[i].y));
+          v[i].z = __bfloat162float(__float2bfloat16_rn(v[i].z)); v[i].w = __bfloat162float(__float2bfloat16_rn(v[i].w));
+        }
+      }
     }
     float s = 0.f, s2 = 0.f;
 #pragma unroll
@@ -165,7 +176,12 @@ static int ln_fwd_dispatch(const LnFwdArgs& a, int D, cudaStream_t st) {
   const int rpc = ceil_div(smax, nchunks);
   const dim3 grid(nsamples, nchunks);
   switch (D / 128) {
-#define CASE(NV) case NV: ln_mod_fwd_kernel<NV, OutT><<<grid, 256, 0, st>>>(a, rpc); break;
+#define CASE(NV)                                                                                              \
+  case NV:                                                                                                    \
+    if (!a.x_bf16 && !(a.x_out && a.xout_bf16)) ln_mod_fwd_kernel<NV, OutT, float, float><<<grid, 256, 0, st>>>(a, rpc);            \
+    else if (!a.x_bf16) ln_mod_fwd_kernel<NV, OutT, float, __nv_bfloat16><<<grid, 256, 0, st>>>(a, rpc);                            \
+    else ln_mod_fwd_kernel<NV, OutT, __nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(a, rpc);                                   \
+    break;
     CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8)
 #undef CASE
     default: set_error("ln_mod_fwd: width %d unsupported (need multiple of 128, <= 1024)", D); return UMD_ERR_UNSUPPORTED;
@@ -177,9 +193,10 @@ static int ln_fwd_dispatch(const LnFwdArgs& a, int D, cudaStream_t st) {
 int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
   if (a.rows_out <= 0) return UMD_OK;
   UMD_REQUIRE(D % 128 == 0 && D <= 1024, "ln_mod_fwd: width %d unsupported", D);
-  // algorithmic bytes: fp32 row in, bf16/fp32 row out
+  UMD_REQUIRE(!(a.x_bf16 && a.x_out && !a.xout_bf16), "ln_mod_fwd: a bf16 stream cannot be written back as fp32");
+  // algorithmic bytes: stream row in (+ branch), LayerNorm row out (+ stream row out)
   ProfScope prof(PC_LN_FWD, static_cast<double>(a.rows_out) * D *
-                     (4 + (out_bf16 ? 2 : 4) + (a.res_branch ? 2 : 0) + (a.x_out ? 4 : 0)), st);
+                     ((a.x_bf16 ? 2 : 4) + (out_bf16 ? 2 : 4) + (a.res_branch ? 2 : 0) + (a.x_out ? (a.xout_bf16 ? 2 : 4) : 0)), st);
   return out_bf16 ? ln_fwd_dispatch<__nv_bfloat16>(a, D, st) : ln_fwd_dispatch<float>(a, D, st);
 }
 
@@ -200,7 +217,7 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
 // one row ahead of their use instead of being loaded into registers when the row starts: with 126 registers per
 // thread only eight rows fit into an SM's register file at once, and a warp pair had no loads in flight while it
 // reduced and stored its row; the shared-memory slots keep a second row per warp pair in flight at all times.
-template <int NV, typename DyT, bool GATE, bool STAGED>
+template <int NV, typename DyT, bool GATE, bool STAGED, bool XB>   // XB: the LayerNorm input x is bf16 (residual_bf16)
 __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs a, int rows_per_chunk) {
   constexpr int D = NV * 128;
   constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;  // warps per row
@@ -257,7 +274,8 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
     const uint32_t sb = stage_u + slot * SLOT_BYTES;
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
-      cp_async16(sb + (i * 32 + lane) * 16, a.x + off + 128 * i);
+      if (XB) cp_async8(sb + (i * 32 + lane) * 16, reinterpret_cast<const __nv_bfloat16*>(a.x) + off + 128 * i);
+      else cp_async16(sb + (i * 32 + lane) * 16, reinterpret_cast<const float*>(a.x) + off + 128 * i);
       if (a.accumulate) cp_async16(sb + OFF_PV + (i * 32 + lane) * 16, a.dx + off + 128 * i);
       if (DYB == 8) cp_async8(sb + OFF_DY + (i * 32 + lane) * 8, reinterpret_cast<const DyT*>(a.dy) + off + 128 * i);
       else cp_async16(sb + OFF_DY + (i * 32 + lane) * 16, reinterpret_cast<const DyT*>(a.dy) + off + 128 * i);
@@ -310,7 +328,8 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
       continue;
     }
     float mean, rstd;
-    const float* xp = a.x + static_cast<long long>(xrow) * D;
+    const float* xp = reinterpret_cast<const float*>(a.x) + static_cast<long long>(xrow) * D;
+    const __nv_bfloat16* xpb = reinterpret_cast<const __nv_bfloat16*>(a.x) + static_cast<long long>(xrow) * D;
     const DyT* dyp = reinterpret_cast<const DyT*>(a.dy) + static_cast<long long>(drow) * D;
     const uint32_t sb = stage_u + slot * SLOT_BYTES;
     if (STAGED) {
@@ -355,8 +374,13 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
       const int c = col0 + 128 * i;
       float4 xv, dy;
       if (STAGED) {
-        const uint4 xr = ld_shared_v4(sb + (i * 32 + lane) * 16);
-        xv = make_float4(__uint_as_float(xr.x), __uint_as_float(xr.y), __uint_as_float(xr.z), __uint_as_float(xr.w));
+        if (XB) {
+          const uint2 xr = ld_shared_v2(sb + (i * 32 + lane) * 16);
+          xv = make_float4(bf16_lo(xr.x), bf16_hi(xr.x), bf16_lo(xr.y), bf16_hi(xr.y));
+        } else {
+          const uint4 xr = ld_shared_v4(sb + (i * 32 + lane) * 16);
+          xv = make_float4(__uint_as_float(xr.x), __uint_as_float(xr.y), __uint_as_float(xr.z), __uint_as_float(xr.w));
+        }
         if (DYB == 8) {
           const uint2 dr = ld_shared_v2(sb + OFF_DY + (i * 32 + lane) * 8);
           dy = make_float4(bf16_lo(dr.x), bf16_hi(dr.x), bf16_lo(dr.y), bf16_hi(dr.y));
@@ -365,7 +389,7 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
           dy = make_float4(__uint_as_float(dr.x), __uint_as_float(dr.y), __uint_as_float(dr.z), __uint_as_float(dr.w));
         }
       } else {
-        xv = *reinterpret_cast<const float4*>(xp + c);
+        xv = XB ? load_row4(xpb + c) : load_row4(xp + c);
         dy = load_row4(dyp + c);
       }
       const float4 gs = *reinterpret_cast<const float4*>(&s_gs[c]);
@@ -473,9 +497,9 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
   }
 }
 
-template <int NV, typename DyT, bool GATE, bool STAGED>
-static int ln_bwd_launch_cfg(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cudaStream_t st) {
-  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE, STAGED>;
+template <int NV, typename DyT, bool GATE, bool STAGED, bool XB>
+static int ln_bwd_launch_x(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cudaStream_t st) {
+  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE, STAGED, XB>;
   if (bytes > 48 * 1024) {
     static bool cfg = false;
     if (!cfg) {
@@ -485,6 +509,11 @@ static int ln_bwd_launch_cfg(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, 
   }
   kern<<<grid, 256, bytes, st>>>(a, rpc);
   return UMD_OK;
+}
+template <int NV, typename DyT, bool GATE, bool STAGED>
+static int ln_bwd_launch_cfg(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cudaStream_t st) {
+  return a.x_bf16 ? ln_bwd_launch_x<NV, DyT, GATE, STAGED, true>(a, grid, rpc, bytes, st)
+                  : ln_bwd_launch_x<NV, DyT, GATE, STAGED, false>(a, grid, rpc, bytes, st);
 }
 template <int NV, typename DyT, bool GATE>
 static int ln_bwd_launch(const LnBwdArgs& a, dim3 grid, int rpc, cudaStream_t st) {
@@ -548,7 +577,7 @@ int ln_mod_bwd(const LnBwdArgs& a, int D, int nsamples, bool dy_bf16, cudaStream
   UMD_REQUIRE(!a.g_dgate || a.g_z, "ln_mod_bwd: the gate stage needs the saved branch output to form dgate");
   // algorithmic bytes: dy in, x in, dx read-modify-write (fp32); gate stage: dz out (bf16), z in (bf16)
   const double rows = static_cast<double>(a.rm.split_row) + static_cast<double>(nsamples - a.rm.n0) * a.rm.s1;
-  ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + 4 + (a.accumulate ? 8 : 4) + (a.g_dz ? 2 : 0) + (a.g_dgate ? 2 : 0)), st);
+  ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + (a.x_bf16 ? 2 : 4) + (a.accumulate ? 8 : 4) + (a.g_dz ? 2 : 0) + (a.g_dgate ? 2 : 0)), st);
   return dy_bf16 ? ln_bwd_dispatch<__nv_bfloat16>(a, D, nsamples, st) : ln_bwd_dispatch<float>(a, D, nsamples, st);
 }
 

@@ -30,7 +30,7 @@ typedef __nv_bfloat16 bf16;
 struct LayerBufs {
   bf16* y0; float* mean0; float* rstd0;
   bf16* qkv; bf16* o; float* lse; bf16* a;
-  float* xmid;
+  void* xmid;               // fp32, or bf16 with Stack::rbf
   bf16* y1; float* mean1; float* rstd1;
   bf16* u; bf16* g; bf16* z;
 };
@@ -43,7 +43,8 @@ struct Stack {
   float* ada;               // [depth][B][6D] fp32 or null: adaLN shift0|scale0|gate0|shift1|scale1|gate1 per layer and sample
   float* dada;              // [depth][B][6D] fp32 gradient
   bf16* dada_bf16;
-  std::vector<float*> x;    // depth+1 residual snapshots
+  int rbf;                  // bf16 residual stream (umd_model_cfg.residual_bf16, training only): x[1..depth] and xmid are bf16
+  std::vector<void*> x;     // depth+1 residual snapshots; x[0] (written by the embedding kernels) is always fp32
   std::vector<LayerBufs> L;
   float* xf; float* meanf; float* rstdf;   // final LayerNorm (encoder: fp32 output; decoder: see Plan.xm)
 };
@@ -52,6 +53,7 @@ struct Plan {
   // geometry
   int B, D, H, Dh, M4, L, p, C, NC, tok0, S0, S1, Sd, Te, Td, ncls;
   int adaln, has_label;
+  int rbf;   // umd_model_cfg.residual_bf16
   // conditioning path
   bf16* temb; float* th1; bf16* ta1; float* tc;
   bf16* lemb; float* lh1; bf16* la1; float* yc;
@@ -140,8 +142,10 @@ void carve_stack(Bump& b, Stack& s, const Plan& P, int depth, int rows, int nsam
   s.x.assign(depth + 1, nullptr);
   s.L.assign(depth, LayerBufs());
   const long long RD = static_cast<long long>(rows) * D;
+  s.rbf = (train && P.rbf) ? 1 : 0;
   if (train) {
-    for (int l = 0; l <= depth; ++l) s.x[l] = b.take<float>(RD);
+    s.x[0] = b.take<float>(RD);
+    for (int l = 1; l <= depth; ++l) s.x[l] = s.rbf ? static_cast<void*>(b.take<bf16>(RD)) : static_cast<void*>(b.take<float>(RD));
   } else {
     float* x = b.take<float>(RD);
     for (int l = 0; l <= depth; ++l) s.x[l] = x;  // GATE_RES epilogue is element-wise in place
@@ -153,7 +157,7 @@ void carve_stack(Bump& b, Stack& s, const Plan& P, int depth, int rows, int nsam
       lb.qkv = b.take<bf16>(3 * RD); lb.o = b.take<bf16>(RD);
       lb.lse = b.take<float>(static_cast<long long>(rows) * P.H);
       lb.a = b.take<bf16>(RD);
-      lb.xmid = train ? b.take<float>(RD) : s.x[0];
+      lb.xmid = train ? (s.rbf ? static_cast<void*>(b.take<bf16>(RD)) : static_cast<void*>(b.take<float>(RD))) : s.x[0];
       lb.y1 = b.take<bf16>(RD); lb.mean1 = b.take<float>(rows); lb.rstd1 = b.take<float>(rows);
       lb.u = b.take<bf16>(static_cast<long long>(rows) * P.M4);
       lb.g = b.take<bf16>(static_cast<long long>(rows) * P.M4);
@@ -176,7 +180,7 @@ int make_plan(Plan& P, const umd_model_cfg& c, const umd_step_shape& sh, void* w
   P.NC = c.patch * c.patch * 2 * c.channels;
   UMD_REQUIRE(P.NC % 8 == 0, "patch*patch*2*channels = %d must be a multiple of 8", P.NC);
   UMD_REQUIRE(P.M4 % 64 == 0, "mlp_dim %d must be a multiple of 64", P.M4);
-  P.adaln = c.adaln; P.has_label = c.num_classes > 0; P.ncls = c.num_cls;
+  P.adaln = c.adaln; P.has_label = c.num_classes > 0; P.ncls = c.num_cls; P.rbf = c.residual_bf16 ? 1 : 0;
   P.tok0 = c.adaln ? 0 : 1;
   UMD_REQUIRE(sh.keep0 <= P.L && sh.keep1 <= P.L && (sh.n0 == 0 || sh.keep0 > 0) && (sh.n1 == 0 || sh.keep1 > 0), "bad keep counts");
   UMD_REQUIRE(sh.masked0 || sh.n0 == 0 || sh.keep0 == P.L, "unmasked segment 0 must keep all %d patches", P.L);
@@ -351,9 +355,9 @@ int cond_forward(Ctx& c, const umd_io& io) {
 // ------------------------------------------------------------------------------------------
 // The residual update that closes block l, x[l+1] = xmid[l] + gate1[l] * z[l] (vit.py:106-108), is not run as a
 // pass of its own: the LayerNorm that consumes x[l+1] performs it on the way in and writes x[l+1] to x_out.
-void pending_residual(LnFwdArgs& ln, const Stack& s, int l, float* x_out) {
+void pending_residual(LnFwdArgs& ln, const Stack& s, int l, void* x_out) {
   const LayerBufs& lb = s.L[l];
-  ln.x = lb.xmid;
+  ln.x = lb.xmid; ln.x_bf16 = s.rbf; ln.xout_bf16 = s.rbf;
   ln.res_branch = lb.z;
   ln.res_gate = s.ada ? s.ada + static_cast<long long>(l) * s.nsamples * 6 * s.D + 5 * s.D : nullptr;
   ln.ldgate = 6 * s.D;
@@ -381,7 +385,7 @@ int stack_forward(Ctx& c, Stack& s) {
     } else {
       pending_residual(ln, s, l - 1, s.x[l]);
     }
-    if (!P.adaln) { ln.cond_row = P.cond; ln.x_out = s.x[l]; }
+    if (!P.adaln) { ln.cond_row = P.cond; ln.x_out = s.x[l]; ln.xout_bf16 = (l > 0) ? s.rbf : 0; }
     ln.gamma = c.W(s.base + UMD_S_LN0_S, l * ls);
     ln.beta = c.W(s.base + UMD_S_LN0_B, l * ls);
     ln.shift = ada; ln.scale = ada ? ada + D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
@@ -401,7 +405,8 @@ int stack_forward(Ctx& c, Stack& s) {
     UMD_TRY(dense_fwd(c, lb.o, T, D, c.WB(s.base + UMD_S_O_W, l * ls), D, c.W(s.base + UMD_S_O_B, l * ls), UMD_EPI_BF16, lb.a));
     // LayerNorm_1 (+ modulate) on xmid = x[l] + gate0 * a (vit.py:89-98)
     memset(&ln, 0, sizeof(ln));
-    ln.x = s.x[l]; ln.res_branch = lb.a; ln.res_gate = ada ? ada + 2 * D : nullptr; ln.ldgate = ldada; ln.x_out = lb.xmid;
+    ln.x = s.x[l]; ln.x_bf16 = (l > 0) ? s.rbf : 0;
+    ln.res_branch = lb.a; ln.res_gate = ada ? ada + 2 * D : nullptr; ln.ldgate = ldada; ln.x_out = lb.xmid; ln.xout_bf16 = s.rbf;
     ln.gamma = c.W(s.base + UMD_S_LN1_S, l * ls);
     ln.beta = c.W(s.base + UMD_S_LN1_B, l * ls);
     ln.shift = ada ? ada + 3 * D : nullptr; ln.scale = ada ? ada + 4 * D : nullptr; ln.ldmod = ldada; ln.rm = s.rm;
@@ -456,7 +461,7 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
     UMD_TRY(dense_wgrad(c, lb.y1, T, D, P.dgb, M4, M4, c.G(s.base + UMD_S_FC1_W, lo)));
     LnBwdArgs lnb;
     memset(&lnb, 0, sizeof(lnb));
-    lnb.dy = P.dyb; lnb.x = lb.xmid; lnb.mean = lb.mean1; lnb.rstd = lb.rstd1;
+    lnb.dy = P.dyb; lnb.x = lb.xmid; lnb.x_bf16 = s.rbf; lnb.mean = lb.mean1; lnb.rstd = lb.rstd1;
     lnb.gamma = c.W(s.base + UMD_S_LN1_S, lo); lnb.beta = c.W(s.base + UMD_S_LN1_B, lo);
     lnb.scale = ada ? ada + 4 * D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
     lnb.dshift = dada ? dada + 3 * D : nullptr; lnb.dscale = dada ? dada + 4 * D : nullptr; lnb.ldd = ldada;
@@ -495,7 +500,7 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
       UMD_TRY(gemm_bf16(g, c.st));
     }
     memset(&lnb, 0, sizeof(lnb));
-    lnb.dy = P.dyb; lnb.x = s.x[l]; lnb.mean = lb.mean0; lnb.rstd = lb.rstd0;
+    lnb.dy = P.dyb; lnb.x = s.x[l]; lnb.x_bf16 = (l > 0) ? s.rbf : 0; lnb.mean = lb.mean0; lnb.rstd = lb.rstd0;
     lnb.gamma = c.W(s.base + UMD_S_LN0_S, lo); lnb.beta = c.W(s.base + UMD_S_LN0_B, lo);
     lnb.scale = ada ? ada + D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
     lnb.dshift = dada ? dada : nullptr; lnb.dscale = dada ? dada + D : nullptr; lnb.ldd = ldada;
@@ -532,7 +537,7 @@ EmbedArgs embed_args(const Ctx& c, const umd_io& io) {
   const Plan& P = c.P;
   EmbedArgs e;
   e.image = io.image; e.ids_keep = io.ids_shuffle; e.W = c.W(UMD_P_EMBED_W); e.bias = c.W(UMD_P_EMBED_B);
-  e.pos = c.W(UMD_P_POS); e.cls = c.W(UMD_P_CLS); e.x = P.enc.x[0]; e.rm = P.enc.rm; e.n1 = c.sh->n1;
+  e.pos = c.W(UMD_P_POS); e.cls = c.W(UMD_P_CLS); e.x = static_cast<float*>(P.enc.x[0]); e.rm = P.enc.rm; e.n1 = c.sh->n1;
   e.keep0 = c.sh->keep0; e.keep1 = c.sh->keep1; e.masked0 = c.sh->masked0; e.masked1 = c.sh->masked1;
   e.img = c.cfg->img_size; e.patch = P.p; e.C = P.C; e.D = P.D; e.L = P.L; e.num_cls = P.ncls; e.tok0 = P.tok0;
   return e;
@@ -541,7 +546,7 @@ DecInArgs decin_args(const Ctx& c, const umd_io& io) {
   const Plan& P = c.P;
   DecInArgs d;
   d.enc = P.enc.xf; d.ids_restore = io.ids_restore; d.ids_keep = io.ids_shuffle; d.mask_token = c.W(UMD_P_MASK_TOKEN);
-  d.dec_pos = c.W(UMD_P_DEC_POS); d.xd = P.dec.x[0]; d.rep = io.pre_logits; d.rm_enc = P.enc.rm;
+  d.dec_pos = c.W(UMD_P_DEC_POS); d.xd = static_cast<float*>(P.dec.x[0]); d.rep = io.pre_logits; d.rm_enc = P.enc.rm;
   d.keep0 = c.sh->keep0; d.keep1 = c.sh->keep1; d.masked0 = c.sh->masked0; d.masked1 = c.sh->masked1;
   d.D = P.D; d.L = P.L; d.num_cls = P.ncls; d.tok0 = P.tok0; d.S_d = P.Sd;
   return d;
@@ -657,7 +662,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
   {  // decoder encoder_norm + final modulation backward
     LnBwdArgs lnb;
     memset(&lnb, 0, sizeof(lnb));
-    lnb.dy = P.dyb; lnb.x = P.dec.x[P.dec.depth]; lnb.mean = P.meanF; lnb.rstd = P.rstdF;
+    lnb.dy = P.dyb; lnb.x = P.dec.x[P.dec.depth]; lnb.x_bf16 = P.dec.rbf; lnb.mean = P.meanF; lnb.rstd = P.rstdF;
     lnb.gamma = c.W(UMD_P_DEC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_DEC_BASE + UMD_S_NORM_B);
     lnb.scale = P.fmod ? P.fmod + D : nullptr; lnb.ldmod = 2 * D; lnb.rm = P.dec.rm; lnb.dx = P.dx_dec; lnb.accumulate = 0;
     lnb.dshift = P.dfmod; lnb.dscale = P.dfmod ? P.dfmod + D : nullptr; lnb.ldd = 2 * D;
@@ -680,7 +685,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
   {  // encoder_norm backward
     LnBwdArgs lnb;
     memset(&lnb, 0, sizeof(lnb));
-    lnb.dy = P.dxf_enc; lnb.x = P.enc.x[P.enc.depth]; lnb.mean = P.enc.meanf; lnb.rstd = P.enc.rstdf;
+    lnb.dy = P.dxf_enc; lnb.x = P.enc.x[P.enc.depth]; lnb.x_bf16 = P.enc.rbf; lnb.mean = P.enc.meanf; lnb.rstd = P.enc.rstdf;
     lnb.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
     lnb.rm = P.enc.rm; lnb.dx = P.dx_enc; lnb.accumulate = 0;
     lnb.dgamma = c.G(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_ENC_BASE + UMD_S_NORM_B);

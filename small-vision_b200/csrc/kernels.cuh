@@ -9,7 +9,9 @@ int gemm_bf16(const umd_gemm_args& a, cudaStream_t stream);
 
 // ---- LayerNorm + modulate (elementwise.cu) --------------------------------------------
 struct LnFwdArgs {
-  const float* x;          // [rows_in, D] fp32 residual stream
+  const void* x;           // [rows_in, D] residual stream: fp32, or bf16 when x_bf16 (umd_model_cfg.residual_bf16)
+  int x_bf16;
+  int xout_bf16;           // dtype of x_out
   const float* gamma;      // [D]
   const float* beta;       // [D]
   const float* shift;      // per-sample rows (stride ldmod) or null
@@ -27,7 +29,7 @@ struct LnFwdArgs {
   const __nv_bfloat16* res_branch;  // [rows_in, D] or null
   const float* res_gate;            // per-sample rows (stride ldgate) or null
   long long ldgate;
-  float* x_out;                     // [rows_in, D] or null
+  void* x_out;                      // [rows_in, D] (fp32 / bf16, see xout_bf16) or null
   // adaln=False (vit.py:73-74): token 0 of every sample is replaced by cond_row[sample] before the norm
   const float* cond_row;            // [nsamples, D] or null
 };
@@ -35,7 +37,8 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st);
 
 struct LnBwdArgs {
   const void* dy;          // [rows_out, D] bf16 or fp32 (gradient of the LN(+mod) output)
-  const float* x;          // fp32 LN input
+  const void* x;           // LN input: fp32, or bf16 when x_bf16
+  int x_bf16;
   const float* mean;
   const float* rstd;
   const float* gamma;

@@ -101,7 +101,7 @@ def gemm(A, B, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, batch=1, 
 
 class ModelCfg(C.Structure):
   _fields_ = [(k, C.c_int) for k in ("img_size", "patch", "channels", "width", "depth", "dec_depth", "heads", "mlp_dim",
-                                      "num_cls", "num_classes", "adaln", "flip_final_conv")]
+                                      "num_cls", "num_classes", "adaln", "flip_final_conv", "residual_bf16")]
 
 
 class StepShape(C.Structure):
@@ -157,6 +157,7 @@ def model_cfg_struct(cfg):
   m.num_classes = cfg.num_classes or 0
   m.adaln = int(cfg.adaln)
   m.flip_final_conv = int(cfg.flip_final_conv)
+  m.residual_bf16 = int(cfg.residual_dtype == "bfloat16")
   return m
 
 

@@ -30,6 +30,24 @@ def test_full_depth_umd_b4_step_matches_cpu_oracle():
   print("umd_b4 full depth:", rep)
 
 
+def test_full_depth_umd_b4_step_bf16_residual_stream_matches_cpu_oracle():
+  """residual_dtype="bfloat16": the stream of the reference's dtype_mm="bfloat16" flow against the fp32 oracle, same
+  App. G tolerances (which were written for a bf16 residual stream)."""
+  rep = U.run_step_parity(variant="B/4", batch=8, adaln=True, steps=1, seed=3, residual_dtype="bfloat16")
+  print("umd_b4 full depth, bf16 residual stream:", rep)
+
+
+def test_full_depth_mae_b4_step_bf16_residual_stream_matches_cpu_oracle():
+  rep = U.run_step_parity(variant="B/4", batch=8, adaln=False, steps=1, seed=4, residual_dtype="bfloat16")
+  print("mae_b4 full depth, bf16 residual stream:", rep)
+
+
+def test_full_depth_latent_umd_l2_step_bf16_residual_stream_matches_cpu_oracle():
+  rep = U.run_step_parity(variant="L/2", batch=4, adaln=True, steps=1, seed=6, img_size=32, channels=4,
+                          beta_schedule="linear", residual_dtype="bfloat16")
+  print("latent_umd_l2 full depth, bf16 residual stream:", rep)
+
+
 def test_full_depth_mae_b4_step_matches_cpu_oracle():
   rep = U.run_step_parity(variant="B/4", batch=8, adaln=False, steps=1, seed=4)
   print("mae_b4 full depth:", rep)
@@ -50,7 +68,7 @@ def test_full_depth_latent_umd_l2_step_matches_cpu_oracle():
 # ---------------------------------------------------------------------------------------------------------------
 # bench shapes, GPU fp32 secondary oracle
 # ---------------------------------------------------------------------------------------------------------------
-def bench_state_and_batch(workload, per_gpu=None, device=DEV):
+def bench_state_and_batch(workload, per_gpu=None, device=DEV, residual_dtype="float32"):
   """Exactly what bench.py builds on rank 0 for `workload`: model, state (seed 0, non-zero adaLN), update_fn and the
   first synthetic batch (generator seed 1 + rank)."""
   import bench
@@ -59,7 +77,7 @@ def bench_state_and_batch(workload, per_gpu=None, device=DEV):
   from small_vision_b200.train import create_train_state, make_update_fn
   mkw, tkw, n = bench.WORKLOADS[workload]
   n = per_gpu or n
-  model = Model(**mkw)
+  model = Model(**mkw, residual_dtype=residual_dtype)
   tcfg = TrainConfig(batch_size=n, **tkw)
   state = create_train_state(model, tcfg, seed=0, device=device, nonzero_adaln=True)
   state["opt"]["count"] = 10
@@ -111,10 +129,10 @@ def gpu_fp32_oracle_loss_and_grads(params_tree, ocfg, tkw, gd, batch, rand, n_ch
     torch.set_float32_matmul_precision(old[2])
 
 
-def bench_shape_parity(workload, n_chunks, per_gpu=None):
+def bench_shape_parity(workload, n_chunks, per_gpu=None, residual_dtype="float32"):
   from small_vision_b200.diffusion import create_gaussian_diffusion
   from small_vision_b200.params import tree_from_arena
-  model, mkw, tkw, state, fn, batch = bench_state_and_batch(workload, per_gpu)
+  model, mkw, tkw, state, fn, batch = bench_state_and_batch(workload, per_gpu, residual_dtype=residual_dtype)
   B = batch["image"].shape[0]
   rand = fn.draw_step_randoms(state, B, torch.device(DEV), rank=0)
   gb = dict(batch)
@@ -140,6 +158,10 @@ def bench_shape_parity(workload, n_chunks, per_gpu=None):
 
 def test_bench_shape_umd_b4_matches_gpu_fp32_oracle():
   bench_shape_parity("umd_b4", n_chunks=8)
+
+
+def test_bench_shape_umd_b4_bf16_residual_stream_matches_gpu_fp32_oracle():
+  bench_shape_parity("umd_b4", n_chunks=8, residual_dtype="bfloat16")
 
 
 def test_bench_shape_mae_b4_matches_gpu_fp32_oracle():
@@ -174,12 +196,13 @@ def test_bench_first_loss_golden_is_current():
 # ---------------------------------------------------------------------------------------------------------------
 # N-step trajectory (App. G: "after N optimiser steps on fixed data loss curves overlap within 2 %")
 # ---------------------------------------------------------------------------------------------------------------
-def test_trajectory_20_steps_umd_s4_matches_cpu_oracle():
+@pytest.mark.parametrize("residual_dtype", ["float32", "bfloat16"])
+def test_trajectory_20_steps_umd_s4_matches_cpu_oracle(residual_dtype):
   from small_vision_b200.config import TrainConfig
   from small_vision_b200.diffusion import create_gaussian_diffusion
   from small_vision_b200.train import create_train_state, make_update_fn
   steps, B = 20, 8
-  model, ocfg = U.make_models("S/4", adaln=True)
+  model, ocfg = U.make_models("S/4", adaln=True, residual_dtype=residual_dtype)
   # a rate at which 20 steps visibly move the loss, warm-up included (lr(0) = 0 is the optax convention)
   tcfg = TrainConfig(batch_size=B, total_steps=200, warmup_steps=4, peak_lr=1e-3 * 256 / B)
   params = U.perturb_init(model, 11, DEV)
