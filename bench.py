@@ -300,8 +300,10 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-dp-check", action="store_true")
-  ap.add_argument("--residual", default="float32", choices=["float32", "bfloat16"],
-                  help="dtype of the residual stream between the blocks (bfloat16 = the reference's dtype_mm='bfloat16' flow)")
+  ap.add_argument("--residual", default="bfloat16", choices=["float32", "bfloat16"],
+                  help="dtype of the residual stream between the blocks.  bfloat16 (default) is the stream of the reference's "
+                       "dtype_mm='bfloat16' flow, i.e. of the 'bf16 pre-training' configuration BASELINE.json names; float32 is "
+                       "the stream of its default dtype_mm.  Both pass the same parity tests (tests/test_fullsize_gpu.py)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 1)
   if args.impl == "reference":

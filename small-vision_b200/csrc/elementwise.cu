@@ -528,12 +528,13 @@ static int ln_bwd_launch(const LnBwdArgs& a, dim3 grid, int rpc, cudaStream_t st
     staged_on = e ? atoi(e) : 1;
   }
   // the staged variant needs every row of the grid to be a LayerNorm row (no gather window); it is sized for two CTAs
-  // per SM (<= 110 KB).  Width 1024 (Latent-UMD-L/2) needs 130 KB: UMD_LN_BWD_STAGED_BIG=1 runs it staged with one CTA
-  // per SM instead of unstaged with two (A/B switch; default from the measurement in profiles/r02_notes.md)
+  // per SM (<= 110 KB).  Width 1024 (Latent-UMD-L/2) needs 130 KB: it runs staged with one CTA per SM, which measured
+  // 6.31 ms against 6.93 ms per step for the unstaged variant with two (profiles/r02_notes.md; UMD_LN_BWD_STAGED_BIG=0
+  // switches back)
   static int staged_big = -1;
   if (staged_big < 0) {
     const char* e = getenv("UMD_LN_BWD_STAGED_BIG");
-    staged_big = e ? atoi(e) : 0;
+    staged_big = e ? atoi(e) : 1;
   }
   const int limit = staged_big ? 200 * 1024 : 110 * 1024;
   if (staged_on && a.gather_L <= 0 && BYTES + STAGE_BYTES <= limit)
