@@ -300,7 +300,7 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-dp-check", action="store_true")
-  ap.add_argument("--residual", default="bfloat16", choices=["float32", "bfloat16"],
+  ap.add_argument("--residual", default="bfloat16", choices=["float32", "bfloat16", "bfloat16+grad"],
                   help="dtype of the residual stream between the blocks.  bfloat16 (default) is the stream of the reference's "
                        "dtype_mm='bfloat16' flow, i.e. of the 'bf16 pre-training' configuration BASELINE.json names; float32 is "
                        "the stream of its default dtype_mm.  Both pass the same parity tests (tests/test_fullsize_gpu.py)")
@@ -346,7 +346,8 @@ def main():
   mkw, tkw, per_gpu = WORKLOADS[args.workload]
   if args.per_gpu_batch:
     per_gpu = args.per_gpu_batch
-  model = Model(**mkw, residual_dtype=args.residual)
+  model = Model(**mkw, residual_dtype=args.residual.split("+")[0],
+                grad_stream_dtype="bfloat16" if args.residual.endswith("+grad") else "float32")
   cfg = model.cfg
   B_global = per_gpu * world
   tcfg = TrainConfig(batch_size=B_global, **tkw)
@@ -519,7 +520,7 @@ def main():
                                f"({per_gpu - int(per_gpu * tkw['no_noise_prob'])} noised + {int(per_gpu * tkw['no_noise_prob'])} clean)",
                    "global_batch": B_global, "per_gpu_batch": per_gpu, "parallelism": f"dp{world}",
                    "params": model.layout.num_params, "l2": "inputs rotate over 4 batches; each step writes > 10 GB of activations (>> 126 MB L2)",
-                   "precision": "bf16 GEMM/attention operands, fp32 accumulate, %s residual stream, fp32 LayerNorm statistics / gradient stream / loss / AdamW (bf16 mu)" % ("bf16" if args.residual == "bfloat16" else "fp32")},
+                   "precision": "bf16 GEMM/attention operands, fp32 accumulate, %s residual stream, fp32 LayerNorm statistics / gradient stream / loss / AdamW (bf16 mu)" % {"float32": "fp32", "bfloat16": "bf16", "bfloat16+grad": "bf16 (forward and gradient)"}[args.residual]},
         "step_tflops_per_gpu": fl_img * value / world / 1e12,
         "step_frac_of_bf16_peak": fl_img * value / world / 1e12 / peaks["tf_sustained"],
         "flops_per_image": fl_img, "final_loss": final_loss, "loss_check": loss_check, "dp_check": dp,

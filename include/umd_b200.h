@@ -190,7 +190,8 @@ typedef struct umd_model_cfg {
   int flip_final_conv;  /* 1 = flax ConvTranspose(transpose_kernel=False) orientation */
   int residual_bf16;    /* training only: 1 = the residual stream between the blocks (and its per-layer snapshots for the
                            backward) is bf16, as in the reference's dtype_mm="bfloat16" flow (ae.py:51,100; vit.py:89-94);
-                           LayerNorm statistics, the gradient stream, loss and optimiser stay fp32.  0 = fp32 stream. */
+                           2 = so is the gradient of the residual stream between the blocks (JAX cotangents take the dtype
+                           of their primals).  LayerNorm statistics, loss and optimiser stay fp32.  0 = fp32 streams. */
 } umd_model_cfg;
 
 /* Leaves of the parameter tree.  offsets[] (UMD_OFFSETS_LEN entries) are element offsets into the

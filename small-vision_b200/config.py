@@ -55,6 +55,9 @@ class ModelConfig:
   # the stream of the reference's default dtype_mm="float32"; "bfloat16" is the stream of its dtype_mm="bfloat16" flow
   # (ae.py:51,100: Dense / Conv outputs and x + y are bf16, LayerNorm statistics fp32)
   residual_dtype: str = "float32"
+  # ... and of the gradient of that stream in the backward pass ("bfloat16" needs residual_dtype="bfloat16": JAX cotangents
+  # take the dtype of their primals, so this is the backward of the same dtype_mm="bfloat16" flow)
+  grad_stream_dtype: str = "float32"
 
   @property
   def patch(self) -> int:
@@ -84,6 +87,8 @@ def make_model_config(*, variant=None, **kw) -> ModelConfig:
     merged["patch_size"] = tuple(int(x) for x in merged["patch_size"])
   if "no_decay_list" in merged:
     merged["no_decay_list"] = tuple(merged["no_decay_list"])
+  if merged.get("grad_stream_dtype", "float32") == "bfloat16" and merged.get("residual_dtype", "float32") != "bfloat16":
+    raise ValueError("grad_stream_dtype='bfloat16' requires residual_dtype='bfloat16'")
   if merged.get("dropout", 0.0) != 0.0:
     raise NotImplementedError("dropout > 0 is not used by any reference recipe (ae.py:48) and is not implemented")
   return ModelConfig(**merged)

@@ -217,8 +217,11 @@ int ln_mod_fwd(const LnFwdArgs& a, int D, bool out_bf16, cudaStream_t st) {
 // one row ahead of their use instead of being loaded into registers when the row starts: with 126 registers per
 // thread only eight rows fit into an SM's register file at once, and a warp pair had no loads in flight while it
 // reduced and stored its row; the shared-memory slots keep a second row per warp pair in flight at all times.
-template <int NV, typename DyT, bool GATE, bool STAGED, bool XB>   // XB: the LayerNorm input x is bf16 (residual_bf16)
+// MODE bits: 1 = the LayerNorm input x is bf16 (residual_bf16 >= 1); 2 = the running gradient dx_in is bf16, 4 = the
+// gradient written to dx is bf16 (residual_bf16 == 2: the gradient stream of the reference's bf16 flow)
+template <int NV, typename DyT, bool GATE, bool STAGED, int MODE>
 __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs a, int rows_per_chunk) {
+  constexpr bool XB = (MODE & 1) != 0, DIB = (MODE & 2) != 0, DOB = (MODE & 4) != 0;
   constexpr int D = NV * 128;
   constexpr int W = (NV % 2 == 0 && NV >= 4) ? 2 : 1;  // warps per row
   constexpr int NL = NV / W;                            // float4 columns per lane
@@ -276,7 +279,10 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
     for (int i = 0; i < NL; ++i) {
       if (XB) cp_async8(sb + (i * 32 + lane) * 16, reinterpret_cast<const __nv_bfloat16*>(a.x) + off + 128 * i);
       else cp_async16(sb + (i * 32 + lane) * 16, reinterpret_cast<const float*>(a.x) + off + 128 * i);
-      if (a.accumulate) cp_async16(sb + OFF_PV + (i * 32 + lane) * 16, a.dx + off + 128 * i);
+      if (a.accumulate) {
+        if (DIB) cp_async8(sb + OFF_PV + (i * 32 + lane) * 16, reinterpret_cast<const __nv_bfloat16*>(a.dx_in) + off + 128 * i);
+        else cp_async16(sb + OFF_PV + (i * 32 + lane) * 16, reinterpret_cast<const float*>(a.dx_in) + off + 128 * i);
+      }
       if (DYB == 8) cp_async8(sb + OFF_DY + (i * 32 + lane) * 8, reinterpret_cast<const DyT*>(a.dy) + off + 128 * i);
       else cp_async16(sb + OFF_DY + (i * 32 + lane) * 16, reinterpret_cast<const DyT*>(a.dy) + off + 128 * i);
       if (want_z_s) cp_async8(sb + OFF_Z + (i * 32 + lane) * 8, a.g_z + off + 128 * i);
@@ -293,7 +299,15 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
   }
   for (int tok = tok_begin + rp; tok < tok_end; tok += RP, slot ^= 1) {
     const int xrow = row_of(a.rm, n, tok);
-    float* dxp = a.dx + static_cast<long long>(xrow) * D;
+    const long long xoff = static_cast<long long>(xrow) * D;
+    auto load_dx = [&](int c) {
+      return DIB ? load_row4(reinterpret_cast<const __nv_bfloat16*>(a.dx_in) + xoff + c)
+                 : load_row4(reinterpret_cast<const float*>(a.dx_in) + xoff + c);
+    };
+    auto store_dx = [&](int c, const float4& o) {
+      if (DOB) store_row4(reinterpret_cast<__nv_bfloat16*>(a.dx) + xoff + c, o.x, o.y, o.z, o.w);
+      else store_row4(reinterpret_cast<float*>(a.dx) + xoff + c, o.x, o.y, o.z, o.w);
+    };
     int drow = xrow;
     bool skip = false;
     if (a.gather_L > 0) {
@@ -307,8 +321,8 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
       for (int i = 0; i < NL; ++i) {
         const int c = col0 + 128 * i;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.accumulate) o = *reinterpret_cast<const float4*>(dxp + c);
-        else *reinterpret_cast<float4*>(dxp + c) = o;
+        if (a.accumulate) o = load_dx(c);
+        if (!a.accumulate || a.dx_in != a.dx) store_dx(c, o);
         if (GATE) {
           const float4 g = *reinterpret_cast<const float4*>(&s_gate[c]);
           store_row4(a.g_dz + static_cast<long long>(xrow) * D + c, g.x * o.x, g.y * o.y, g.z * o.z, g.w * o.w);
@@ -361,11 +375,16 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
     for (int i = 0; i < NL; ++i) {
       const int c = col0 + 128 * i;
       if (STAGED) {
-        const uint4 pr = a.accumulate ? ld_shared_v4(sb + OFF_PV + (i * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
-        pv[i] = make_float4(__uint_as_float(pr.x), __uint_as_float(pr.y), __uint_as_float(pr.z), __uint_as_float(pr.w));
+        if (DIB) {
+          const uint2 pr = a.accumulate ? ld_shared_v2(sb + OFF_PV + (i * 32 + lane) * 16) : make_uint2(0u, 0u);
+          pv[i] = make_float4(bf16_lo(pr.x), bf16_hi(pr.x), bf16_lo(pr.y), bf16_hi(pr.y));
+        } else {
+          const uint4 pr = a.accumulate ? ld_shared_v4(sb + OFF_PV + (i * 32 + lane) * 16) : make_uint4(0u, 0u, 0u, 0u);
+          pv[i] = make_float4(__uint_as_float(pr.x), __uint_as_float(pr.y), __uint_as_float(pr.z), __uint_as_float(pr.w));
+        }
         zraw[i] = want_z ? ld_shared_v2(sb + OFF_Z + (i * 32 + lane) * 8) : make_uint2(0u, 0u);
       } else {
-        pv[i] = a.accumulate ? *reinterpret_cast<const float4*>(dxp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[i] = a.accumulate ? load_dx(c) : make_float4(0.f, 0.f, 0.f, 0.f);
         zraw[i] = want_z ? *reinterpret_cast<const uint2*>(a.g_z + static_cast<long long>(xrow) * D + c) : make_uint2(0u, 0u);
       }
     }
@@ -428,7 +447,7 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
         *dc = t;
         o = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      *reinterpret_cast<float4*>(dxp + c) = o;
+      store_dx(c, o);
       if (GATE) {
         const float4 g = *reinterpret_cast<const float4*>(&s_gate[c]);
         store_row4(a.g_dz + static_cast<long long>(xrow) * D + c, g.x * o.x, g.y * o.y, g.z * o.z, g.w * o.w);
@@ -497,9 +516,9 @@ __global__ void __launch_bounds__(256, LN_BWD_CTAS) ln_mod_bwd_kernel(LnBwdArgs 
   }
 }
 
-template <int NV, typename DyT, bool GATE, bool STAGED, bool XB>
+template <int NV, typename DyT, bool GATE, bool STAGED, int MODE>
 static int ln_bwd_launch_x(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cudaStream_t st) {
-  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE, STAGED, XB>;
+  auto kern = ln_mod_bwd_kernel<NV, DyT, GATE, STAGED, MODE>;
   if (bytes > 48 * 1024) {
     static bool cfg = false;
     if (!cfg) {
@@ -512,8 +531,20 @@ static int ln_bwd_launch_x(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cu
 }
 template <int NV, typename DyT, bool GATE, bool STAGED>
 static int ln_bwd_launch_cfg(const LnBwdArgs& a, dim3 grid, int rpc, int bytes, cudaStream_t st) {
-  return a.x_bf16 ? ln_bwd_launch_x<NV, DyT, GATE, STAGED, true>(a, grid, rpc, bytes, st)
-                  : ln_bwd_launch_x<NV, DyT, GATE, STAGED, false>(a, grid, rpc, bytes, st);
+  const int mode = (a.x_bf16 ? 1 : 0) | ((a.accumulate && a.dxin_bf16) ? 2 : 0) | (a.dxout_bf16 ? 4 : 0);
+  if (mode == 0) return ln_bwd_launch_x<NV, DyT, GATE, STAGED, 0>(a, grid, rpc, bytes, st);
+  // the reduced-precision streams exist for the widths of the reference's variants (S 384, B 768, L 1024)
+  if constexpr (NV == 3 || NV == 6 || NV == 8) {
+    switch (mode) {
+      case 1: return ln_bwd_launch_x<NV, DyT, GATE, STAGED, 1>(a, grid, rpc, bytes, st);   // x bf16
+      case 2: return ln_bwd_launch_x<NV, DyT, GATE, STAGED, 2>(a, grid, rpc, bytes, st);   // layer 0: x fp32, dx bf16 -> fp32
+      case 5: return ln_bwd_launch_x<NV, DyT, GATE, STAGED, 5>(a, grid, rpc, bytes, st);   // first of a stack: dx out bf16
+      case 7: return ln_bwd_launch_x<NV, DyT, GATE, STAGED, 7>(a, grid, rpc, bytes, st);   // x, dx in, dx out bf16
+      default: break;
+    }
+  }
+  set_error("ln_mod_bwd: stream dtype combination %d is not instantiated for width %d", mode, NV * 128);
+  return UMD_ERR_UNSUPPORTED;
 }
 template <int NV, typename DyT, bool GATE>
 static int ln_bwd_launch(const LnBwdArgs& a, dim3 grid, int rpc, cudaStream_t st) {
@@ -578,7 +609,8 @@ int ln_mod_bwd(const LnBwdArgs& a, int D, int nsamples, bool dy_bf16, cudaStream
   UMD_REQUIRE(!a.g_dgate || a.g_z, "ln_mod_bwd: the gate stage needs the saved branch output to form dgate");
   // algorithmic bytes: dy in, x in, dx read-modify-write (fp32); gate stage: dz out (bf16), z in (bf16)
   const double rows = static_cast<double>(a.rm.split_row) + static_cast<double>(nsamples - a.rm.n0) * a.rm.s1;
-  ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + (a.x_bf16 ? 2 : 4) + (a.accumulate ? 8 : 4) + (a.g_dz ? 2 : 0) + (a.g_dgate ? 2 : 0)), st);
+  ProfScope prof(PC_LN_BWD, rows * D * ((dy_bf16 ? 2 : 4) + (a.x_bf16 ? 2 : 4) + (a.accumulate ? (a.dxin_bf16 ? 2 : 4) : 0) +
+                                        (a.dxout_bf16 ? 2 : 4) + (a.g_dz ? 2 : 0) + (a.g_dgate ? 2 : 0)), st);
   return dy_bf16 ? ln_bwd_dispatch<__nv_bfloat16>(a, D, nsamples, st) : ln_bwd_dispatch<float>(a, D, nsamples, st);
 }
 

@@ -65,6 +65,7 @@ struct Plan {
   bf16* Wf_mat; float* biasm; float* predp; bf16* dpredp; float* loss_partials; int n_loss_partials;
   // backward scratch
   float* dx_dec; float* dx_enc; float* dxf_enc;
+  bf16* dxb_dec; bf16* dxb_enc;   // running gradient streams in bf16 (residual_bf16 == 2), else null
   bf16* dzb; bf16* dgb; bf16* dyb; bf16* dqkv; float* delta;
   float* dcond; bf16* ds; bf16* dta1; bf16* dth1; bf16* dla1; bf16* dlh1; float* dlemb;
   float* dWf_mat; float* dbiasm;
@@ -219,6 +220,8 @@ int make_plan(Plan& P, const umd_model_cfg& c, const umd_step_shape& sh, void* w
     const long long Tmax = P.Te > P.Td ? P.Te : P.Td;
     P.dx_dec = b.take<float>(static_cast<long long>(P.Td) * D);
     P.dx_enc = b.take<float>(static_cast<long long>(P.Te) * D);
+    P.dxb_dec = P.rbf >= 2 ? b.take<bf16>(static_cast<long long>(P.Td) * D) : nullptr;
+    P.dxb_enc = P.rbf >= 2 ? b.take<bf16>(static_cast<long long>(P.Te) * D) : nullptr;
     P.dxf_enc = b.take<float>(static_cast<long long>(P.Te) * D);
     P.dzb = b.take<bf16>(Tmax * D); P.dgb = b.take<bf16>(Tmax * P.M4); P.dyb = b.take<bf16>(Tmax * D);
     P.dqkv = b.take<bf16>(Tmax * 3 * D);
@@ -439,7 +442,18 @@ void gate_stage_mlp(const Ctx& c, const Stack& s, int l, LnBwdArgs& lnb) {
 // last block's MLP branch (gate_stage_mlp fused into the caller's LayerNorm backward); on exit dx holds d x[0].
 // Every parameter gradient of layer l (the adaLN projection included) is final once layer l's kernels have been
 // enqueued; then cb(cb_user, ev0 + depth-1-l) tells the host that the layer's arena block may be all-reduced.
-int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user, int ev0) {
+// dxb != null: the running gradient stream is bf16 in dxb; the last LayerNorm backward of the stack (layer 0) reads it and
+// writes the stack's input gradient to dx in fp32 (its consumers, the embedding / decoder-input backward, read fp32).
+int stack_backward(Ctx& c, Stack& s, float* dx, bf16* dxb, umd_bucket_cb cb, void* cb_user, int ev0) {
+  auto set_dx = [&](LnBwdArgs& lnb, bool last) {
+    if (dxb) {
+      lnb.dx_in = dxb; lnb.dxin_bf16 = 1;
+      if (last) { lnb.dx = dx; lnb.dxout_bf16 = 0; } else { lnb.dx = dxb; lnb.dxout_bf16 = 1; }
+    } else {
+      lnb.dx = dx; lnb.dx_in = dx; lnb.dxin_bf16 = 0; lnb.dxout_bf16 = 0;
+    }
+    lnb.accumulate = 1;
+  };
   Plan& P = c.P;
   const int D = P.D, T = s.rows, M4 = P.M4, B = P.B;
   const long long ldada = 6 * D, ada_ls = static_cast<long long>(B) * 6 * D, ls = s.lstride;
@@ -463,7 +477,7 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
     memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dyb; lnb.x = lb.xmid; lnb.x_bf16 = s.rbf; lnb.mean = lb.mean1; lnb.rstd = lb.rstd1;
     lnb.gamma = c.W(s.base + UMD_S_LN1_S, lo); lnb.beta = c.W(s.base + UMD_S_LN1_B, lo);
-    lnb.scale = ada ? ada + 4 * D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
+    lnb.scale = ada ? ada + 4 * D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; set_dx(lnb, false);
     lnb.dshift = dada ? dada + 3 * D : nullptr; lnb.dscale = dada ? dada + 4 * D : nullptr; lnb.ldd = ldada;
     lnb.dgamma = c.G(s.base + UMD_S_LN1_S, lo); lnb.dbeta = c.G(s.base + UMD_S_LN1_B, lo);
     // ... followed in the same pass by the gate backward of the attention branch (App. E step 6)
@@ -502,7 +516,7 @@ int stack_backward(Ctx& c, Stack& s, float* dx, umd_bucket_cb cb, void* cb_user,
     memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dyb; lnb.x = s.x[l]; lnb.x_bf16 = (l > 0) ? s.rbf : 0; lnb.mean = lb.mean0; lnb.rstd = lb.rstd0;
     lnb.gamma = c.W(s.base + UMD_S_LN0_S, lo); lnb.beta = c.W(s.base + UMD_S_LN0_B, lo);
-    lnb.scale = ada ? ada + D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; lnb.dx = dx; lnb.accumulate = 1;
+    lnb.scale = ada ? ada + D : nullptr; lnb.ldmod = ldada; lnb.rm = s.rm; set_dx(lnb, l == 0);
     lnb.dshift = dada ? dada : nullptr; lnb.dscale = dada ? dada + D : nullptr; lnb.ldd = ldada;
     lnb.dgamma = c.G(s.base + UMD_S_LN0_S, lo); lnb.dbeta = c.G(s.base + UMD_S_LN0_B, lo);
     if (!P.adaln) lnb.dcond = P.dcond;            // token-0 row: gradient of the conditioning token (vit.py:73-74)
@@ -664,7 +678,9 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dyb; lnb.x = P.dec.x[P.dec.depth]; lnb.x_bf16 = P.dec.rbf; lnb.mean = P.meanF; lnb.rstd = P.rstdF;
     lnb.gamma = c.W(UMD_P_DEC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_DEC_BASE + UMD_S_NORM_B);
-    lnb.scale = P.fmod ? P.fmod + D : nullptr; lnb.ldmod = 2 * D; lnb.rm = P.dec.rm; lnb.dx = P.dx_dec; lnb.accumulate = 0;
+    lnb.scale = P.fmod ? P.fmod + D : nullptr; lnb.ldmod = 2 * D; lnb.rm = P.dec.rm; lnb.accumulate = 0;
+    if (P.dxb_dec) { lnb.dx = P.dxb_dec; lnb.dxout_bf16 = 1; } else { lnb.dx = P.dx_dec; }
+    lnb.dx_in = lnb.dx;
     lnb.dshift = P.dfmod; lnb.dscale = P.dfmod ? P.dfmod + D : nullptr; lnb.ldd = 2 * D;
     lnb.dgamma = c.G(UMD_P_DEC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_DEC_BASE + UMD_S_NORM_B);
     lnb.gather_L = P.L; lnb.gather_off = P.tok0 + 1;
@@ -679,7 +695,7 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     g.lda = 2 * D; g.ldb = 2 * D; g.epi = UMD_EPI_ATOMIC; g.out0 = P.dcond; g.ld0 = D;
     UMD_TRY(gemm_bf16(g, st));
   }
-  UMD_TRY(stack_backward(c, P.dec, P.dx_dec, nullptr, nullptr, 0));
+  UMD_TRY(stack_backward(c, P.dec, P.dx_dec, P.dxb_dec, nullptr, nullptr, 0));
   UMD_TRY(decoder_input_bwd(decin_args(c, *io), B, P.Te, P.dx_dec, P.dxf_enc, c.G(UMD_P_DEC_POS), c.G(UMD_P_MASK_TOKEN), st));
   if (cb) cb(cb_user, 0);
   {  // encoder_norm backward
@@ -687,12 +703,14 @@ int engine_backward(const umd_model_cfg* cfg, const umd_step_shape* shape, const
     memset(&lnb, 0, sizeof(lnb));
     lnb.dy = P.dxf_enc; lnb.x = P.enc.x[P.enc.depth]; lnb.x_bf16 = P.enc.rbf; lnb.mean = P.enc.meanf; lnb.rstd = P.enc.rstdf;
     lnb.gamma = c.W(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.beta = c.W(UMD_P_ENC_BASE + UMD_S_NORM_B);
-    lnb.rm = P.enc.rm; lnb.dx = P.dx_enc; lnb.accumulate = 0;
+    lnb.rm = P.enc.rm; lnb.accumulate = 0;
+    if (P.dxb_enc) { lnb.dx = P.dxb_enc; lnb.dxout_bf16 = 1; } else { lnb.dx = P.dx_enc; }
+    lnb.dx_in = lnb.dx;
     lnb.dgamma = c.G(UMD_P_ENC_BASE + UMD_S_NORM_S); lnb.dbeta = c.G(UMD_P_ENC_BASE + UMD_S_NORM_B);
     gate_stage_mlp(c, P.enc, P.enc.depth - 1, lnb);
     UMD_TRY(ln_mod_bwd(lnb, D, B, false, st));
   }
-  UMD_TRY(stack_backward(c, P.enc, P.dx_enc, cb, cb_user, 1));
+  UMD_TRY(stack_backward(c, P.enc, P.dx_enc, P.dxb_enc, cb, cb_user, 1));
   UMD_TRY(embed_bwd(embed_args(c, *io), B, P.dx_enc, c.G(UMD_P_EMBED_W), c.G(UMD_P_EMBED_B), c.G(UMD_P_POS),
                     c.G(UMD_P_CLS), st));
   // ---- conditioning path backward (ae.py:121-124, embeddings.py:50-59)
@@ -930,7 +948,7 @@ extern "C" int umd_ln_modulate_bwd(const void* dy, int dy_is_bf16, const float* 
   LnBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.dy = dy; a.x = x; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.scale = scale; a.ldmod = ldmod;
-  a.rm = ragged_rowmap(n0, s0, n1, s1); a.dx = dx; a.accumulate = accumulate; a.dshift = dshift; a.dscale = dscale;
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.dx = dx; a.dx_in = dx; a.accumulate = accumulate; a.dshift = dshift; a.dscale = dscale;
   a.ldd = ldd; a.dgamma = dgamma; a.dbeta = dbeta;
   return ln_mod_bwd(a, D, n0 + n1, dy_is_bf16 != 0, static_cast<cudaStream_t>(stream));
 }
@@ -943,7 +961,7 @@ extern "C" int umd_ln_modulate_bwd_gated(const void* dy, int dy_is_bf16, const f
   LnBwdArgs a;
   memset(&a, 0, sizeof(a));
   a.dy = dy; a.x = x; a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.scale = scale; a.ldmod = ldmod;
-  a.rm = ragged_rowmap(n0, s0, n1, s1); a.dx = dx; a.accumulate = accumulate; a.dshift = dshift; a.dscale = dscale;
+  a.rm = ragged_rowmap(n0, s0, n1, s1); a.dx = dx; a.dx_in = dx; a.accumulate = accumulate; a.dshift = dshift; a.dscale = dscale;
   a.ldd = ldd; a.dgamma = dgamma; a.dbeta = dbeta;
   a.g_dz = static_cast<__nv_bfloat16*>(dz_bf16); a.g_z = static_cast<const __nv_bfloat16*>(z_bf16); a.g_gate = gate;
   a.g_ldgate = ldgate; a.g_dgate = dgate; a.g_lddgate = lddgate; a.g_dbias = dbias;

@@ -46,7 +46,9 @@ struct LnBwdArgs {
   const float* scale;      // per-sample (1+scale) factor or null
   long long ldmod;
   RowMap rm;
-  float* dx;               // [rows_in, D] fp32; += if accumulate else =
+  void* dx;                // [rows_in, D] gradient of the residual stream (fp32, or bf16 when dxout_bf16): written
+  const void* dx_in;       // with accumulate: the running gradient that is added (may be dx itself: in place); dxin_bf16
+  int dxin_bf16, dxout_bf16;
   int accumulate;
   float* dshift;           // per-sample outputs (stride ldd) or null
   float* dscale;

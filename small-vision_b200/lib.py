@@ -157,7 +157,7 @@ def model_cfg_struct(cfg):
   m.num_classes = cfg.num_classes or 0
   m.adaln = int(cfg.adaln)
   m.flip_final_conv = int(cfg.flip_final_conv)
-  m.residual_bf16 = int(cfg.residual_dtype == "bfloat16")
+  m.residual_bf16 = (2 if cfg.grad_stream_dtype == "bfloat16" else 1) if cfg.residual_dtype == "bfloat16" else 0
   return m
 
 

@@ -37,6 +37,18 @@ def test_full_depth_umd_b4_step_bf16_residual_stream_matches_cpu_oracle():
   print("umd_b4 full depth, bf16 residual stream:", rep)
 
 
+@pytest.mark.parametrize("case", ["umd_b4", "mae_b4", "dit_b4", "latent_umd_l2"])
+def test_full_depth_step_bf16_residual_and_gradient_streams_match_cpu_oracle(case):
+  """residual_dtype = grad_stream_dtype = "bfloat16": forward AND backward streams of the reference's bf16 flow."""
+  kw = {"umd_b4": dict(variant="B/4", batch=8, adaln=True, seed=3),
+        "mae_b4": dict(variant="B/4", batch=8, adaln=False, seed=4),
+        "dit_b4": dict(variant="B/4", batch=6, adaln=True, num_classes=1000, use_labels=True, mask_ratio=0.0, no_noise_prob=0.0,
+                       seed=5, ema_decay=1e-4),
+        "latent_umd_l2": dict(variant="L/2", batch=4, adaln=True, seed=6, img_size=32, channels=4, beta_schedule="linear")}[case]
+  rep = U.run_step_parity(steps=1, residual_dtype="bfloat16", grad_stream_dtype="bfloat16", **kw)
+  print(f"{case} full depth, bf16 residual + gradient streams:", rep)
+
+
 def test_full_depth_mae_b4_step_bf16_residual_stream_matches_cpu_oracle():
   rep = U.run_step_parity(variant="B/4", batch=8, adaln=False, steps=1, seed=4, residual_dtype="bfloat16")
   print("mae_b4 full depth, bf16 residual stream:", rep)
@@ -68,7 +80,7 @@ def test_full_depth_latent_umd_l2_step_matches_cpu_oracle():
 # ---------------------------------------------------------------------------------------------------------------
 # bench shapes, GPU fp32 secondary oracle
 # ---------------------------------------------------------------------------------------------------------------
-def bench_state_and_batch(workload, per_gpu=None, device=DEV, residual_dtype="float32"):
+def bench_state_and_batch(workload, per_gpu=None, device=DEV, residual_dtype="float32", grad_stream_dtype="float32"):
   """Exactly what bench.py builds on rank 0 for `workload`: model, state (seed 0, non-zero adaLN), update_fn and the
   first synthetic batch (generator seed 1 + rank)."""
   import bench
@@ -77,7 +89,7 @@ def bench_state_and_batch(workload, per_gpu=None, device=DEV, residual_dtype="fl
   from small_vision_b200.train import create_train_state, make_update_fn
   mkw, tkw, n = bench.WORKLOADS[workload]
   n = per_gpu or n
-  model = Model(**mkw, residual_dtype=residual_dtype)
+  model = Model(**mkw, residual_dtype=residual_dtype, grad_stream_dtype=grad_stream_dtype)
   tcfg = TrainConfig(batch_size=n, **tkw)
   state = create_train_state(model, tcfg, seed=0, device=device, nonzero_adaln=True)
   state["opt"]["count"] = 10
@@ -129,10 +141,11 @@ def gpu_fp32_oracle_loss_and_grads(params_tree, ocfg, tkw, gd, batch, rand, n_ch
     torch.set_float32_matmul_precision(old[2])
 
 
-def bench_shape_parity(workload, n_chunks, per_gpu=None, residual_dtype="float32"):
+def bench_shape_parity(workload, n_chunks, per_gpu=None, residual_dtype="float32", grad_stream_dtype="float32"):
   from small_vision_b200.diffusion import create_gaussian_diffusion
   from small_vision_b200.params import tree_from_arena
-  model, mkw, tkw, state, fn, batch = bench_state_and_batch(workload, per_gpu, residual_dtype=residual_dtype)
+  model, mkw, tkw, state, fn, batch = bench_state_and_batch(workload, per_gpu, residual_dtype=residual_dtype,
+                                                            grad_stream_dtype=grad_stream_dtype)
   B = batch["image"].shape[0]
   rand = fn.draw_step_randoms(state, B, torch.device(DEV), rank=0)
   gb = dict(batch)
@@ -162,6 +175,11 @@ def test_bench_shape_umd_b4_matches_gpu_fp32_oracle():
 
 def test_bench_shape_umd_b4_bf16_residual_stream_matches_gpu_fp32_oracle():
   bench_shape_parity("umd_b4", n_chunks=8, residual_dtype="bfloat16")
+
+
+@pytest.mark.parametrize("workload,chunks", [("umd_b4", 8), ("dit_b4", 8), ("latent_umd_l2", 4)])
+def test_bench_shape_bf16_residual_and_gradient_streams_match_gpu_fp32_oracle(workload, chunks):
+  bench_shape_parity(workload, n_chunks=chunks, residual_dtype="bfloat16", grad_stream_dtype="bfloat16")
 
 
 def test_bench_shape_mae_b4_matches_gpu_fp32_oracle():
@@ -196,13 +214,14 @@ def test_bench_first_loss_golden_is_current():
 # ---------------------------------------------------------------------------------------------------------------
 # N-step trajectory (App. G: "after N optimiser steps on fixed data loss curves overlap within 2 %")
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("residual_dtype", ["float32", "bfloat16"])
+@pytest.mark.parametrize("residual_dtype", ["float32", "bfloat16", "bfloat16+grad"])
 def test_trajectory_20_steps_umd_s4_matches_cpu_oracle(residual_dtype):
   from small_vision_b200.config import TrainConfig
   from small_vision_b200.diffusion import create_gaussian_diffusion
   from small_vision_b200.train import create_train_state, make_update_fn
   steps, B = 20, 8
-  model, ocfg = U.make_models("S/4", adaln=True, residual_dtype=residual_dtype)
+  model, ocfg = U.make_models("S/4", adaln=True, residual_dtype=residual_dtype.split("+")[0],
+                              grad_stream_dtype="bfloat16" if residual_dtype.endswith("+grad") else "float32")
   # a rate at which 20 steps visibly move the loss, warm-up included (lr(0) = 0 is the optax convention)
   tcfg = TrainConfig(batch_size=B, total_steps=200, warmup_steps=4, peak_lr=1e-3 * 256 / B)
   params = U.perturb_init(model, 11, DEV)

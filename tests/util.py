@@ -156,14 +156,15 @@ def _compare_updated(ours, ref, init, what):
 def run_step_parity(*, variant="S/4", batch=8, adaln=True, num_classes=None, use_labels=False, mask_ratio=0.375,
                     mask_ratio_no_noise=0.75, no_noise_prob=0.5, steps=2, seed=0, device="cuda", depth=None,
                     dec_depth=None, ema_decay=None, img_size=64, channels=3, beta_schedule="cosine",
-                    check_grads=True, residual_dtype="float32"):
+                    check_grads=True, residual_dtype="float32", grad_stream_dtype="float32"):
   """Runs `steps` update_fn steps in the engine and in the oracle from identical state and draws and asserts
   App. G tolerances on loss, gradients (first step), grad-norm, l2 measurements and updated parameters."""
   from small_vision_b200.config import TrainConfig
   from small_vision_b200.train import create_train_state, make_update_fn
   from small_vision_b200.diffusion import create_gaussian_diffusion
   model, ocfg = make_models(variant, adaln=adaln, num_classes=num_classes, depth=depth, dec_depth=dec_depth,
-                            img_size=img_size, channels=channels, residual_dtype=residual_dtype)
+                            img_size=img_size, channels=channels, residual_dtype=residual_dtype,
+                            grad_stream_dtype=grad_stream_dtype)
   tcfg = TrainConfig(batch_size=batch, no_noise_prob=no_noise_prob, mask_ratio=mask_ratio,
                      mask_ratio_no_noise=mask_ratio_no_noise, use_labels=use_labels, total_steps=1000, warmup_steps=0,
                      peak_lr=2e-3, ema_decay=ema_decay, beta_schedule=beta_schedule,
