@@ -556,6 +556,7 @@ struct BwdParams {
   int lse_bulk;  // the sample's [S][H] lse block is 16-byte aligned: fetch it with one bulk copy
   int ahead;     // L2 prefetch of this CTA's next item on / off
   int nitems;    // (sample, head) pairs of the segment
+  int pingpong;  // two softmax warp groups, one per 64-query half of a block (see the softmax section)
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py): CTA 0 records clock64() at its sync points
   float scale, scale_log2;
@@ -653,8 +654,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar_s[i], 1);
-      mbar_init(&bar_sfree[i], AT_BWD_SM);
-      mbar_init(&bar_p[i], AT_BWD_SM);
+      mbar_init(&bar_sfree[i], p.pingpong ? AT_BWD_SM / 2 : AT_BWD_SM);   // one warp group per half-step with pingpong
+      mbar_init(&bar_p[i], p.pingpong ? AT_BWD_SM / 2 : AT_BWD_SM);
     }
     mbar_init(bar_tfree, 1);
     mbar_init(bar_acc, 1);
@@ -855,52 +856,74 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     if (p.ntail > 0) bar_arrive_named(3, AT_BWD_SM + AT_TAIL_THREADS);   // sLse / sDelta are complete
     TL(4, 1);
     bool store_pending = false;
+    // Ping-pong: the 16 softmax warps form two groups of 8 (two per TMEM lane quadrant); group g owns the 64-query half
+    // hh = g of every block and walks over its 32 columns per row in two chunks of 16.  In lockstep (all 16 warps on
+    // every half) each thread paid the barrier round trip score-ready -> buffer-free -> tile-free -> fence -> P-ready
+    // twice per block and the MUFU, FP32 and shared-memory-store phases of all warps coincided; with two groups a thread
+    // pays it once per block and one group's exponentials overlap the other group's stores.
+    const bool pp = p.pingpong != 0;
+    const int grp = hf >> 1, sub = hf & 1;
     for (int j = 0; j < nt; ++j, ++jj) {
+      if (pp && store_pending) {   // dK_j / dV_j of the previous key tile were staged in the P^T tile
+        if (tid == 0) bulk_wait_read<0>();
+        bar_softmax_n<AT_BWD_SM>();
+        store_pending = false;
+      }
       for (int i = 0; i < nt; ++i) {
         const int nq = min(128, SPm - 128 * i);
         const int nh = (nq + 63) >> 6;
         for (int hh = 0; hh < nh; ++hh, ++step) {
+          if (pp && hh != grp) continue;
           const int b = step % nbuf, u = step / nbuf;
           mbar_wait(&bar_s[b], u & 1);
           tc_fence_after();
           TL(5, step);
-          uint32_t sv[16], dv[16];
-          tmem_ld_32x16(t_lane + b * 128 + 16 * hf, sv);
-          tmem_ld_32x16(t_lane + b * 128 + 64 + 16 * hf, dv);
-          tmem_ld_wait_dep16(sv);
-          tmem_ld_wait_dep16(dv);
-          tc_fence_before();
-          mbar_arrive(&bar_sfree[b]);
-          TL(6, step);
-          if (hh == 0 && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
-          if (store_pending) {   // dK_j / dV_j of the previous key tile were staged in the P^T tile
-            if (tid == 0) bulk_wait_read<0>();
-            bar_softmax_n<AT_BWD_SM>();
-            store_pending = false;
-          }
-          TL(7, step);
-          // No masking: query columns >= S have Q = dO = 0 (TMA zero fill), lse = delta = 0, hence P = 1 against a zero
-          // dO row and dS = 0; key rows >= S only reach dK / dV rows that the TMA stores clip, and enter dQ against
-          // zero-filled K rows (rows >= SP are never read by the dQ MMA).
-          const int q0 = i * 128 + hh * 64 + 16 * hf;
           const uint32_t rowP = pt_row + hh * AT_SLAB, rowS = st_row + hh * AT_SLAB;
-#pragma unroll
-          for (int c = 0; c < 16; c += 8) {
-            float pe[8], de[8];
-            const float4 la = *reinterpret_cast<const float4*>(&sLse[q0 + c]);
-            const float4 lb = *reinterpret_cast<const float4*>(&sLse[q0 + c + 4]);
-            const float4 da = *reinterpret_cast<const float4*>(&sDelta[q0 + c]);
-            const float4 db = *reinterpret_cast<const float4*>(&sDelta[q0 + c + 4]);
-            const float l2[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
-            const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              pe[e] = ex2(fmaf(__uint_as_float(sv[c + e]), sl2, -l2[e]));
-              de[e] = pe[e] * (__uint_as_float(dv[c + e]) - dl[e]);
+          const int nchunk = pp ? 2 : 1;
+#pragma unroll 1
+          for (int cc = 0; cc < nchunk; ++cc) {
+            const int hfc = pp ? 2 * sub + cc : hf;   // which 16 of the 64 query columns of this half
+            uint32_t sv[16], dv[16];
+            tmem_ld_32x16(t_lane + b * 128 + 16 * hfc, sv);
+            tmem_ld_32x16(t_lane + b * 128 + 64 + 16 * hfc, dv);
+            tmem_ld_wait_dep16(sv);
+            tmem_ld_wait_dep16(dv);
+            if (cc == nchunk - 1) {
+              tc_fence_before();
+              mbar_arrive(&bar_sfree[b]);
             }
-            const uint32_t off = ((2 * hf + (c >> 3)) ^ r7) << 4;
-            st_shared_v4(rowP + off, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
-            st_shared_v4(rowS + off, pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7]));
+            if (cc == 0) {
+              TL(6, step);
+              if ((pp || hh == 0) && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
+              if (!pp && store_pending) {   // dK_j / dV_j of the previous key tile were staged in the P^T tile
+                if (tid == 0) bulk_wait_read<0>();
+                bar_softmax_n<AT_BWD_SM>();
+                store_pending = false;
+              }
+              TL(7, step);
+            }
+            // No masking: query columns >= S have Q = dO = 0 (TMA zero fill), lse = delta = 0, hence P = 1 against a zero
+            // dO row and dS = 0; key rows >= S only reach dK / dV rows that the TMA stores clip, and enter dQ against
+            // zero-filled K rows (rows >= SP are never read by the dQ MMA).
+            const int q0 = i * 128 + hh * 64 + 16 * hfc;
+#pragma unroll
+            for (int c = 0; c < 16; c += 8) {
+              float pe[8], de[8];
+              const float4 la = *reinterpret_cast<const float4*>(&sLse[q0 + c]);
+              const float4 lb = *reinterpret_cast<const float4*>(&sLse[q0 + c + 4]);
+              const float4 da = *reinterpret_cast<const float4*>(&sDelta[q0 + c]);
+              const float4 db = *reinterpret_cast<const float4*>(&sDelta[q0 + c + 4]);
+              const float l2[8] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
+              const float dl[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                pe[e] = ex2(fmaf(__uint_as_float(sv[c + e]), sl2, -l2[e]));
+                de[e] = pe[e] * (__uint_as_float(dv[c + e]) - dl[e]);
+              }
+              const uint32_t off = ((2 * hfc + (c >> 3)) ^ r7) << 4;
+              st_shared_v4(rowP + off, pack_bf16x2(pe[0], pe[1]), pack_bf16x2(pe[2], pe[3]), pack_bf16x2(pe[4], pe[5]), pack_bf16x2(pe[6], pe[7]));
+              st_shared_v4(rowS + off, pack_bf16x2(de[0], de[1]), pack_bf16x2(de[2], de[3]), pack_bf16x2(de[4], de[5]), pack_bf16x2(de[6], de[7]));
+            }
           }
           TL(10, 2 + step);
           fence_proxy_async();
@@ -1251,6 +1274,9 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     if (pf < 0) { const char* e = getenv("UMD_ATTN_L2PF"); pf = e ? atoi(e) : 1; }
     p.ahead = pf;
     p.nitems = n * a.H;
+    static int pingpong = -1;
+    if (pingpong < 0) { const char* e = getenv("UMD_ATTN_PINGPONG"); pingpong = e ? atoi(e) : 1; }
+    p.pingpong = pingpong;
     int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 256 + 1024;   // + 3 KB of static shared memory
     if (p.ntail > 0) smem += (4 * AT_TAIL * p.SP + 9 * 64) * 4;
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
