@@ -557,6 +557,8 @@ struct BwdParams {
   int ahead;     // L2 prefetch of this CTA's next item on / off
   int nitems;    // (sample, head) pairs of the segment
   int pingpong;  // two softmax warp groups, one per 64-query half of a block (see the softmax section)
+  int ntile;     // P^T / dS^T tile pairs in shared memory (2 when they fit: the softmax of block n + 1 then overlaps the
+                 // accumulation MMAs of block n instead of waiting for them)
   int tl_cta;
   long long* tl;  // optional timeline buffer (tools/attn_timeline.py): CTA 0 records clock64() at its sync points
   float scale, scale_log2;
@@ -585,14 +587,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
   // never alias them and can hoist their loads
   __shared__ __align__(16) float sLse[AT_STAT_N];     // lse * log2e
   __shared__ __align__(16) float sDelta[AT_STAT_N];   // rowsum(dO * O)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + 2 * AT_SLAB);
+  // (a second P^T / dS^T pair follows when p.ntile == 2; staging for the epilogues always uses the first)
+  constexpr uint32_t TILE_BYTES = 4 * AT_SLAB;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdSt + 2 * AT_SLAB + (p.ntile - 1) * TILE_BYTES);
   uint64_t* bar_ld = bars + 0;      // Q, K, V have landed (the last of the two load groups)
   uint64_t* bar_ld0 = bars + 11;    // dO, O and the lse block have landed: delta can be formed while Q, K, V stream in
   uint64_t* bar_done = bars + 12;   // the softmax warps have finished the item (its operands, tiles and accumulators are free)
   uint64_t* bar_s = bars + 1;       // [2]
   uint64_t* bar_sfree = bars + 3;   // [2]
   uint64_t* bar_p = bars + 5;       // [2] one per 64-query half
-  uint64_t* bar_tfree = bars + 7;
+  uint64_t* bar_tfree0 = bars + 7;   // tile pair t is free again (its accumulation MMAs have completed): t = 0 / 1
+  uint64_t* bar_tfree1 = bars + 13;
+  const int ntile = p.ntile;
   uint64_t* bar_acc = bars + 8;
   uint64_t* bar_accfree = bars + 9;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
@@ -657,7 +663,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
       mbar_init(&bar_sfree[i], p.pingpong ? AT_BWD_SM / 2 : AT_BWD_SM);   // one warp group per half-step with pingpong
       mbar_init(&bar_p[i], p.pingpong ? AT_BWD_SM / 2 : AT_BWD_SM);
     }
-    mbar_init(bar_tfree, 1);
+    mbar_init(bar_tfree0, 1);
+    mbar_init(bar_tfree1, 1);
     mbar_init(bar_acc, 1);
     mbar_init(bar_accfree, AT_BWD_SM);
     mbar_init(bar_done, AT_BWD_SM);
@@ -694,6 +701,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
     int jj = 0;            // key tiles finished so far, over all items
     uint32_t cnt_p[2] = {0, 0};
     int kit = 0;
+    int gblk = 0;          // blocks finished so far, over all items (selects the P^T / dS^T tile pair)
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++kit) {
     mbar_wait(bar_ld0, kit & 1);
     mbar_wait(bar_ld, kit & 1);
@@ -754,6 +762,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
         tc_fence_after();
       }
       const int kq = nq >> 4, kkv = nkv >> 4;
+      const int tsel = gblk % ntile;
+      const uint64_t toff = static_cast<uint64_t>(tsel) * (TILE_BYTES / 16);
+      ++gblk;
       if (elect_one()) {
       // (fully unrolled with constant descriptor increments: the rolled loops cost ~60 cycles of address arithmetic
       // per MMA, 1.5 k cycles per block on the critical path between P^T / dS^T and the next block's tiles)
@@ -763,7 +774,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           if (kk < kq)
-            umma_f16_ss(d0, pt_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
+            umma_f16_ss(d0, pt_k + toff + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
                         bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
       }
       {  // dK_j += dS^T Q_i
@@ -772,7 +783,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           if (kk < kq)
-            umma_f16_ss(d0, st_k + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
+            umma_f16_ss(d0, st_k + toff + static_cast<uint64_t>((kk >> 2) * (AT_SLAB / 16) + (kk & 3) * 2),
                         bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_kt, (i > 0 || kk > 0) ? 1u : 0u);
       }
       {  // dQ_i += dS K_j   (dS^T tile read as an MN-major A operand)
@@ -781,10 +792,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           if (kk < kkv)
-            umma_f16_ss(d0, st_mn + static_cast<uint64_t>(kk * 16 * ROW16), bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_mn,
+            umma_f16_ss(d0, st_mn + toff + static_cast<uint64_t>(kk * 16 * ROW16), bb + static_cast<uint64_t>(kk * 16 * ROW16), idesc_mn,
                         (j > 0 || kk > 0) ? 1u : 0u);
       }
-      umma_commit(bar_tfree);
+      umma_commit(tsel ? bar_tfree1 : bar_tfree0);
       if (i == nt - 1) umma_commit(bar_acc);
       }
       if (i == nt - 1) ++jj;
@@ -878,7 +889,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
           mbar_wait(&bar_s[b], u & 1);
           tc_fence_after();
           TL(5, step);
-          const uint32_t rowP = pt_row + hh * AT_SLAB, rowS = st_row + hh * AT_SLAB;
+          const int tsel = blk % ntile, tuse = blk / ntile;   // tile pair of this block and how often it has been used
+          const uint32_t rowP = pt_row + tsel * TILE_BYTES + hh * AT_SLAB, rowS = st_row + tsel * TILE_BYTES + hh * AT_SLAB;
           const int nchunk = pp ? 2 : 1;
 #pragma unroll 1
           for (int cc = 0; cc < nchunk; ++cc) {
@@ -894,7 +906,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tq128, const __grid_const
             }
             if (cc == 0) {
               TL(6, step);
-              if ((pp || hh == 0) && blk > 0) mbar_wait(bar_tfree, (blk - 1) & 1);
+              if ((pp || hh == 0) && tuse > 0) mbar_wait(tsel ? bar_tfree1 : bar_tfree0, (tuse - 1) & 1);
               if (!pp && store_pending) {   // dK_j / dV_j of the previous key tile were staged in the P^T tile
                 if (tid == 0) bulk_wait_read<0>();
                 bar_softmax_n<AT_BWD_SM>();
@@ -1276,9 +1288,15 @@ int attention_bwd_tc(const AttnBwdArgs& a, cudaStream_t st) {
     p.nitems = n * a.H;
     static int pingpong = -1;
     if (pingpong < 0) { const char* e = getenv("UMD_ATTN_PINGPONG"); pingpong = e ? atoi(e) : 1; }
-    p.pingpong = pingpong;
+    // (with one TMEM score buffer the two groups would have to share one score-ready barrier and skip each other's
+    // phases, which a parity wait cannot express: lockstep there)
+    p.pingpong = (pingpong && p.nbuf == 2) ? 1 : 0;
+    static int tiles2 = -1;
+    if (tiles2 < 0) { const char* e = getenv("UMD_ATTN_BWD_TILES"); tiles2 = e ? atoi(e) : 2; }
     int smem = 4 * p.SP * AT_ROW + 4 * AT_SLAB + 256 + 1024;   // + 3 KB of static shared memory
     if (p.ntail > 0) smem += (4 * AT_TAIL * p.SP + 9 * 64) * 4;
+    p.ntile = (tiles2 >= 2 && smem + 4 * AT_SLAB <= 220 * 1024) ? 2 : 1;
+    smem += (p.ntile - 1) * 4 * AT_SLAB;
     if (smem < 120 * 1024) smem = 120 * 1024;  // the kernel owns all 512 TMEM columns: one CTA per SM
     const int grid = p.nitems < sm_count() ? p.nitems : sm_count();
     attn_bwd_tc_kernel<<<grid, AT_BWD_THREADS, smem, st>>>(tq128, tq16, td128, td16, tmdq, to128, to16, p);
