@@ -677,13 +677,14 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   if (col >= N) return;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int r = r0 + rl;
-  // four independent 16-byte loads in flight per thread
-  for (; r + 24 < r1; r += 32) {
-    uint4 v[4];
+  // eight independent 16-byte loads in flight per thread: beside a persistent GEMM CTA only one of these CTAs fits on an
+  // SM, so the bytes in flight per thread are what keeps the pass short
+  for (; r + 56 < r1; r += 64) {
+    uint4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * u) * ld + col);
+    for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 8 * u) * ld + col);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       acc[0] += bf16_lo(v[u].x); acc[1] += bf16_hi(v[u].x); acc[2] += bf16_lo(v[u].y); acc[3] += bf16_hi(v[u].y);
       acc[4] += bf16_lo(v[u].z); acc[5] += bf16_hi(v[u].z); acc[6] += bf16_lo(v[u].w); acc[7] += bf16_hi(v[u].w);
     }
