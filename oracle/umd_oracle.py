@@ -4,7 +4,7 @@ __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs; 
 product path (small-vision_b200/) never imports it.
 
 PARITY STATUS: pinned to the reference's own source for the model, diffusion and loss;
-unpinned for the optimiser.  The reference (philippe-eecs/small-vision) is JAX/Flax/Optax
+the optimiser restates optax's published algorithm (library release unpinned, see below).  The reference (philippe-eecs/small-vision) is JAX/Flax/Optax
 code; none of the three can be installed in this image (no wheels, no network) and the
 repository ships no golden vectors or tests for this path.
   * Model forward, masking, conditioning, classifier-free guidance, q_sample, the DDIM
@@ -23,10 +23,21 @@ repository ships no golden vectors or tests for this path (SURVEY.md F2, F5, §8
   * Few-shot probe, sharding declarations, checkpoint naming, value_range and the recipe
     wiring (step counts, schedule / AdamW arguments, decay mask) are pinned the same way
     (tests/golden/refshim/README.md lists every fixture and the reference code behind it).
-  * Optimiser (optax 0.2.x: clip_by_global_norm, adamw with bf16 mu, masked decay,
-    warmup_cosine_decay_schedule; train_ae.py:135-151): restated from optax's published
-    semantics and checked against torch.optim.AdamW and closed forms —
-    PARITY UNPINNED for this part.
+  * Optimiser (optax: clip_by_global_norm, adamw with bf16 mu, masked decay,
+    warmup_cosine_decay_schedule; train_ae.py:135-151): optax is absent from /root/reference
+    and from this image, and requirements.txt:5 pins no version.  optimizer_update restates
+    optax/_src/clipping.py::clip_by_global_norm (select(norm < c, g, g / norm * c)),
+    optax/_src/transform.py::{scale_by_adam (update_moment, bias_correction, the mu_dtype cast
+    AFTER the update is formed), add_decayed_weights, scale_by_schedule (step size from the
+    pre-increment count)}, optax/_src/schedule.py::warmup_cosine_decay_schedule
+    (join_schedules(linear_schedule, cosine_decay_schedule)) and optax/_src/update.py::
+    {apply_updates, incremental_update} as published in optax 0.1.7 - 0.2.3 (their arithmetic
+    is the same across those releases).  tests/test_optimizer_pins_cpu.py checks it against a
+    second, transformation-by-transformation restatement in numpy (bf16 rounding by bit
+    manipulation), closed forms, torch.optim.AdamW and the reference's own decay mask —
+    PARITY UNPINNED only with respect to the library release itself.
+  * The same code runs on the GPU (fp32, TF32 off) as the secondary oracle for full-size
+    shapes (tests/test_fullsize_gpu.py): every tensor it creates follows its inputs' device.
 
 Each function cites the reference lines it follows (paths relative to /root/reference).
 Every random quantity the reference draws inside the step (mask noise, t, noise, label
