@@ -66,7 +66,8 @@ def main(csv_path, log_path, out_path):
   try:
     commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
   except Exception:
-    commit = "?"
+    commit = ""
+  commit = commit or "(stamped when the table is copied into profiles/: the GPU box has no .git)"
   out = {"commit": commit, "source": f"{csv_path} + {log_path} (one step of tools/step_once.py under ncu; cold-cache, serialised launches)",
          "fwd_dgrad_launches_per_step": nfd,
          "fwd_dgrad_traffic_bytes_per_launch": sum(e["dram_bytes_per_launch"] * e["launches"] for e in fd) / nfd,
