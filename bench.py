@@ -152,6 +152,35 @@ def attention_bytes_per_step(cfg, tkw, per_gpu):
   return {"attention_fwd": rows * (4 * D * 2 + H * 4), "attention_bwd": rows * (7 * D * 2 + 2 * H * 4)}
 
 
+class Watchdog:
+  """Fail fast instead of hanging: if the benchmark makes no progress for `limit` seconds (a collective that never
+  completes, a rendezvous that never forms) every thread's stack goes to stderr and the process exits with code 3."""
+
+  def __init__(self, limit=600.0):
+    import threading
+    self.limit = limit
+    self.phase = "start"
+    self.t = time.time()
+    self.done = False
+    threading.Thread(target=self._run, daemon=True).start()
+
+  def beat(self, phase=None):
+    self.t = time.time()
+    if phase:
+      self.phase = phase
+
+  def _run(self):
+    import faulthandler
+    while not self.done:
+      time.sleep(5.0)
+      if time.time() - self.t > self.limit:
+        sys.stderr.write(f"bench.py watchdog: no progress for {self.limit:.0f} s in phase '{self.phase}' "
+                         f"(rank {os.environ.get('RANK', '0')}); stacks follow\n")
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        os._exit(3)
+
+
 def load_peaks():
   p = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(p):
@@ -321,6 +350,7 @@ def main():
   world = int(os.environ.get("WORLD_SIZE", "1"))
   rank = int(os.environ.get("RANK", "0"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
+  dog = Watchdog(float(os.environ.get("UMD_BENCH_WATCHDOG_S", "600")))
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device: the UMD hot path has no CPU fallback")
   torch.cuda.set_device(local)
@@ -334,9 +364,11 @@ def main():
     saved = os.dup(1)
     os.dup2(2, 1)
     try:
+      dog.beat("init_process_group")
       dist.init_process_group("nccl", device_id=dev)
       dist.barrier()
       torch.cuda.synchronize()
+      dog.beat("process group up")
     finally:
       ctypes.CDLL(None).fflush(None)
       os.dup2(saved, 1)
@@ -368,13 +400,16 @@ def main():
     torch.cuda.synchronize()
 
   def timed(fn, steps):
+    dog.beat()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(steps):
       fn(s)
+      dog.beat()
     e1.record()
     barrier()
+    dog.beat()
     ms = e0.elapsed_time(e1)
     if world > 1:
       t = torch.tensor([ms], device=dev)
@@ -423,8 +458,11 @@ def main():
     e2e_loss[slot].copy_(meas["training_loss"].reshape(1), non_blocking=True)   # device -> host read of the loss
     e2e_ev[slot].record(cur)
 
+  dog.beat("warm-up (first step creates the umd_comm communicator)")
   for s in range(args.warmup):
     step_resident(s)
+    dog.beat()
+  dog.beat("timed steps")
   L = lib.load()
   import ctypes as Ct
   ncat = L.umd_profile_num_categories()
@@ -461,6 +499,7 @@ def main():
   if not math.isfinite(final_loss):
     raise SystemExit(f"non-finite training loss {final_loss}")
   loss_check = first_loss_check(args.workload, per_gpu, world, float(losses[0])) if rank == 0 else None
+  dog.beat("checks")
   dp = None
   if world > 1 and not args.no_dp_check:
     dp = dp_check(update_fn, state, model, lambda r: make_device_batches(cfg, per_gpu, dev, r, 1), world, rank, pg, dev)
@@ -534,9 +573,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
       line["cpu_baseline"] = cpu_baseline(args, mkw, tkw)
     print(json.dumps(line), flush=True)
+  dog.beat("shutdown")
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
+  dog.done = True
 
 
 if __name__ == "__main__":
