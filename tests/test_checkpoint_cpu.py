@@ -42,7 +42,11 @@ def test_load_params_accepts_the_three_layouts(tmp_path):
   old = K.load_params({"opt/target/" + k: v for k, v in flat.items()})         # Flax-optimizer checkpoints
   assert set(old) == set(tree)
   np.testing.assert_array_equal(old["final_conv"]["kernel"], bare["final_conv"]["kernel"])
-  with pytest.raises(NotImplementedError):
+  # anything that is not an .npz is a tensorstore-layout directory (utils.py:279-283; tests/test_checkpoint_ts_cpu.py)
+  with pytest.raises(FileNotFoundError):
     K.load_params(str(tmp_path / "tensorstore_dir"))
+  K.save_checkpoint_ts({"params": tree}, str(tmp_path / "ck"), 1)
+  ts = K.load_params(str(tmp_path / "ck"))
+  np.testing.assert_array_equal(ts["final_conv"]["kernel"], bare["final_conv"]["kernel"])
   with pytest.raises(KeyError):
     K.tree_get(bare, "Encoder/nope")
