@@ -388,6 +388,13 @@ def main():
   # start the optimiser past the lr(0) = 0 warm-up step so that every timed step really moves the parameters
   state["opt"]["count"] = 10
   update_fn = make_update_fn(model, tcfg, process_group=pg)
+  if world > 1:
+    # create the C-level NCCL communicator now, while the GPUs are idle, instead of inside the first step
+    dog.beat("umd_comm init")
+    update_fn.communicator(dev)
+    dist.barrier()
+    torch.cuda.synchronize()
+    dog.beat("umd_comm up")
 
   H, C = cfg.img_size, cfg.channels
   n_dev_batches = 4   # 4 x 25 MB of inputs; activations written per step (tens of GB) flush the 126 MB L2 anyway

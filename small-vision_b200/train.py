@@ -213,4 +213,5 @@ def make_update_fn(model: ViTAE, tcfg: TrainConfig, *, process_group=None):
   update_fn.grads = lambda: sc.grads
   update_fn.forward_backward = forward_backward
   update_fn.draw_step_randoms = draw_step_randoms
+  update_fn.communicator = communicator
   return update_fn
