@@ -42,6 +42,23 @@ WORKLOADS = {
 }
 
 
+def workload_config(workload, per_gpu, world, num_params):
+  """The `config` object of the JSON line.  Both arms print the SAME object for the same command line (the reference arm
+  times a bounded sample of this workload and says which in `cpu_baseline.sample`); what differs between the arms —
+  arithmetic type, where the step runs — is in `dtype`, `precision` and `impl`, outside `config`."""
+  mkw, tkw, _ = WORKLOADS[workload]
+  H, C = mkw["img_size"], mkw["channels"]
+  n_clean = int(per_gpu * tkw["no_noise_prob"])
+  return {"workload": f"{workload}: {mkw['variant']} {H}x{H}x{C} update_fn step, {per_gpu} img/GPU "
+                      f"({per_gpu - n_clean} noised + {n_clean} clean)",
+          "global_batch": per_gpu * world, "per_gpu_batch": per_gpu, "parallelism": f"dp{world}", "params": num_params,
+          "l2": "inputs rotate over 4 batches; each step writes > 10 GB of activations (>> 126 MB L2)"}
+
+
+def metric_name(workload):
+  return METRIC if workload == "umd_b4" else f"train images/sec ({workload})"
+
+
 def step_flops_per_image(cfg, tkw):
   """Algorithmic FLOPs of one training step per image: 3 x forward, 2MNK per GEMM,
   4 S^2 D per attention layer; no rematerialisation."""
@@ -276,11 +293,15 @@ def run_reference(args):
   ms = 1e3 * sum(times) / len(times)
   v = B / (ms / 1e3)
   sample = f"{args.steps} steps of batch {B} ({B - n_clean} noised + {n_clean} clean) after {args.warmup} warm-up, fp32, torch-CPU"
-  line = {"metric": METRIC, "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+  if args.per_gpu_batch:
+    per_gpu = args.per_gpu_batch
+  line = {"metric": metric_name(args.workload), "value": v, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
           "data": "synthetic", "impl": "reference",
-          "config": {"workload": f"{args.workload}: {mkw['variant']} {mkw['img_size']}x{mkw['img_size']} one update_fn step",
-                     "global_batch": B, "note": "CPU restatement of the reference step (oracle port; JAX is not installable here)"},
+          "config": workload_config(args.workload, per_gpu, args.gpus, model.layout.num_params),
+          "precision": "fp32 throughout (the reference's default dtype_mm), torch-CPU",
+          "note": f"CPU restatement of the reference step (oracle port; JAX is not installable here), timed on rank 0's host cores on a "
+                  f"bounded sample of the workload: batch {B} per step instead of {per_gpu} per GPU; images/sec does not depend on N",
           "cpu_baseline": {"value": v, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
           "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
           "gpu_launches": 0}
@@ -560,14 +581,11 @@ def main():
         breakdown[nm].update(bound="hbm", gbs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peaks["hbm"], 3),
                              frac_of_tensor_peak=breakdown[nm].pop("frac_of_peak"))
     line = {
-        "metric": METRIC if args.workload == "umd_b4" else f"train images/sec ({args.workload})", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args.workload), "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {mkw['variant']} {H}x{H}x{C} update_fn step, {per_gpu} img/GPU "
-                               f"({per_gpu - int(per_gpu * tkw['no_noise_prob'])} noised + {int(per_gpu * tkw['no_noise_prob'])} clean)",
-                   "global_batch": B_global, "per_gpu_batch": per_gpu, "parallelism": f"dp{world}",
-                   "params": model.layout.num_params, "l2": "inputs rotate over 4 batches; each step writes > 10 GB of activations (>> 126 MB L2)",
-                   "precision": "bf16 GEMM/attention operands, fp32 accumulate, %s residual stream, fp32 LayerNorm statistics / gradient stream / loss / AdamW (bf16 mu)" % {"float32": "fp32", "bfloat16": "bf16", "bfloat16+grad": "bf16 (forward and gradient)"}[args.residual]},
+        "config": workload_config(args.workload, per_gpu, world, model.layout.num_params),
+        "precision": "bf16 GEMM/attention operands, fp32 accumulate, %s residual stream, fp32 LayerNorm statistics / gradient stream / loss / AdamW (bf16 mu)" % {"float32": "fp32", "bfloat16": "bf16", "bfloat16+grad": "bf16 (forward and gradient)"}[args.residual],
         "step_tflops_per_gpu": fl_img * value / world / 1e12,
         "step_frac_of_bf16_peak": fl_img * value / world / 1e12 / peaks["tf_sustained"],
         "flops_per_image": fl_img, "final_loss": final_loss, "loss_check": loss_check, "dp_check": dp,

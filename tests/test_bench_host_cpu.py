@@ -50,3 +50,19 @@ def test_watchdog_stays_quiet_while_beaten():
   dog.beat()
   assert dog.phase == "phase a" and time.time() - dog.t < 5
   dog.done = True
+
+
+def test_both_arms_print_the_same_config_object():
+  """bench.py --impl reference must carry the b200 arm's `config`, `metric`, `unit` (the driver compares them): both come
+  from workload_config / metric_name, and nothing arm-specific (precision, sample size) lives inside `config`."""
+  for wl, (mkw, tkw, per_gpu) in bench.WORKLOADS.items():
+    for world in (1, 8):
+      c = bench.workload_config(wl, per_gpu, world, 123)
+      assert set(c) == {"workload", "global_batch", "per_gpu_batch", "parallelism", "params", "l2"}
+      assert c["global_batch"] == per_gpu * world and c["parallelism"] == f"dp{world}"
+      assert c["workload"].startswith(wl + ": " + mkw["variant"])
+  assert bench.metric_name("umd_b4") == bench.METRIC
+  c = bench.workload_config("umd_b4", 512, 1, 1)
+  assert "256 noised + 256 clean" in c["workload"]
+  src = open(os.path.join(bench.ROOT, "bench.py")).read()
+  assert src.count('"config": workload_config(') == 2          # one per arm, no hand-built config dict left
