@@ -229,3 +229,42 @@ def test_seed_from_rng_mixes_rank_and_stream():
   assert len(seeds) == 24
   assert seed_from_rng(torch.tensor([1, 8])) != base and seed_from_rng(5) == 5 and seed_from_rng(None) == 0
   assert all(0 <= x < 2 ** 63 for x in seeds)
+
+
+def test_ctypes_structures_have_the_headers_layout(tmp_path):
+  """Every ctypes.Structure of lib.py against the struct of the same role in include/umd_b200.h: gcc compiles a program
+  that prints sizeof and the offset of every field BY NAME (a renamed or missing field is a compile error), and the numbers
+  must equal ctypes' own.  A drifted field would otherwise shift every later pointer of umd_train_step's argument block."""
+  import ctypes as C
+  import subprocess
+  from small_vision_b200 import lib
+  pairs = [("umd_gemm_args", lib.GemmArgs), ("umd_adamw_args", lib.AdamwArgs), ("umd_model_cfg", lib.ModelCfg),
+           ("umd_step_shape", lib.StepShape), ("umd_io", lib.IO), ("umd_train_step_args", lib.TrainStepArgs)]
+  lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "umd_b200.h"', 'int main(void) {']
+  want = []
+  for cname, cls in pairs:
+    lines.append(f'  printf("%zu\\n", sizeof({cname}));')
+    want.append(C.sizeof(cls))
+    for fname, _ in cls._fields_:
+      lines.append(f'  printf("%zu\\n", offsetof({cname}, {fname}));')
+      want.append(getattr(cls, fname).offset)
+  from small_vision_b200 import params as P
+  # enumerators, again by name: leaf ids (params.py), epilogue ids and flags (lib.py)
+  enums = [("UMD_" + k, getattr(P, k)) for k in dir(P) if (k.startswith("P_") or k.startswith("S_")) and isinstance(getattr(P, k), int)]
+  enums += [("UMD_OFFSETS_LEN", P.OFFSETS_LEN), ("UMD_STEP_NO_OPTIMIZER", lib.UMD_STEP_NO_OPTIMIZER)]
+  enums += [("UMD_" + k, getattr(lib, k)) for k in dir(lib) if k.startswith("EPI_")]
+  assert len(enums) >= 19 + 5 + 20 + 2 + 7
+  for name, _ in enums:
+    lines.append(f'  printf("%d\\n", (int){name});')
+  lines += ['  return 0;', '}']
+  src = tmp_path / "layout.c"
+  src.write_text("\n".join(lines) + "\n")
+  exe = tmp_path / "layout"
+  inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+  r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], capture_output=True, text=True)
+  assert r.returncode == 0, r.stderr
+  out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+  got = [int(x) for x in out[:len(want)]]
+  assert got == want
+  got_enums = [int(x) for x in out[len(want):len(want) + len(enums)]]
+  assert got_enums == [v for _, v in enums], [(n, v, g) for (n, v), g in zip(enums, got_enums) if v != g]
